@@ -1,0 +1,313 @@
+// C-ABI of libhrfuser_b200.so (see include/hrfuser_b200.h).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "hrfuse.cuh"
+#include "mixffn.cuh"
+#include "window_attn.cuh"
+
+namespace hrf {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return HRF_ECUDA;
+}
+cudaError_t ensure_smem(const void* kern, size_t bytes) {
+  static std::mutex mu;
+  static std::map<const void*, size_t> done;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find(kern);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done[kern] = bytes;
+  return e;
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// eval-mode BatchNorm as y = x*scale + shift
+static void bn_affine(const float* const bn[4], int n, float eps, std::vector<float>& scale,
+                      std::vector<float>& shift) {
+  scale.assign(n, 1.f);
+  shift.assign(n, 0.f);
+  if (!bn) return;
+  for (int i = 0; i < n; ++i) {
+    const float s = bn[0][i] / std::sqrt(bn[3][i] + eps);
+    scale[i] = s;
+    shift[i] = bn[1][i] - bn[2][i] * s;
+  }
+}
+
+static void pack_pw(const PwLayout& L, const float* w, const float* bias, const float* const bn[4],
+                    float eps, float* blob) {
+  std::vector<float> sc, sh;
+  bn_affine(bn, L.Cout, eps, sc, sh);
+  std::memset(blob, 0, sizeof(float) * L.total);
+  for (int n = 0; n < L.Cout; ++n) {
+    for (int k = 0; k < L.Cin; ++k) blob[L.o_w + (size_t)k * L.Cout + n] = w[(size_t)n * L.Cin + k] * sc[n];
+    blob[L.o_b + n] = (bias ? bias[n] : 0.f) * sc[n] + sh[n];
+  }
+}
+
+}  // namespace hrf
+
+using namespace hrf;
+
+extern "C" {
+
+int hrf_abi_version(void) { return HRF_ABI_VERSION; }
+const char* hrf_last_error(void) { return g_err; }
+unsigned long long hrf_launch_count(void) { return g_launches.load(); }
+
+int hrf_device_check(void) {
+  int dev = 0;
+  HRF_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  HRF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  HRF_REQUIRE(prop.major == 10, HRF_EDEVICE, "device %s is sm_%d%d; this library is sm_100a only",
+              prop.name, prop.major, prop.minor);
+  return HRF_OK;
+}
+
+// ------------------------------------------------------------------ attention
+static int check_attn(const HrfAttnDesc* d) {
+  HRF_REQUIRE(d != nullptr, HRF_EINVAL, "attn: null descriptor");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->heads > 0, HRF_EINVAL,
+              "attn: non-positive dimension");
+  HRF_REQUIRE(d->C % d->heads == 0, HRF_EINVAL, "attn: C=%d not divisible by heads=%d", d->C, d->heads);
+  HRF_REQUIRE(d->C % 2 == 0, HRF_EUNSUPPORTED, "attn: C=%d must be even", d->C);
+  HRF_REQUIRE(d->win >= 1 && d->win * d->win <= 256, HRF_EUNSUPPORTED, "attn: window %d", d->win);
+  HRF_REQUIRE(d->n_kv >= 0 && d->n_kv <= 8, HRF_EINVAL, "attn: n_kv=%d", d->n_kv);
+  HRF_REQUIRE(d->dtype == HRF_F32 || d->dtype == HRF_BF16, HRF_EINVAL, "attn: dtype");
+  const AttnLayout L(d->C, d->heads, d->win);
+  HRF_REQUIRE(L.ldx <= 256, HRF_EUNSUPPORTED, "attn: C=%d too wide for the fused kernel", d->C);
+  const size_t smem = L.smem_floats(d->n_kv > 0, kAttnThreads / 32) * sizeof(float);
+  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED,
+              "attn: C=%d heads=%d win=%d needs %zu B shared memory (max 232448)", d->C, d->heads,
+              d->win, smem);
+  return HRF_OK;
+}
+
+size_t hrf_attn_blob_floats(const HrfAttnDesc* d) {
+  if (!d || d->heads <= 0 || d->C <= 0) return 0;
+  return (size_t)AttnLayout(d->C, d->heads, d->win).total;
+}
+
+int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b,
+                  const float* ln_kv_w, const float* ln_kv_b, const float* wq, const float* bq,
+                  const float* wk, const float* bk, const float* wv, const float* bv,
+                  const float* wo, const float* bo, const float* rpb_table, float* blob) {
+  int rc = check_attn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(ln_q_w && ln_q_b && ln_kv_w && ln_kv_b && wq && wk && wv && wo && blob, HRF_EINVAL,
+              "attn_pack: null pointer");
+  const AttnLayout L(d->C, d->heads, d->win);
+  const int C = L.C;
+  std::memset(blob, 0, sizeof(float) * L.total);
+  const float scale = 1.0f / std::sqrt((float)L.hd);
+  for (int c = 0; c < C; ++c) {
+    blob[L.o_lnq_w + c] = ln_q_w[c];
+    blob[L.o_lnq_b + c] = ln_q_b[c];
+    blob[L.o_lnkv_w + c] = ln_kv_w[c];
+    blob[L.o_lnkv_b + c] = ln_kv_b[c];
+    blob[L.o_bq + c] = (bq ? bq[c] : 0.f) * scale;
+    blob[L.o_bk + c] = bk ? bk[c] : 0.f;
+    blob[L.o_bv + c] = bv ? bv[c] : 0.f;
+    blob[L.o_bo + c] = bo ? bo[c] : 0.f;
+  }
+  for (int n = 0; n < C; ++n)
+    for (int k = 0; k < C; ++k) {
+      blob[L.o_wq + (size_t)k * C + n] = wq[(size_t)n * C + k] * scale;
+      blob[L.o_wk + (size_t)k * C + n] = wk[(size_t)n * C + k];
+      blob[L.o_wv + (size_t)k * C + n] = wv[(size_t)n * C + k];
+      // out_proj consumes the head-padded O layout: input channel k = h*hd+dd
+      // lives at row h*hdp+dd
+      const int h = k / L.hd, dd = k - h * L.hd;
+      blob[L.o_wo + (size_t)(h * L.hdp + dd) * C + n] = wo[(size_t)n * C + k];
+    }
+  if (rpb_table)
+    for (int h = 0; h < L.heads; ++h)
+      for (int t = 0; t < L.T; ++t) blob[L.o_rpb + (size_t)h * L.T + t] = rpb_table[(size_t)t * L.heads + h];
+  return HRF_OK;
+}
+
+int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
+                        const float* const* blobs, void* out, void* stream) {
+  int rc = check_attn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(x && blobs && out, HRF_EINVAL, "attn_fwd: null pointer");
+  HRF_REQUIRE(x != out, HRF_EINVAL, "attn_fwd: out must not alias x");
+  HRF_REQUIRE(d->n_kv == 0 || kv, HRF_EINVAL, "attn_fwd: kv list missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int passes = d->n_kv > 0 ? d->n_kv : 1;
+  for (int k = 0; k < passes; ++k) {
+    AttnParams p;
+    p.xq = x;
+    p.resid = k == 0 ? x : out;   // later modalities accumulate onto out
+    p.z = d->n_kv > 0 ? kv[k] : x;
+    p.blob = blobs[k];
+    p.out = out;
+    HRF_REQUIRE(p.z && p.blob, HRF_EINVAL, "attn_fwd: null kv/blob %d", k);
+    p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.heads = d->heads; p.win = d->win;
+    p.cross = d->n_kv > 0; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
+    rc = d->dtype == HRF_F32 ? launch_window_attn<float>(p, st)
+                             : launch_window_attn<__nv_bfloat16>(p, st);
+    if (rc) return rc;
+  }
+  return HRF_OK;
+}
+
+// ------------------------------------------------------------------ MixFFN
+static int check_ffn(const HrfFfnDesc* d) {
+  HRF_REQUIRE(d != nullptr, HRF_EINVAL, "ffn: null descriptor");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->hidden > 0, HRF_EINVAL,
+              "ffn: non-positive dimension");
+  HRF_REQUIRE(d->C % 2 == 0 && d->hidden % 4 == 0, HRF_EUNSUPPORTED,
+              "ffn: C=%d must be even and hidden=%d a multiple of 4", d->C, d->hidden);
+  HRF_REQUIRE(d->dtype == HRF_F32 || d->dtype == HRF_BF16, HRF_EINVAL, "ffn: dtype");
+  HRF_REQUIRE(FfnLayout(d->C, d->hidden).ldx <= 256, HRF_EUNSUPPORTED, "ffn: C=%d too wide", d->C);
+  return HRF_OK;
+}
+
+size_t hrf_ffn_blob_floats(const HrfFfnDesc* d) {
+  if (!d || d->C <= 0 || d->hidden <= 0) return 0;
+  return (size_t)FfnLayout(d->C, d->hidden).total;
+}
+
+int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, const float* w1,
+                 const float* b1, const float* const bn1[4], const float* wd, const float* bd,
+                 const float* const bn2[4], const float* w2, const float* b2,
+                 const float* const bn3[4], float bn_eps, float* blob) {
+  int rc = check_ffn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(ln_w && ln_b && w1 && wd && w2 && blob, HRF_EINVAL, "ffn_pack: null pointer");
+  const FfnLayout L(d->C, d->hidden);
+  const int C = L.C, Hd = L.hidden;
+  std::memset(blob, 0, sizeof(float) * L.total);
+  std::vector<float> s1, t1, s2, t2, s3, t3;
+  bn_affine(bn1, Hd, bn_eps, s1, t1);
+  bn_affine(bn2, Hd, bn_eps, s2, t2);
+  bn_affine(bn3, C, bn_eps, s3, t3);
+  for (int c = 0; c < C; ++c) {
+    blob[L.o_ln_w + c] = ln_w[c];
+    blob[L.o_ln_b + c] = ln_b[c];
+    blob[L.o_b2 + c] = (b2 ? b2[c] : 0.f) * s3[c] + t3[c];
+  }
+  for (int j = 0; j < Hd; ++j) {
+    for (int k = 0; k < C; ++k) blob[L.o_w1 + (size_t)k * Hd + j] = w1[(size_t)j * C + k] * s1[j];
+    blob[L.o_b1 + j] = (b1 ? b1[j] : 0.f) * s1[j] + t1[j];
+    for (int t = 0; t < 9; ++t) blob[L.o_wd + (size_t)t * Hd + j] = wd[(size_t)j * 9 + t] * s2[j];
+    blob[L.o_bd + j] = (bd ? bd[j] : 0.f) * s2[j] + t2[j];
+    for (int n = 0; n < C; ++n) blob[L.o_w2 + (size_t)j * C + n] = w2[(size_t)n * Hd + j] * s3[n];
+  }
+  return HRF_OK;
+}
+
+int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out, void* stream) {
+  int rc = check_ffn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(x && blob && out, HRF_EINVAL, "ffn_fwd: null pointer");
+  HRF_REQUIRE(x != out, HRF_EINVAL, "ffn_fwd: out must not alias x (3x3 halo reads)");
+  FfnParams p{x, blob, out, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps};
+  return d->dtype == HRF_F32 ? launch_mixffn<float>(p, (cudaStream_t)stream)
+                             : launch_mixffn<__nv_bfloat16>(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ exchange
+size_t hrf_pw_blob_floats(const HrfPwDesc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
+  return (size_t)PwLayout(d->Cin, d->Cout).total;
+}
+int hrf_pw_pack(const HrfPwDesc* d, const float* w, const float* bias, const float* const bn[4],
+                float bn_eps, float* blob) {
+  HRF_REQUIRE(d && w && blob, HRF_EINVAL, "pw_pack: null pointer");
+  pack_pw(PwLayout(d->Cin, d->Cout), w, bias, bn, bn_eps, blob);
+  return HRF_OK;
+}
+int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, void* stream) {
+  HRF_REQUIRE(d && x && blob && out, HRF_EINVAL, "pw_fwd: null pointer");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, HRF_EINVAL, "pw_fwd: dims");
+  PwParams p{x, blob, out, d->B * d->H * d->W, d->Cin, d->Cout, d->relu};
+  if (d->dtype == HRF_F32) return launch_pw<float>(p, (cudaStream_t)stream);
+  if (d->dtype == HRF_BF16) return launch_pw<__nv_bfloat16>(p, (cudaStream_t)stream);
+  HRF_REQUIRE(false, HRF_EINVAL, "pw_fwd: dtype");
+}
+
+size_t hrf_dwpw_blob_floats(const HrfDwPwDesc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
+  return (size_t)DwPwLayout(d->Cin, d->Cout).total;
+}
+int hrf_dwpw_pack(const HrfDwPwDesc* d, const float* wdw, const float* const bn_dw[4],
+                  const float* wpw, const float* const bn_pw[4], float bn_eps, float* blob) {
+  HRF_REQUIRE(d && wdw && wpw && blob, HRF_EINVAL, "dwpw_pack: null pointer");
+  const DwPwLayout D(d->Cin, d->Cout);
+  std::memset(blob, 0, sizeof(float) * D.total);
+  std::vector<float> s, t;
+  bn_affine(bn_dw, d->Cin, bn_eps, s, t);
+  for (int c = 0; c < d->Cin; ++c) {
+    for (int k = 0; k < 9; ++k) blob[D.o_wd + (size_t)k * d->Cin + c] = wdw[(size_t)c * 9 + k] * s[c];
+    blob[D.o_bd + c] = t[c];
+  }
+  pack_pw(PwLayout(d->Cin, d->Cout), wpw, nullptr, bn_pw, bn_eps, blob + D.o_pw);
+  return HRF_OK;
+}
+int hrf_dwpw_fwd(const HrfDwPwDesc* d, const void* x, const float* blob, void* out, void* stream) {
+  HRF_REQUIRE(d && x && blob && out, HRF_EINVAL, "dwpw_fwd: null pointer");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, HRF_EINVAL, "dwpw_fwd: dims");
+  DwPwParams p{x, blob, out, d->B, d->H, d->W, (d->H + 1) / 2, (d->W + 1) / 2, d->Cin, d->Cout, d->relu};
+  if (d->dtype == HRF_F32) return launch_dwpw<float>(p, (cudaStream_t)stream);
+  if (d->dtype == HRF_BF16) return launch_dwpw<__nv_bfloat16>(p, (cudaStream_t)stream);
+  HRF_REQUIRE(false, HRF_EINVAL, "dwpw_fwd: dtype");
+}
+
+int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
+                     const void* const* same, void* out, float* out_nchw_f32, void* stream) {
+  HRF_REQUIRE(d && x && out, HRF_EINVAL, "fuse_fwd: null pointer");
+  HRF_REQUIRE(d->n_up >= 0 && d->n_up <= HRF_MAX_FUSE_TERMS && d->n_same >= 0 &&
+                  d->n_same <= HRF_MAX_FUSE_TERMS, HRF_EINVAL, "fuse_fwd: term count");
+  HRF_REQUIRE((d->n_up == 0 || up) && (d->n_same == 0 || same), HRF_EINVAL, "fuse_fwd: term list");
+  FuseParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.out = out; p.out_nchw = out_nchw_f32;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.n_up = d->n_up; p.n_same = d->n_same;
+  p.relu = d->relu;
+  for (int j = 0; j < d->n_up; ++j) {
+    HRF_REQUIRE(up[j] && d->up_H[j] > 0 && d->up_W[j] > 0, HRF_EINVAL, "fuse_fwd: up term %d", j);
+    p.up[j] = up[j]; p.up_H[j] = d->up_H[j]; p.up_W[j] = d->up_W[j];
+  }
+  for (int j = 0; j < d->n_same; ++j) {
+    HRF_REQUIRE(same[j], HRF_EINVAL, "fuse_fwd: same term %d", j);
+    p.same[j] = same[j];
+  }
+  if (d->dtype == HRF_F32) return launch_fuse<float>(p, (cudaStream_t)stream);
+  if (d->dtype == HRF_BF16) return launch_fuse<__nv_bfloat16>(p, (cudaStream_t)stream);
+  HRF_REQUIRE(false, HRF_EINVAL, "fuse_fwd: dtype");
+}
+
+int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, const void* src,
+                     int32_t ddt, void* dst, void* stream) {
+  HRF_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, HRF_EINVAL, "nchw_to_nhwc: args");
+  return launch_layout<true>(B, C, H, W, sdt, src, ddt, dst, (cudaStream_t)stream);
+}
+int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, const void* src,
+                     int32_t ddt, void* dst, void* stream) {
+  HRF_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, HRF_EINVAL, "nhwc_to_nchw: args");
+  return launch_layout<false>(B, C, H, W, sdt, src, ddt, dst, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// Multi-resolution exchange kernels (HRModule.forward, reference hrnet.py:184-207
+// with the fuse layers of hrformer.py:498-561) and boundary layout converters.
+// All three are bandwidth kernels on channels-last tokens.
+#pragma once
+#include "common.cuh"
+
+namespace hrf {
+
+// ---------------------------------------------------------------------------
+// 1x1 conv + folded BN (+ReLU):  blob = Wt [Kp][Cout] (k-major, BN scale folded)
+// followed by bias [round_up(Cout,4)].
+// ---------------------------------------------------------------------------
+struct PwLayout {
+  int Cin, Cout, Kp, o_w, o_b, total, lda;
+  __host__ __device__ PwLayout(int cin, int cout) {
+    Cin = cin; Cout = cout; Kp = round_up(cin, 4);
+    o_w = 0; o_b = round_up(Kp * cout, 4); total = o_b + round_up(cout, 4);
+    lda = stride4odd(Kp);
+  }
+};
+constexpr int kPwThreads = 256;
+constexpr int kPwTokens = 64;
+
+struct PwParams {
+  const void* x; const float* blob; void* out;
+  int ntok, Cin, Cout, relu;
+};
+
+template <typename T, int CT>
+__global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const PwLayout L(p.Cin, p.Cout);
+  const T* x = static_cast<const T*>(p.x);
+  T* out = static_cast<T*>(p.out);
+  const int t0 = blockIdx.x * kPwTokens;
+  const int m = min(kPwTokens, p.ntok - t0);
+  // stage the token tile (contiguous in memory) as fp32, zero-padded to lda
+  for (int e = threadIdx.x; e < kPwTokens * L.lda; e += blockDim.x) {
+    const int r = e / L.lda, c = e - r * L.lda;
+    smem[e] = (r < m && c < p.Cin) ? Elem<T>::ld(x + (size_t)(t0 + r) * p.Cin + c) : 0.f;
+  }
+  __syncthreads();
+  const float* bias = p.blob + L.o_b;
+  const int relu = p.relu, Cout = p.Cout;
+  block_gemm<4, CT>(smem, L.lda, m, p.blob + L.o_w, L.Kp, Cout, [&](int r, int n, float v) {
+    v += __ldg(bias + n);
+    if (relu) v = fmaxf(v, 0.f);
+    Elem<T>::st(out + (size_t)(t0 + r) * Cout + n, v);
+  });
+}
+
+template <typename T>
+static int launch_pw(const PwParams& p, cudaStream_t stream) {
+  const PwLayout L(p.Cin, p.Cout);
+  const size_t smem = (size_t)kPwTokens * L.lda * sizeof(float);
+  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "pw: Cin=%d too wide", p.Cin);
+  HRF_REQUIRE(p.Cout % 2 == 0, HRF_EUNSUPPORTED, "pw: Cout=%d must be even", p.Cout);
+  auto kern = (p.Cout % 4 == 0) ? pw_kernel<T, 4> : pw_kernel<T, 2>;
+  HRF_CUDA(ensure_smem((const void*)kern, smem));
+  kern<<<ceil_div(p.ntok, kPwTokens), kPwThreads, smem, stream>>>(p);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// depthwise 3x3 stride-2 (pad 1) + BN, then 1x1 + BN (+ReLU).
+// blob = Wdw [9][Cin] (BN folded), bdw [c4(Cin)], then a PwLayout blob.
+// ---------------------------------------------------------------------------
+struct DwPwLayout {
+  int Cin, Cout, o_wd, o_bd, o_pw, total;
+  __host__ __device__ DwPwLayout(int cin, int cout) {
+    Cin = cin; Cout = cout;
+    o_wd = 0; o_bd = round_up(9 * cin, 4); o_pw = o_bd + round_up(cin, 4);
+    total = o_pw + PwLayout(cin, cout).total;
+  }
+};
+struct DwPwParams {
+  const void* x; const float* blob; void* out;
+  int B, H, W, Ho, Wo, Cin, Cout, relu;
+};
+
+template <typename T, int CT>
+__global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const DwPwLayout D(p.Cin, p.Cout);
+  const PwLayout L(p.Cin, p.Cout);
+  const T* x = static_cast<const T*>(p.x);
+  T* out = static_cast<T*>(p.out);
+  const int ntok = p.B * p.Ho * p.Wo;
+  const int t0 = blockIdx.x * kPwTokens;
+  const int m = min(kPwTokens, ntok - t0);
+  const float* wd = p.blob + D.o_wd;
+  const float* bd = p.blob + D.o_bd;
+  for (int e = threadIdx.x; e < kPwTokens * L.lda; e += blockDim.x) {
+    const int r = e / L.lda, c = e - r * L.lda;
+    float s = 0.f;
+    if (r < m && c < p.Cin) {
+      const int t = t0 + r;
+      const int b = t / (p.Ho * p.Wo), oy = (t / p.Wo) % p.Ho, ox = t % p.Wo;
+      s = __ldg(bd + c);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int iy = oy * 2 - 1 + dy;
+        if (iy < 0 || iy >= p.H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int ix = ox * 2 - 1 + dx;
+          if (ix < 0 || ix >= p.W) continue;
+          s = fmaf(Elem<T>::ld(x + ((size_t)(b * p.H + iy) * p.W + ix) * p.Cin + c),
+                   __ldg(wd + (dy * 3 + dx) * p.Cin + c), s);
+        }
+      }
+    }
+    smem[e] = s;
+  }
+  __syncthreads();
+  const float* pw = p.blob + D.o_pw;
+  const float* bias = pw + L.o_b;
+  const int relu = p.relu, Cout = p.Cout;
+  block_gemm<4, CT>(smem, L.lda, m, pw + L.o_w, L.Kp, Cout, [&](int r, int n, float v) {
+    v += __ldg(bias + n);
+    if (relu) v = fmaxf(v, 0.f);
+    Elem<T>::st(out + (size_t)(t0 + r) * Cout + n, v);
+  });
+}
+
+template <typename T>
+static int launch_dwpw(const DwPwParams& p, cudaStream_t stream) {
+  const PwLayout L(p.Cin, p.Cout);
+  const size_t smem = (size_t)kPwTokens * L.lda * sizeof(float);
+  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "dwpw: Cin=%d too wide", p.Cin);
+  HRF_REQUIRE(p.Cout % 2 == 0, HRF_EUNSUPPORTED, "dwpw: Cout=%d must be even", p.Cout);
+  auto kern = (p.Cout % 4 == 0) ? dwpw_kernel<T, 4> : dwpw_kernel<T, 2>;
+  HRF_CUDA(ensure_smem((const void*)kern, smem));
+  kern<<<ceil_div(p.B * p.Ho * p.Wo, kPwTokens), kPwThreads, smem, stream>>>(p);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// out = ReLU(x + sum_j bilinear(up_j -> (H,W)) + sum_j same_j), optional second
+// copy of the result as contiguous fp32 NCHW (the backbone's output contract).
+// Bilinear: align_corners=False, scale = in/out from sizes, source index clamped
+// at 0 (ATen upsample_bilinear2d semantics used by hrnet.py:199-203).
+// ---------------------------------------------------------------------------
+struct FuseParams {
+  const void* x;
+  const void* up[HRF_MAX_FUSE_TERMS];
+  const void* same[HRF_MAX_FUSE_TERMS];
+  int up_H[HRF_MAX_FUSE_TERMS], up_W[HRF_MAX_FUSE_TERMS];
+  void* out;
+  float* out_nchw;
+  int B, H, W, C, n_up, n_same, relu;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
+  const size_t total = (size_t)p.B * p.H * p.W * p.C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % p.C);
+    const size_t t = e / p.C;
+    const int w = (int)(t % p.W), h = (int)((t / p.W) % p.H), b = (int)(t / ((size_t)p.W * p.H));
+    float v = Elem<T>::ld(static_cast<const T*>(p.x) + e);
+    for (int j = 0; j < p.n_same; ++j) v += Elem<T>::ld(static_cast<const T*>(p.same[j]) + e);
+    for (int j = 0; j < p.n_up; ++j) {
+      const int ih = p.up_H[j], iw = p.up_W[j];
+      const T* u = static_cast<const T*>(p.up[j]);
+      const float sh = (float)ih / (float)p.H, sw = (float)iw / (float)p.W;
+      const float fy = fmaxf(sh * ((float)h + 0.5f) - 0.5f, 0.f);
+      const float fx = fmaxf(sw * ((float)w + 0.5f) - 0.5f, 0.f);
+      const int y0 = min((int)fy, ih - 1), x0 = min((int)fx, iw - 1);
+      const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
+      const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      const size_t base = (size_t)b * ih * iw;
+      const float v00 = Elem<T>::ld(u + ((base + (size_t)y0 * iw + x0) * p.C + c));
+      const float v01 = Elem<T>::ld(u + ((base + (size_t)y0 * iw + x1) * p.C + c));
+      const float v10 = Elem<T>::ld(u + ((base + (size_t)y1 * iw + x0) * p.C + c));
+      const float v11 = Elem<T>::ld(u + ((base + (size_t)y1 * iw + x1) * p.C + c));
+      v += hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    }
+    if (p.relu) v = fmaxf(v, 0.f);
+    Elem<T>::st(static_cast<T*>(p.out) + e, v);
+    if (p.out_nchw) {
+      // round through the storage type so both copies hold the same values
+      const float vs = Elem<T>::ld(static_cast<const T*>(p.out) + e);
+      p.out_nchw[(((size_t)b * p.C + c) * p.H + h) * p.W + w] = vs;
+    }
+  }
+}
+
+template <typename T>
+static int launch_fuse(const FuseParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.B * p.H * p.W * p.C;
+  const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  fuse_sum_kernel<T><<<grid, 256, 0, stream>>>(p);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// layout converters (tiled transpose through shared memory)
+// ---------------------------------------------------------------------------
+template <typename TS, typename TD, bool ToNhwc>
+__global__ void __launch_bounds__(256) layout_kernel(const TS* src, TD* dst, int C, int HW) {
+  // ToNhwc: src [B][C][HW] -> dst [B][HW][C];   else src [B][HW][C] -> dst [B][C][HW]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x / 32;  // 32 x 8
+  const size_t base = (size_t)b * C * HW;
+  if (ToNhwc) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, q = p0 + tx;
+      tile[i][tx] = (c < C && q < HW) ? Elem<TS>::ld(src + base + (size_t)c * HW + q) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int q = p0 + i, c = c0 + tx;
+      if (c < C && q < HW) Elem<TD>::st(dst + base + (size_t)q * C + c, tile[tx][i]);
+    }
+  } else {
+    for (int i = ty; i < 32; i += 8) {
+      const int q = p0 + i, c = c0 + tx;
+      tile[i][tx] = (c < C && q < HW) ? Elem<TS>::ld(src + base + (size_t)q * C + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, q = p0 + tx;
+      if (c < C && q < HW) Elem<TD>::st(dst + base + (size_t)c * HW + q, tile[tx][i]);
+    }
+  }
+}
+
+template <bool ToNhwc>
+static int launch_layout(int B, int C, int H, int W, int sdt, const void* src, int ddt, void* dst,
+                         cudaStream_t stream) {
+  const int HW = H * W;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B);
+  HRF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, HRF_EUNSUPPORTED, "layout: tensor too large");
+  using bf = __nv_bfloat16;
+  if (sdt == HRF_F32 && ddt == HRF_F32)
+    layout_kernel<float, float, ToNhwc><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, C, HW);
+  else if (sdt == HRF_F32 && ddt == HRF_BF16)
+    layout_kernel<float, bf, ToNhwc><<<grid, 256, 0, stream>>>((const float*)src, (bf*)dst, C, HW);
+  else if (sdt == HRF_BF16 && ddt == HRF_F32)
+    layout_kernel<bf, float, ToNhwc><<<grid, 256, 0, stream>>>((const bf*)src, (float*)dst, C, HW);
+  else if (sdt == HRF_BF16 && ddt == HRF_BF16)
+    layout_kernel<bf, bf, ToNhwc><<<grid, 256, 0, stream>>>((const bf*)src, (bf*)dst, C, HW);
+  else
+    HRF_REQUIRE(false, HRF_EINVAL, "layout: bad dtype");
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+}  // namespace hrf

@@ -1,0 +1,311 @@
+"""Inference engine: walks a `HRFuserHRFormerBased` module once, packs its
+parameters for the sm_100a kernels, and runs the forward with them.
+
+What runs where:
+  * window attention (LSA / MWCA), MixFFN, the multi-resolution exchange and the
+    pad/partition/merge reshapes  -> hand-written kernels behind the C-ABI (`ops`)
+  * stems, Bottlenecks and 3x3 transition convs ("next")
+    -> cuDNN through torch, BatchNorm folded into the conv, channels-last
+Activations between the two worlds are channels-last, so no layout copy is made:
+a (B,C,H,W) channels_last tensor *is* the (B,H,W,C) token tensor the kernels read.
+
+The wiring follows the reference forward (hrfuser_hrformer_based.py:522-627),
+including the `transition1[i][0]` quirk (:550-551).
+"""
+import contextlib
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+def _fold_conv_bn(conv, bn, dtype):
+    """conv (no bias or bias) followed by eval-mode BN -> (weight, bias) tensors."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * s.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return (w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype))
+
+
+class _Conv:
+    """Folded conv+BN(+ReLU) executed by cuDNN (channels-last)."""
+
+    def __init__(self, conv, bn, relu, dtype):
+        self.w, self.b = _fold_conv_bn(conv, bn, dtype)
+        self.stride, self.padding, self.groups, self.relu = conv.stride, conv.padding, conv.groups, relu
+
+    def __call__(self, x, residual=None):
+        y = F.conv2d(x, self.w, self.b, self.stride, self.padding, 1, self.groups)
+        if residual is not None:
+            y += residual
+        return y.relu_() if self.relu else y
+
+
+def _seq(mods, dtype):
+    """nn.Sequential of [conv, bn, (relu)] -> _Conv"""
+    mods = list(mods)
+    relu = len(mods) > 2 and isinstance(mods[2], nn.ReLU)
+    return _Conv(mods[0], mods[1], relu, dtype)
+
+
+class _Bottleneck:
+    def __init__(self, m, dtype):
+        self.c1 = _Conv(m.conv1, m.bn1, True, dtype)
+        self.c2 = _Conv(m.conv2, m.bn2, True, dtype)
+        self.c3 = _Conv(m.conv3, m.bn3, True, dtype)     # ReLU after the residual add
+        self.down = _Conv(m.downsample[0], m.downsample[1], False, dtype) \
+            if m.downsample is not None else None
+
+    def __call__(self, x):
+        idt = x if self.down is None else self.down(x)
+        return self.c3(self.c2(self.c1(x)), residual=idt)
+
+
+class BackboneEngine:
+    def __init__(self, module, precision='fp32', device_ops=None):
+        """`device_ops` replaces the forward ops of `ops` (the packers always come
+        from the real library); only the CPU test-suite passes it, to check the
+        packing and the wiring against a blob-level emulation without a GPU."""
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        lib = _lib.load()                       # raises if the CUDA library is not built
+        dev = module.conv1.weight.device
+        self.ops = device_ops or ops
+        if device_ops is None:
+            if dev.type != 'cuda':
+                raise _lib.HrfError('HRFuserHRFormerBased inference needs a CUDA device: the '
+                                    'eval forward runs on sm_100a kernels and has no CPU '
+                                    'fallback (call .cuda() first)')
+            with torch.cuda.device(dev):
+                _lib.check(lib.hrf_device_check())
+        if any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training
+               for m in module.modules()):
+            raise _lib.HrfError('engine built while BatchNorm layers are in training mode')
+        self.device, self.precision = dev, precision
+        self.dtype = torch.float32 if precision == 'fp32' else torch.bfloat16
+        self.M = module.num_fused_modalities
+        self.pad_mask = module.with_pad_mask
+        self._host_blobs, self._blob_slots = [], []
+        m, dt = module, self.dtype
+
+        self.stem = [_Conv(m.conv1, m.bn1, True, dt), _Conv(m.conv2, m.bn2, True, dt)] + \
+                    [_Bottleneck(b, dt) for b in m.layer1]
+        self.stem_mod = [[_Conv(m.conv_a[k], m.norm_a[k], True, dt),
+                          _Conv(m.conv_b[k], m.norm_b[k], True, dt)] +
+                         [_Bottleneck(b, dt) for b in m.layer_a[k]] for k in range(self.M)]
+        # transition1[i][0]: bare conv on branch 0, full conv-bn-relu on branch 1
+        self.trans1 = [_Conv(m.transition1[0][0], None, False, dt)] + \
+                      [_seq(m.transition1[i][0], dt) for i in range(1, len(m.transition1))]
+        self.trans_cam = {2: self._transitions(m.transition2), 3: self._transitions(m.transition3)}
+        letters = ['a', 'b', 'c'] + (['d'] if m.pre_neck_fusion else [])
+        self.trans_mod = {l: [self._transitions(getattr(m, f'transition_{l}')[k])
+                              for k in range(self.M)] for l in letters}
+        self.fusion = {l: [self._fusion_block(b) for b in getattr(m, f'fusion_{l}')]
+                       for l in letters}
+        self.stage = {i: self._stage(getattr(m, f'stage{i}')) for i in (2, 3, 4)}
+        self.stage_mod = {l: [self._stage(getattr(m, f'stage_{l}')[k]) for k in range(self.M)]
+                          for l in letters[1:]}
+        self.pre_neck_fusion = m.pre_neck_fusion
+        self._upload()
+
+    # ---------------------------------------------------------------- packing
+    def _blob(self, host_blob):
+        """register a host blob; returns a slot whose .t is the device view after upload"""
+        slot = type('Blob', (), {})()
+        self._host_blobs.append(host_blob)
+        self._blob_slots.append(slot)
+        return slot
+
+    def _upload(self):
+        """one H2D copy for all packed weights; 256-byte aligned sub-views"""
+        offs, total = [], 0
+        for b in self._host_blobs:
+            offs.append(total)
+            total += (b.numel() + 63) // 64 * 64
+        arena = torch.zeros(max(total, 64), dtype=torch.float32)
+        for b, o in zip(self._host_blobs, offs):
+            arena[o:o + b.numel()] = b
+        self.arena = arena.to(self.device)
+        for slot, b, o in zip(self._blob_slots, self._host_blobs, offs):
+            slot.t = self.arena[o:o + b.numel()]
+        self._host_blobs = None
+
+    def _transitions(self, tl):
+        out = []
+        for t in tl:
+            if t is None:
+                out.append(None)
+            elif isinstance(t[0], nn.Conv2d):
+                out.append([_seq(t, self.dtype)])
+            else:
+                out.append([_seq(s, self.dtype) for s in t])
+        return out
+
+    def _ffn(self, ln, ffn):
+        L = ffn.layers
+        return dict(blob=self._blob(ops.pack_ffn(ln, L[0], L[1], L[3], L[4], L[6], L[7], L[1].eps)),
+                    hidden=L[0].weight.shape[0], eps=ln.eps)
+
+    def _hrformer_block(self, b):
+        a = b.attn.attn
+        Cc = a.qkv.weight.shape[1]
+        wq, wk, wv = a.qkv.weight.detach().split(Cc, 0)
+        bq, bk, bv = a.qkv.bias.detach().split(Cc, 0)
+        ln = (b.norm1.weight, b.norm1.bias)
+        blob = ops.pack_attn(Cc, a.num_heads, a.Wh, ln, ln, wq, bq, wk, bk, wv, bv,
+                             a.out_proj.weight, a.out_proj.bias,
+                             a.relative_position_bias_table if a.with_rpe else None)
+        assert a.Wh == a.Ww
+        return dict(attn=[self._blob(blob)], heads=a.num_heads, win=a.Wh, eps=b.norm1.eps,
+                    pad_mask=b.attn.with_pad_mask, ffn=self._ffn(b.norm2, b.ffn))
+
+    def _fusion_block(self, b):
+        blobs = []
+        for k in range(b.num_fused_modalities):
+            a = b.attn[k].attn
+            Cc = a.q_proj.weight.shape[0]
+            blobs.append(self._blob(ops.pack_attn(
+                Cc, a.num_heads, a.Wh, (b.norm1[k].weight, b.norm1[k].bias),
+                (b.norm2[k].weight, b.norm2[k].bias), a.q_proj.weight, a.q_proj.bias,
+                a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias,
+                a.out_proj.weight, a.out_proj.bias,
+                a.relative_position_bias_table if a.with_rpe else None)))
+        a = b.attn[0].attn
+        return dict(attn=blobs, heads=a.num_heads, win=a.Wh, eps=b.norm1[0].eps,
+                    pad_mask=b.attn[0].with_pad_mask, ffn=self._ffn(b.norm3, b.ffn))
+
+    def _stage(self, seq):
+        mods = []
+        for hm in seq:
+            branches = [[self._hrformer_block(b) for b in br] for br in hm.branches]
+            rows = None
+            if hm.fuse_layers is not None:
+                rows = []
+                for i, row in enumerate(hm.fuse_layers):
+                    ups, downs = [], []
+                    for j, layer in enumerate(row):
+                        if j > i:
+                            ups.append((j, self._blob(ops.pack_pw(layer[0], layer[1], layer[1].eps)),
+                                        layer[0].weight.shape[0]))
+                        elif j < i:
+                            chain = [(self._blob(ops.pack_dwpw(s[0], s[1], s[2], s[3], s[1].eps)),
+                                      s[2].weight.shape[0], len(s) > 4) for s in layer]
+                            downs.append((j, chain))
+                    rows.append((ups, downs))
+            mods.append((branches, rows))
+        return mods
+
+    # ---------------------------------------------------------------- running
+    @staticmethod
+    def _tokens(x):
+        """(B,C,H,W) channels_last -> (B,H,W,C) contiguous view"""
+        t = x.permute(0, 2, 3, 1)
+        return t if t.is_contiguous() else t.contiguous()
+
+    @staticmethod
+    def _image(t):
+        """(B,H,W,C) contiguous -> (B,C,H,W) channels_last view"""
+        return t.permute(0, 3, 1, 2)
+
+    def _run_block(self, blk, x, kv=None):
+        y = self.ops.window_attention(x, kv, [s.t for s in blk['attn']], blk['heads'], blk['win'],
+                                 blk['pad_mask'], blk['eps'])
+        f = blk['ffn']
+        return self.ops.mixffn(y, f['blob'].t, f['hidden'], f['eps'])
+
+    def _run_stage(self, mods, xs, final_nchw=False):
+        nchw = None
+        for mi, (branches, rows) in enumerate(mods):
+            ys = []
+            for br, x in zip(branches, xs):
+                for blk in br:
+                    x = self._run_block(blk, x)
+                ys.append(x)
+            if rows is None:
+                xs = ys
+                continue
+            want_nchw = final_nchw and mi == len(mods) - 1
+            outs, nchw = [], []
+            for i, (ups, downs) in enumerate(rows):
+                up_t = [self.ops.pointwise(ys[j], blob.t, cout) for j, blob, cout in ups]
+                same_t = []
+                for j, chain in downs:
+                    t = ys[j]
+                    for blob, cout, relu in chain:
+                        t = self.ops.dw_down(t, blob.t, cout, relu)
+                    same_t.append(t)
+                r = self.ops.fuse_sum(ys[i], up_t, same_t, relu=True, nchw_out=want_nchw)
+                if want_nchw:
+                    outs.append(r[0])
+                    nchw.append(r[1])
+                else:
+                    outs.append(r)
+            xs = outs
+        return (xs, nchw) if final_nchw else xs
+
+    def _apply_chain(self, chain, x_img):
+        for c in chain:
+            x_img = c(x_img)
+        return x_img
+
+    def _fuse(self, letter, cams, stream):
+        outs, firsts = [], None
+        for i, cam in enumerate(cams):
+            ms = []
+            for k in range(self.M):
+                tr = self.trans_mod[letter][k][i]
+                ms.append(stream[k] if tr is None else
+                          self._tokens(self._apply_chain(tr, self._image(stream[k]))))
+            if i == 0:
+                firsts = ms
+            outs.append(self._run_block(self.fusion[letter][i], cam, ms))
+        return outs, firsts
+
+    def _prep(self, t):
+        return t.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
+
+    @torch.no_grad()
+    def forward(self, x, mods):
+        if len(mods) != self.M:
+            raise Exception('num_fused_modalities does not fit the given input length')
+        fp32_cuda = self.precision == 'fp32' and self.device.type == 'cuda'
+        ctx = torch.backends.cudnn.flags(enabled=True, allow_tf32=False) \
+            if fp32_cuda else contextlib.nullcontext()
+        dctx = torch.cuda.device(self.device) if self.device.type == 'cuda' \
+            else contextlib.nullcontext()
+        with ctx, dctx:
+            x = self._apply_chain(self.stem, self._prep(x))
+            stream = [self._tokens(self._apply_chain(self.stem_mod[k], self._prep(mods[k])))
+                      for k in range(self.M)]
+            cams = [self._tokens(t(x)) for t in self.trans1]
+            xs, firsts = self._fuse('a', cams, stream)
+            ys = self._run_stage(self.stage[2], xs)
+            stream = [self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0] for k in range(self.M)]
+
+            for idx, letter, nxt in ((2, 'b', 'c'), (3, 'c', 'd')):
+                cams = list(ys)
+                for i, tr in enumerate(self.trans_cam[idx]):
+                    if tr is not None:
+                        t = self._tokens(self._apply_chain(tr, self._image(ys[-1])))
+                        if i < len(cams):
+                            cams[i] = t
+                        else:
+                            cams.append(t)
+                xs, firsts = self._fuse(letter, cams, stream)
+                last = idx == 3
+                if last:
+                    ys, nchw = self._run_stage(self.stage[4], xs, final_nchw=True)
+                else:
+                    ys = self._run_stage(self.stage[3], xs)
+                if nxt in self.stage_mod:
+                    stream = [self._run_stage(self.stage_mod[nxt][k], [firsts[k]])[0]
+                              for k in range(self.M)]
+            if self.pre_neck_fusion:
+                xs, _ = self._fuse('d', ys, stream)
+                nchw = [self.ops.fuse_sum(t, relu=True, nchw_out=True)[1] for t in xs]
+            return nchw

@@ -1,0 +1,209 @@
+"""Torch-tensor front end of the C-ABI ops (device memory, streams: plumbing only).
+
+Activations are channels-last token tensors of shape (B, H, W, C), contiguous,
+fp32 or bf16, on a CUDA device.  Packed weights are fp32 blobs produced by the
+`pack_*` helpers (host side, via the library's own packers) and uploaded once.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (AttnDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, check)
+
+_DT = {torch.float32: HRF_F32, torch.bfloat16: HRF_BF16}
+_F = C.POINTER(C.c_float)
+
+
+def _dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f'unsupported activation dtype {t.dtype}') from None
+
+
+def _host(t):
+    """detached fp32 contiguous CPU tensor (kept alive by the caller's list)"""
+    return t.detach().to('cpu', torch.float32).contiguous()
+
+
+def _fp(t):
+    return C.cast(t.data_ptr(), _F) if t is not None else None
+
+
+def _bn4(bn, keep):
+    """BatchNorm module -> `const float* const[4]` (weight, bias, mean, var)."""
+    if bn is None:
+        return None
+    ts = [_host(bn.weight), _host(bn.bias), _host(bn.running_mean), _host(bn.running_var)]
+    keep.extend(ts)
+    return (_F * 4)(*[_fp(t) for t in ts])
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_act(x, name='x'):
+    if not (x.is_cuda and x.dim() == 4 and x.is_contiguous()):
+        raise ValueError(f'{name} must be a contiguous CUDA (B,H,W,C) tensor')
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * max(1, len(tensors)))(*[t.data_ptr() for t in tensors])
+
+
+# ----------------------------------------------------------------------------
+# packers (host)
+# ----------------------------------------------------------------------------
+def attn_desc(B, H, W, Cc, heads, n_kv, dtype=torch.float32, win=7, with_pad_mask=False,
+              eps=1e-6):
+    return AttnDesc(B, H, W, Cc, heads, win, n_kv, _DT[dtype], int(with_pad_mask), eps)
+
+
+def pack_attn(Cc, heads, win, ln_q, ln_kv, wq, bq, wk, bk, wv, bv, wo, bo, rpb_table):
+    """-> fp32 CPU blob.  ln_q / ln_kv are (weight, bias) pairs."""
+    lib = _lib.load()
+    d = AttnDesc(1, win, win, Cc, heads, win, 0, HRF_F32, 0, 1e-6)
+    blob = torch.empty(lib.hrf_attn_blob_floats(C.byref(d)), dtype=torch.float32)
+    ts = [_host(t) if t is not None else None
+          for t in (ln_q[0], ln_q[1], ln_kv[0], ln_kv[1], wq, bq, wk, bk, wv, bv, wo, bo, rpb_table)]
+    check(lib.hrf_attn_pack(C.byref(d), *[_fp(t) for t in ts], _fp(blob)))
+    return blob
+
+
+def pack_ffn(ln, conv1, bn1, convd, bn2, conv2, bn3, bn_eps=1e-5):
+    lib = _lib.load()
+    Cc, hidden = conv1.weight.shape[1], conv1.weight.shape[0]
+    d = FfnDesc(1, 8, 8, Cc, hidden, HRF_F32, 1e-6)
+    blob = torch.empty(lib.hrf_ffn_blob_floats(C.byref(d)), dtype=torch.float32)
+    keep = []
+    h = lambda t: (keep.append(_host(t)) or keep[-1]) if t is not None else None
+    args = [h(ln.weight), h(ln.bias), h(conv1.weight), h(conv1.bias), _bn4(bn1, keep),
+            h(convd.weight), h(convd.bias), _bn4(bn2, keep), h(conv2.weight), h(conv2.bias),
+            _bn4(bn3, keep)]
+    conv = [a if isinstance(a, (type(None), C.Array)) else _fp(a) for a in args]
+    check(lib.hrf_ffn_pack(C.byref(d), *conv, C.c_float(bn_eps), _fp(blob)))
+    return blob
+
+
+def pack_pw(conv, bn, bn_eps=1e-5):
+    lib = _lib.load()
+    cout, cin = conv.weight.shape[:2]
+    d = PwDesc(1, 1, 1, cin, cout, HRF_F32, 0)
+    blob = torch.empty(lib.hrf_pw_blob_floats(C.byref(d)), dtype=torch.float32)
+    keep = []
+    w = _host(conv.weight)
+    b = _host(conv.bias) if conv.bias is not None else None
+    check(lib.hrf_pw_pack(C.byref(d), _fp(w), _fp(b), _bn4(bn, keep), C.c_float(bn_eps), _fp(blob)))
+    return blob
+
+
+def pack_dwpw(conv_dw, bn_dw, conv_pw, bn_pw, bn_eps=1e-5):
+    lib = _lib.load()
+    cout, cin = conv_pw.weight.shape[:2]
+    d = DwPwDesc(1, 2, 2, cin, cout, HRF_F32, 0)
+    blob = torch.empty(lib.hrf_dwpw_blob_floats(C.byref(d)), dtype=torch.float32)
+    keep = []
+    wd, wp = _host(conv_dw.weight), _host(conv_pw.weight)
+    check(lib.hrf_dwpw_pack(C.byref(d), _fp(wd), _bn4(bn_dw, keep), _fp(wp), _bn4(bn_pw, keep),
+                            C.c_float(bn_eps), _fp(blob)))
+    return blob
+
+
+# ----------------------------------------------------------------------------
+# forward ops (device)
+# ----------------------------------------------------------------------------
+def window_attention(x, kv, blobs, heads, win=7, with_pad_mask=False, eps=1e-6, out=None):
+    """LSA when `kv` is empty/None (out = x + Attn(LN x)), else MWCA over the
+    modalities in `kv` (out = x + sum_k[kv_k + Attn_k(LN1_k x, LN2_k kv_k)])."""
+    lib = _lib.load()
+    _check_act(x)
+    kv = list(kv or [])
+    for t in kv:
+        _check_act(t, 'kv')
+        assert t.shape == x.shape and t.dtype == x.dtype
+    assert len(blobs) == max(1, len(kv))
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x) if out is None else out
+    d = attn_desc(B, H, W, Cc, heads, len(kv), x.dtype, win, with_pad_mask, eps)
+    check(lib.hrf_window_attn_fwd(C.byref(d), x.data_ptr(), _ptr_array(kv), _ptr_array(blobs),
+                                  out.data_ptr(), _stream()))
+    return out
+
+
+def mixffn(x, blob, hidden, eps=1e-6, out=None):
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x) if out is None else out
+    d = FfnDesc(B, H, W, Cc, hidden, _dtype_code(x), eps)
+    check(lib.hrf_mixffn_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def pointwise(x, blob, cout, relu=False):
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cin = x.shape
+    out = x.new_empty(B, H, W, cout)
+    d = PwDesc(B, H, W, Cin, cout, _dtype_code(x), int(relu))
+    check(lib.hrf_pw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def dw_down(x, blob, cout, relu=False):
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cin = x.shape
+    out = x.new_empty(B, (H + 1) // 2, (W + 1) // 2, cout)
+    d = DwPwDesc(B, H, W, Cin, cout, _dtype_code(x), int(relu))
+    check(lib.hrf_dwpw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def fuse_sum(x, ups=(), sames=(), relu=True, nchw_out=False):
+    """ReLU(x + sum bilinear(ups) + sum sames); with nchw_out also returns the
+    result as a contiguous fp32 (B,C,H,W) tensor."""
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cc = x.shape
+    ups, sames = list(ups), list(sames)
+    d = FuseDesc(B, H, W, Cc, _dtype_code(x), len(ups))
+    for j, u in enumerate(ups):
+        _check_act(u, 'up')
+        assert u.shape[0] == B and u.shape[3] == Cc and u.dtype == x.dtype
+        d.up_H[j], d.up_W[j] = u.shape[1], u.shape[2]
+    for s in sames:
+        _check_act(s, 'same')
+        assert s.shape == x.shape and s.dtype == x.dtype
+    d.n_same, d.relu = len(sames), int(relu)
+    out = torch.empty_like(x)
+    nchw = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device) if nchw_out else None
+    check(lib.hrf_fuse_sum_fwd(C.byref(d), x.data_ptr(), _ptr_array(ups), _ptr_array(sames),
+                               out.data_ptr(), nchw.data_ptr() if nchw_out else None, _stream()))
+    return (out, nchw) if nchw_out else out
+
+
+def nchw_to_nhwc(x, dtype=None):
+    lib = _lib.load()
+    assert x.is_cuda and x.dim() == 4 and x.is_contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, dtype=dtype or x.dtype, device=x.device)
+    check(lib.hrf_nchw_to_nhwc(B, Cc, H, W, _dtype_code(x), x.data_ptr(), _dtype_code(out),
+                               out.data_ptr(), _stream()))
+    return out
+
+
+def nhwc_to_nchw(x, dtype=None):
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, Cc, H, W, dtype=dtype or x.dtype, device=x.device)
+    check(lib.hrf_nhwc_to_nchw(B, Cc, H, W, _dtype_code(x), x.data_ptr(), _dtype_code(out),
+                               out.data_ptr(), _stream()))
+    return out
+
+
+def launch_count():
+    return int(_lib.load().hrf_launch_count())

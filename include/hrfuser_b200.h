@@ -1,0 +1,168 @@
+/*
+ * hrfuser_b200 -- C-ABI of the B200 (sm_100a) HRFuser fusion-backbone hot path.
+ *
+ * The reference (timbroed/HRFuser) is pure Python/PyTorch and has no native
+ * layer; the entry points below are what a native binding for its hot path
+ * binds instead of the PyTorch op sequences cited at each function
+ * (file:line relative to the reference checkout).  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch types; all activation pointers are DEVICE pointers to
+ *     channels-last token tensors  [B][H][W][C]  (== the reference's (B, H*W, C)
+ *     "NLC" layout, hrformer.py:368 / models/utils/transformer.py:49-59) of
+ *     `dtype` HRF_F32 or HRF_BF16; arithmetic is fp32 unless stated.
+ *   - weights are fp32 blobs packed by the hrf_*_pack() helpers below (host
+ *     pointers in, host pointer out; copy the blob to the device yourself).
+ *   - every *_fwd call is stream-ordered, non-allocating and non-blocking;
+ *     the caller owns all memory.  `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success, a negative HRF_E* code otherwise;
+ *     hrf_last_error() returns a thread-local message.  Nothing throws or exits.
+ */
+#ifndef HRFUSER_B200_H_
+#define HRFUSER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRF_ABI_VERSION 2
+
+enum { HRF_F32 = 0, HRF_BF16 = 1 };
+enum {
+  HRF_OK = 0,
+  HRF_EINVAL = -1,      /* bad descriptor / null pointer            */
+  HRF_EUNSUPPORTED = -2,/* shape outside what the kernels cover     */
+  HRF_ECUDA = -3,       /* CUDA runtime error (see hrf_last_error)  */
+  HRF_EDEVICE = -4      /* not an sm_100 device                     */
+};
+
+int hrf_abi_version(void);
+const char* hrf_last_error(void);
+/* 0 when the current device can run the sm_100a kernels. */
+int hrf_device_check(void);
+/* Number of kernels this library has launched since load (all threads). */
+unsigned long long hrf_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Window attention: LocalWindowSelfAttention + WindowMSA
+ * (hrformer.py:96-131,184-236) and MultiWindowCrossAttention + WindowMCA
+ * (hrfuser_hrformer_based.py:106-151,189-248), fused with the LayerNorms in
+ * front of them and the residual adds behind them
+ * (hrformer.py:369; hrfuser_hrformer_based.py:305-313).
+ *
+ *   n_kv == 0 :  out = x + Attn(LN(x))                                 (LSA)
+ *   n_kv >= 1 :  out = x + sum_k [ kv_k + Attn_k(LN1_k(x), LN2_k(kv_k)) ] (MWCA)
+ *
+ * Centre padding to window multiples happens after the LayerNorm with zeros;
+ * padded slots are live keys unless with_pad_mask (and both pads > 0).
+ * No window tensor is materialised: pad / partition / merge / crop are
+ * address arithmetic inside the kernel.
+ * ---------------------------------------------------------------------- */
+typedef struct HrfAttnDesc {
+  int32_t B, H, W, C;
+  int32_t heads;
+  int32_t win;            /* window edge; 7 in every shipped config */
+  int32_t n_kv;           /* 0 = self-attention, else number of key/value modalities */
+  int32_t dtype;          /* HRF_F32 | HRF_BF16 (activation storage) */
+  int32_t with_pad_mask;
+  float   ln_eps;         /* 1e-6 */
+} HrfAttnDesc;
+
+/* floats in one packed blob (one per modality for MWCA, one for LSA) */
+size_t hrf_attn_blob_floats(const HrfAttnDesc* d);
+/* Host-side packing.  wq/wk/wv/wo are row-major (C_out, C_in) nn.Linear
+ * weights; for LSA pass the three (C, C) slices of qkv.weight.  ln_kv_* may
+ * equal ln_q_* (LSA).  rpb_table is ((2*win-1)^2, heads) or NULL (with_rpe=False). */
+int hrf_attn_pack(const HrfAttnDesc* d,
+                  const float* ln_q_w, const float* ln_q_b,
+                  const float* ln_kv_w, const float* ln_kv_b,
+                  const float* wq, const float* bq, const float* wk, const float* bk,
+                  const float* wv, const float* bv, const float* wo, const float* bo,
+                  const float* rpb_table, float* blob_out);
+/* kv: array of n_kv device pointers (ignored when n_kv == 0);
+ * blobs: array of max(1, n_kv) device pointers to packed blobs.
+ * out may alias x only when n_kv == 0 is false ... no aliasing is allowed. */
+int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
+                        const float* const* blobs, void* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * MixFFN (CrossFFN, hrformer.py:267-295) fused with the LayerNorm in front and
+ * the residual behind (hrformer.py:371; hrfuser_hrformer_based.py:315):
+ *   out = x + GELU(BN3(W2 * GELU(BN2(dw3x3(GELU(BN1(W1 * LN(x) + b1))) + bd)) + b2))
+ * BatchNorms are eval-mode affines folded into the packed weights.
+ * ---------------------------------------------------------------------- */
+typedef struct HrfFfnDesc {
+  int32_t B, H, W, C;
+  int32_t hidden;         /* mlp_ratio * C */
+  int32_t dtype;
+  float   ln_eps;
+} HrfFfnDesc;
+
+size_t hrf_ffn_blob_floats(const HrfFfnDesc* d);
+/* bnX = {weight, bias, running_mean, running_var} each of the layer's width. */
+int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b,
+                 const float* w1, const float* b1, const float* const bn1[4],
+                 const float* wd, const float* bd, const float* const bn2[4],
+                 const float* w2, const float* b2, const float* const bn3[4],
+                 float bn_eps, float* blob_out);
+int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out,
+                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-resolution exchange (HRModule.forward hrnet.py:184-207 with the fuse
+ * layers of hrformer.py:498-561).
+ * ---------------------------------------------------------------------- */
+typedef struct HrfPwDesc {      /* pointwise (1x1) conv + folded BN (+ReLU)  */
+  int32_t B, H, W, Cin, Cout;
+  int32_t dtype;
+  int32_t relu;
+} HrfPwDesc;
+size_t hrf_pw_blob_floats(const HrfPwDesc* d);
+/* w: (Cout, Cin); bn = {weight,bias,mean,var} or NULL; bias may be NULL */
+int hrf_pw_pack(const HrfPwDesc* d, const float* w, const float* bias,
+                const float* const bn[4], float bn_eps, float* blob_out);
+int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, void* stream);
+
+typedef struct HrfDwPwDesc {    /* dw3x3 stride 2 pad 1 + BN + 1x1 + BN (+ReLU): one
+                                   down-sampling step, hrformer.py:531-557 */
+  int32_t B, H, W, Cin, Cout;   /* H, W: INPUT size; output is ceil(H/2) x ceil(W/2) */
+  int32_t dtype;
+  int32_t relu;
+} HrfDwPwDesc;
+size_t hrf_dwpw_blob_floats(const HrfDwPwDesc* d);
+int hrf_dwpw_pack(const HrfDwPwDesc* d, const float* wdw /*(Cin,1,3,3)*/,
+                  const float* const bn_dw[4], const float* wpw /*(Cout,Cin)*/,
+                  const float* const bn_pw[4], float bn_eps, float* blob_out);
+int hrf_dwpw_fwd(const HrfDwPwDesc* d, const void* x, const float* blob, void* out,
+                 void* stream);
+
+#define HRF_MAX_FUSE_TERMS 4
+typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_j same_j) */
+  int32_t B, H, W, C;           /* output branch size */
+  int32_t dtype;
+  int32_t n_up;                 /* coarser terms, bilinearly up-sampled (align_corners=False,
+                                   scale from sizes: hrnet.py:199-203) */
+  int32_t up_H[HRF_MAX_FUSE_TERMS], up_W[HRF_MAX_FUSE_TERMS];
+  int32_t n_same;               /* terms already at (H, W) */
+  int32_t relu;
+} HrfFuseDesc;
+/* out_nchw_f32 may be NULL; when given, the result is additionally written as a
+ * contiguous fp32 (B, C, H, W) tensor -- the backbone's output contract
+ * (hrfuser_hrformer_based.py:627). */
+int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
+                     const void* const* same, void* out, float* out_nchw_f32, void* stream);
+
+/* Layout converters at the boundary of the path. */
+int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t src_dtype,
+                     const void* src, int32_t dst_dtype, void* dst, void* stream);
+int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t src_dtype,
+                     const void* src, int32_t dst_dtype, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRFUSER_B200_H_ */

@@ -1,0 +1,179 @@
+"""GPU parity of every C-ABI op against the oracle (oracle/hrfuser_oracle.py)."""
+import pytest
+import torch
+
+from helpers import (EDGE, NUS_B_FUSED, NUS_T, STF_T, assert_parity, make_block, make_exchange,
+                     tokens)
+from oracle import hrfuser_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = {'fp32': torch.float32, 'bf16': torch.bfloat16}
+
+
+def _engine_stub():
+    """pack with the real packers through a throw-away engine-like holder"""
+    from hrfuser_b200.engine import BackboneEngine
+    e = BackboneEngine.__new__(BackboneEngine)
+    e._host_blobs, e._blob_slots = [], []
+    e.device = torch.device('cuda')
+    e.dtype = torch.float32
+    return e
+
+
+def _nlc(t):
+    return t.reshape(t.shape[0], -1, t.shape[-1])
+
+
+def _ref_lsa(x, sd, heads, H, W, pad_mask=False):
+    t = _nlc(x)
+    n = O.layer_norm(t, sd, 'blk.norm1')
+    return (t + O.window_attention(n, n, sd, 'blk.attn', H, W, heads, False,
+                                   with_pad_mask=pad_mask)).view_as(x)
+
+
+def _ref_mwca(x, zs, sd, heads, H, W):
+    cam = _nlc(x)
+    acc = cam.clone()
+    for k, z in enumerate(zs):
+        zt = _nlc(z)
+        acc = acc + zt + O.window_attention(O.layer_norm(cam, sd, f'blk.norm1.{k}'),
+                                            O.layer_norm(zt, sd, f'blk.norm2.{k}'),
+                                            sd, f'blk.attn.{k}', H, W, heads, True)
+    return acc.view_as(x)
+
+
+SHAPES = NUS_T + STF_T + NUS_B_FUSED + EDGE
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('H,W,C,heads', SHAPES)
+def test_lsa(built_lib, H, W, C, heads, mode):
+    from hrfuser_b200 import ops
+    B = 2
+    blk, sd = make_block('lsa', C, heads, seed=H + C)
+    e = _engine_stub()
+    packed = e._hrformer_block(blk)
+    e._upload()
+    x = tokens(B, H, W, C, seed=1).to(DT[mode])
+    got = ops.window_attention(x.cuda(), None, [s.t for s in packed['attn']], heads)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = _ref_lsa(x.float(), sd, heads, H, W)
+    assert_parity(got, ref, mode, f'lsa {H}x{W} C{C}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('M', [1, 2, 3])
+@pytest.mark.parametrize('H,W,C,heads', NUS_T + STF_T[:2] + NUS_B_FUSED[:1] + EDGE[:4])
+def test_mwca(built_lib, H, W, C, heads, M, mode):
+    from hrfuser_b200 import ops
+    B = 2
+    blk, sd = make_block('mwca', C, heads, M=M, seed=H + C + M)
+    e = _engine_stub()
+    packed = e._fusion_block(blk)
+    e._upload()
+    x = tokens(B, H, W, C, seed=1).to(DT[mode])
+    zs = [tokens(B, H, W, C, seed=2 + k).to(DT[mode]) for k in range(M)]
+    if M == 3:
+        zs[1].zero_()            # a dropped modality (RandomDrop zeroes whole sensors)
+    got = ops.window_attention(x.cuda(), [z.cuda() for z in zs], [s.t for s in packed['attn']], heads)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = _ref_mwca(x.float(), [z.float() for z in zs], sd, heads, H, W)
+    assert_parity(got, ref, mode, f'mwca {H}x{W} C{C} M{M}')
+
+
+def test_lsa_pad_mask(built_lib):
+    from hrfuser_b200 import ops
+    for (H, W) in [(12, 20), (14, 20), (5, 3)]:     # (14,20): pad_h == 0 -> mask inactive
+        blk, sd = make_block('lsa', 36, 2, seed=3, with_pad_mask=True)
+        e = _engine_stub()
+        packed = e._hrformer_block(blk)
+        e._upload()
+        x = tokens(2, H, W, 36, seed=4)
+        got = ops.window_attention(x.cuda(), None, [s.t for s in packed['attn']], 2, with_pad_mask=True)
+        with torch.no_grad():
+            ref = _ref_lsa(x, sd, 2, H, W, pad_mask=True)
+        assert_parity(got, ref, 'fp32', f'lsa pad-mask {H}x{W}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('H,W,C,heads', SHAPES)
+def test_mixffn(built_lib, H, W, C, heads, mode):
+    from hrfuser_b200 import ops
+    B = 2
+    blk, sd = make_block('lsa', C, heads, seed=H + C + 7)
+    e = _engine_stub()
+    f = e._ffn(blk.norm2, blk.ffn)
+    e._upload()
+    x = tokens(B, H, W, C, seed=5).to(DT[mode])
+    got = ops.mixffn(x.cuda(), f['blob'].t, f['hidden'], f['eps'])
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        t = _nlc(x.float())
+        ref = (t + O.cross_ffn(O.layer_norm(t, sd, 'blk.norm2'), sd, 'blk.ffn', H, W)).view_as(x)
+    assert_parity(got, ref, mode, f'ffn {H}x{W} C{C}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('H,W,channels,heads', [
+    (96, 160, (18, 36), (1, 2)), (96, 160, (18, 36, 72), (1, 2, 4)),
+    (96, 160, (18, 36, 72, 144), (1, 2, 4, 8)), (96, 312, (18, 36, 72, 144), (1, 2, 4, 8)),
+    (32, 32, (78, 156), (2, 4)), (8, 24, (18, 36, 72), (1, 2, 4))])
+def test_exchange(built_lib, H, W, channels, heads, mode):
+    """HRModule fuse step: every output branch, incl. the fp32 NCHW copy."""
+    from hrfuser_b200 import ops
+    B = 2
+    mod, sd = make_exchange(channels, heads, seed=len(channels))
+    e = _engine_stub()
+    stage = e._stage([mod])
+    e._upload()
+    xs = [tokens(B, H >> i, W >> i, c, seed=10 + i).to(DT[mode]) for i, c in enumerate(channels)]
+    (branches, rows), = stage
+    e.ops = ops
+    outs, nchw = [], []
+    ys = [x.cuda() for x in xs]
+    for i, (ups, downs) in enumerate(rows):
+        up_t = [ops.pointwise(ys[j], blob.t, cout) for j, blob, cout in ups]
+        same_t = []
+        for j, chain in downs:
+            t = ys[j]
+            for blob, cout, relu in chain:
+                t = ops.dw_down(t, blob.t, cout, relu)
+            same_t.append(t)
+        o, n = ops.fuse_sum(ys[i], up_t, same_t, relu=True, nchw_out=True)
+        outs.append(o)
+        nchw.append(n)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.hr_exchange([x.float().permute(0, 3, 1, 2) for x in xs], sd, 'm')
+    for i, r in enumerate(ref):
+        assert_parity(outs[i].permute(0, 3, 1, 2), r, mode, f'exchange out{i}')
+        assert nchw[i].is_contiguous() and nchw[i].dtype == torch.float32
+        assert torch.equal(nchw[i].cpu(), outs[i].float().permute(0, 3, 1, 2).cpu())
+
+
+def test_layout_roundtrip(built_lib):
+    from hrfuser_b200 import ops
+    for (B, C, H, W) in [(2, 18, 12, 20), (1, 3, 33, 65), (2, 144, 5, 7)]:
+        x = torch.randn(B, C, H, W, device='cuda')
+        t = ops.nchw_to_nhwc(x)
+        assert torch.equal(t, x.permute(0, 2, 3, 1).contiguous())
+        assert torch.equal(ops.nhwc_to_nchw(t), x)
+        tb = ops.nchw_to_nhwc(x, torch.bfloat16)
+        assert torch.equal(tb, x.permute(0, 2, 3, 1).contiguous().bfloat16())
+        assert torch.equal(ops.nhwc_to_nchw(tb, torch.float32), x.bfloat16().float())
+
+
+def test_error_paths(built_lib):
+    """bad descriptors come back as error codes with a message, never a crash"""
+    from hrfuser_b200 import _lib, ops
+    x = torch.zeros(1, 7, 7, 18, device='cuda')
+    blob = torch.zeros(10, device='cuda')
+    with pytest.raises(_lib.HrfError, match='divisible'):
+        ops.window_attention(x, None, [blob], heads=4)
+    xw = torch.zeros(1, 7, 7, 624, device='cuda')
+    with pytest.raises(_lib.HrfError, match='too wide|shared memory'):
+        ops.window_attention(xw, None, [blob], heads=16)
+    with pytest.raises(_lib.HrfError, match='alias'):
+        ops.mixffn(x, blob, 72, out=x)
