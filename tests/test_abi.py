@@ -1,0 +1,101 @@
+"""The C-ABI library builds, loads on a CPU-only host, exports every symbol the
+header declares, and its host-side entry points (packers, validation) behave."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from hrfuser_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'hrfuser_b200.h')
+
+
+def _declared():
+    txt = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(hrf_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_header_symbols_exported_and_bound(built_lib):
+    names = _declared()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(built_lib, n), f'{n} declared in the header but not exported'
+        assert n in _lib.SIGNATURES, f'{n} has no ctypes signature'
+    assert sorted(_lib.SIGNATURES) == names
+    assert built_lib.hrf_abi_version() == _lib.ABI_VERSION
+    ver = int(re.search(r'#define HRF_ABI_VERSION (\d+)', open(HEADER).read()).group(1))
+    assert ver == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    # plain int32/float PODs: sizes as the C compiler lays them out
+    assert C.sizeof(_lib.AttnDesc) == 40
+    assert C.sizeof(_lib.FfnDesc) == 28
+    assert C.sizeof(_lib.PwDesc) == 28
+    assert C.sizeof(_lib.FuseDesc) == 4 * (6 + 2 * _lib.MAX_FUSE_TERMS + 2)
+
+
+def test_validation_errors_are_codes_with_messages(built_lib):
+    d = _lib.AttnDesc(1, 7, 7, 18, 4, 7, 0, 0, 0, 1e-6)          # 18 % 4 != 0
+    buf = (C.c_float * 8)()
+    rc = built_lib.hrf_attn_pack(C.byref(d), *([buf] * 13), buf)
+    assert rc == -1 and b'divisible' in built_lib.hrf_last_error()
+    d = _lib.AttnDesc(1, 7, 7, 624, 16, 7, 0, 0, 0, 1e-6)        # wider than the fused kernel
+    assert built_lib.hrf_attn_pack(C.byref(d), *([buf] * 13), buf) == -2
+    assert built_lib.hrf_attn_blob_floats(None) == 0
+    f = _lib.FfnDesc(1, 8, 8, 18, 70, 0, 1e-6)                   # hidden not a multiple of 4
+    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None) == -2
+    f = _lib.FfnDesc(1, 8, 8, 18, 72, 0, 1e-6)
+    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None) == -1   # null pointers
+
+
+def test_attn_packer_layout(built_lib):
+    """q is pre-scaled, weights are k-major, out_proj rows follow the head-padded
+    layout, the rpb table is transposed to (heads, 169)."""
+    from blob_emul import AttnLayout
+    from hrfuser_b200 import ops
+    Cc, heads = 36, 2
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    lnq, lnk = (r(Cc), r(Cc)), (r(Cc), r(Cc))
+    wq, wk, wv, wo = r(Cc, Cc), r(Cc, Cc), r(Cc, Cc), r(Cc, Cc)
+    bq, bk, bv, bo = r(Cc), r(Cc), r(Cc), r(Cc)
+    table = r(169, heads)
+    blob = ops.pack_attn(Cc, heads, 7, lnq, lnk, wq, bq, wk, bk, wv, bv, wo, bo, table)
+    L = AttnLayout(Cc, heads, 7)
+    assert blob.numel() == L.total
+    scale = (Cc // heads) ** -0.5
+    sec = lambda n, sz: blob[L.o[n]:L.o[n] + sz]
+    assert torch.allclose(sec('wq', Cc * Cc).view(Cc, Cc), wq.t() * scale)
+    assert torch.allclose(sec('bq', Cc), bq * scale)
+    assert torch.equal(sec('wk', Cc * Cc).view(Cc, Cc), wk.t())
+    assert torch.equal(sec('lnkv_b', Cc), lnk[1])
+    wo_p = sec('wo', L.KO * Cc).view(L.KO, Cc)
+    hd, hdp = L.hd, L.hdp
+    for h in range(heads):
+        assert torch.equal(wo_p[h * hdp:h * hdp + hd], wo.t()[h * hd:(h + 1) * hd])
+        assert wo_p[h * hdp + hd:(h + 1) * hdp].abs().sum() == 0
+    assert torch.equal(sec('rpb', heads * 169).view(heads, 169), table.t())
+
+
+def test_inference_without_gpu_fails_loudly():
+    import copy
+    from hrfuser_b200 import HRFuserHRFormerBased, tiny_cfg
+    c = copy.deepcopy(tiny_cfg(2))
+    c.pop('type')
+    net = HRFuserHRFormerBased(**c).eval()
+    x = torch.zeros(1, 3, 32, 32)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.HrfError, match='no CPU'):
+            with torch.no_grad():
+                net(x, [x, x])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_lib.HrfError, match='not built'):
+        _lib.load()

@@ -1,0 +1,116 @@
+"""Host logic without a GPU: the C packers + the engine wiring, evaluated through
+a blob-level CPU emulation of the device ops (tests/blob_emul.py), must
+reproduce the reference goldens; the torch training path must too."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import blob_emul
+from helpers import rel_err
+from hrfuser_b200 import HRFuserHRFormerBased, backbone_cfg, tiny_cfg
+from hrfuser_b200.engine import BackboneEngine
+from hrfuser_b200.utils import randomize_parameters, synthetic_inputs
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+E2E = np.load(os.path.join(G, 'e2e.npz'))
+
+
+def _net(cfg, seed=1):
+    c = copy.deepcopy(cfg)
+    c.pop('type')
+    net = HRFuserHRFormerBased(**c)
+    randomize_parameters(net, seed)
+    net.eval()
+    return net
+
+
+def test_hrfuser_b_wide_branches_are_refused_not_faked(built_lib):
+    """Round-1 gap: the fused kernels cover C <= 252; HRFuser-B's
+    312/624-wide branches must raise, not silently fall back."""
+    from hrfuser_b200 import _lib
+    net = _net(backbone_cfg('b', 'nus'))
+    with pytest.raises(_lib.HrfError, match='too wide'):
+        BackboneEngine(net, 'fp32', device_ops=blob_emul)
+
+
+@pytest.mark.parametrize('tag,v,d,mc', [('t_nus', 't', 'nus', (3, 3)), ('t_stf', 't', 'stf', (3, 2, 1))])
+def test_engine_wiring_and_packers_vs_reference_golden(built_lib, tag, v, d, mc):
+    net = _net(backbone_cfg(v, d))
+    H, W = (int(t) for t in E2E[tag + '_hw'])
+    x, mods = synthetic_inputs(1, H, W, mc, seed=3)
+    eng = BackboneEngine(net, 'fp32', device_ops=blob_emul)
+    out = eng.forward(x, mods)
+    assert len(out) == 4
+    for i, y in enumerate(out):
+        assert y.dtype == torch.float32 and y.is_contiguous()
+        assert rel_err(y, torch.from_numpy(E2E[f'{tag}_out{i}'])) < 3e-6
+
+
+@pytest.mark.parametrize('tag,v,d,mc', [('t_nus', 't', 'nus', (3, 3)), ('t_stf', 't', 'stf', (3, 2, 1))])
+def test_training_path_matches_reference_golden(tag, v, d, mc):
+    net = _net(backbone_cfg(v, d))
+    H, W = (int(t) for t in E2E[tag + '_hw'])
+    x, mods = synthetic_inputs(1, H, W, mc, seed=3)
+    with torch.no_grad():
+        out = net._forward_autograd(x, mods)          # eval-mode BN, torch ops
+    for i, y in enumerate(out):
+        assert rel_err(y, torch.from_numpy(E2E[f'{tag}_out{i}'])) < 2e-6
+
+
+def test_state_dict_layout_digest():
+    import hashlib
+    want = json.load(open(os.path.join(G, 'state_dict_layout.json')))['layouts']
+    for tag, (v, d) in {'t_nus': ('t', 'nus'), 't_stf': ('t', 'stf'), 'b_nus': ('b', 'nus')}.items():
+        c = backbone_cfg(v, d)
+        c.pop('type')
+        sd = HRFuserHRFormerBased(**c).state_dict()
+        txt = '\n'.join(f'{k} {tuple(t.shape)} {t.dtype}' for k, t in sd.items())
+        assert len(sd) == want[tag]['count']
+        assert hashlib.sha256(txt.encode()).hexdigest() == want[tag]['digest']
+
+
+def test_training_mode_backward_and_quirks():
+    torch.manual_seed(0)          # DropPath / Dropout masks
+    net = _net(tiny_cfg(2))
+    net.train()
+    x, mods = synthetic_inputs(4, 32, 32, (3, 3), seed=1)
+    out = net(x, mods)
+    sum(o.sum() for o in out).backward()
+    grads = {n: p.grad for n, p in net.named_parameters()}
+    # transition1[0] is applied conv-only: its BN never receives a gradient
+    assert grads['transition1.0.1.weight'] is None and grads['transition1.0.1.bias'] is None
+    assert grads['transition1.0.0.weight'] is not None
+    assert grads['fusion_a.0.attn.1.attn.relative_position_bias_table'].abs().sum() > 0
+    # drop_path_rate is ignored for HRFormer stages, DropPath(0.2) lives in fusion blocks only
+    from hrfuser_b200.modules import DropPath
+    dp = [n for n, m in net.named_modules() if isinstance(m, DropPath)]
+    assert dp and all(n.startswith('fusion_') for n in dp)
+
+
+def test_norm_eval_and_extra_mutation():
+    cfg = tiny_cfg(2)
+    c = copy.deepcopy(cfg)
+    c.pop('type')
+    c['norm_eval'] = True
+    net = HRFuserHRFormerBased(**c)
+    net.train()
+    assert all(not m.training for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    assert c['extra']['stage3']['drop_path_rates'] == [0.0] * 2
+    assert c['extra']['LidarStageC']['drop_path_rates'] is c['extra']['stage3']['drop_path_rates']
+
+
+def test_bad_configs_raise():
+    c = copy.deepcopy(tiny_cfg(2))
+    c.pop('type')
+    c['extra']['ModFusionA']['block'] = 'NOPE'
+    with pytest.raises(Exception):
+        HRFuserHRFormerBased(**c)
+    c = copy.deepcopy(tiny_cfg(2))
+    c.pop('type')
+    c['extra']['stage2']['num_channels'] = (18,)
+    with pytest.raises(AssertionError):
+        HRFuserHRFormerBased(**c)
