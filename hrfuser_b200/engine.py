@@ -309,3 +309,35 @@ class BackboneEngine:
                 xs, _ = self._fuse('d', ys, stream)
                 nchw = [self.ops.fuse_sum(t, relu=True, nchw_out=True)[1] for t in xs]
             return nchw
+
+
+class GraphedForward:
+    """One CUDA graph of the whole backbone forward for fixed input tensors.
+
+    The reference is launch-bound (~3 000 kernels per forward, SURVEY.md section
+    3.2); replaying a captured graph removes the Python and launch overhead of
+    the ~700 launches this engine still issues.  `x` / `mods` are the static
+    input buffers: write new data into them (copy_) and call the object."""
+
+    def __init__(self, engine, x, mods, pool=None, warmup=2):
+        self.engine, self.x, self.mods = engine, x, list(mods)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                engine.forward(self.x, self.mods)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.out = engine.forward(self.x, self.mods)
+        self.launches = ops.launch_count() - n0      # hrfuser_b200 kernels per replay
+
+    def pool(self):
+        return self.graph.pool()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out

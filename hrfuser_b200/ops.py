@@ -4,6 +4,7 @@ Activations are channels-last token tensors of shape (B, H, W, C), contiguous,
 fp32 or bf16, on a CUDA device.  Packed weights are fp32 blobs produced by the
 `pack_*` helpers (host side, via the library's own packers) and uploaded once.
 """
+import contextlib
 import ctypes as C
 
 import torch
@@ -47,6 +48,52 @@ def _stream():
 def _check_act(x, name='x'):
     if not (x.is_cuda and x.dim() == 4 and x.is_contiguous()):
         raise ValueError(f'{name} must be a contiguous CUDA (B,H,W,C) tensor')
+
+
+class Recorder:
+    """Per-call CUDA-event timing of the ops (used by bench.py for the roofline
+    lines).  Events are recorded on the launching stream around each C-ABI call."""
+
+    def __init__(self):
+        self.calls = []          # (kind, meta dict, start event, end event)
+
+    def summary(self):
+        """-> {(kind, C): dict(calls, total_ms, avg_ms, bytes, flops)} after a sync"""
+        out = {}
+        for kind, meta, a, b in self.calls:
+            g = out.setdefault((kind, meta['C']), dict(calls=0, total_ms=0.0, bytes=0.0, flops=0.0))
+            g['calls'] += 1
+            g['total_ms'] += a.elapsed_time(b)
+            g['bytes'] += meta['bytes']
+            g['flops'] += meta['flops']
+        for g in out.values():
+            g['avg_ms'] = g['total_ms'] / g['calls']
+        return out
+
+
+_RECORDER = None
+
+
+@contextlib.contextmanager
+def record():
+    global _RECORDER
+    prev, _RECORDER = _RECORDER, Recorder()
+    try:
+        yield _RECORDER
+    finally:
+        _RECORDER = prev
+
+
+@contextlib.contextmanager
+def _timed(kind, **meta):
+    if _RECORDER is None:
+        yield
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    yield
+    b.record()
+    _RECORDER.calls.append((kind, meta, a, b))
 
 
 def _ptr_array(tensors):
@@ -127,8 +174,15 @@ def window_attention(x, kv, blobs, heads, win=7, with_pad_mask=False, eps=1e-6, 
     B, H, W, Cc = x.shape
     out = torch.empty_like(x) if out is None else out
     d = attn_desc(B, H, W, Cc, heads, len(kv), x.dtype, win, with_pad_mask, eps)
-    check(lib.hrf_window_attn_fwd(C.byref(d), x.data_ptr(), _ptr_array(kv), _ptr_array(blobs),
-                                  out.data_ptr(), _stream()))
+    # algorithmic cost: per token and modality pass,
+    # FLOPs 8C^2 + 4*S*C (S = win^2 keys), bytes 2C (LSA) / 3C (MWCA) elements
+    n, S, s = B * H * W, win * win, x.element_size()
+    passes = max(1, len(kv))
+    with _timed('mwca' if kv else 'lsa', C=Cc, launches=passes,
+                bytes=float(n * passes * (3 if kv else 2) * Cc * s),
+                flops=float(n * passes * (8 * Cc * Cc + 4 * S * Cc))):
+        check(lib.hrf_window_attn_fwd(C.byref(d), x.data_ptr(), _ptr_array(kv), _ptr_array(blobs),
+                                      out.data_ptr(), _stream()))
     return out
 
 
@@ -138,7 +192,11 @@ def mixffn(x, blob, hidden, eps=1e-6, out=None):
     B, H, W, Cc = x.shape
     out = torch.empty_like(x) if out is None else out
     d = FfnDesc(B, H, W, Cc, hidden, _dtype_code(x), eps)
-    check(lib.hrf_mixffn_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    n = B * H * W
+    with _timed('mixffn', C=Cc, launches=1, bytes=float(n * 2 * Cc * x.element_size()),
+                flops=float(n * (4 * Cc * hidden + 18 * hidden))):
+        check(lib.hrf_mixffn_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(),
+                                 _stream()))
     return out
 
 
@@ -148,7 +206,10 @@ def pointwise(x, blob, cout, relu=False):
     B, H, W, Cin = x.shape
     out = x.new_empty(B, H, W, cout)
     d = PwDesc(B, H, W, Cin, cout, _dtype_code(x), int(relu))
-    check(lib.hrf_pw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    n = B * H * W
+    with _timed('pw', C=Cin, launches=1, bytes=float(n * (Cin + cout) * x.element_size()),
+                flops=float(2 * n * Cin * cout)):
+        check(lib.hrf_pw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
     return out
 
 
@@ -158,7 +219,12 @@ def dw_down(x, blob, cout, relu=False):
     B, H, W, Cin = x.shape
     out = x.new_empty(B, (H + 1) // 2, (W + 1) // 2, cout)
     d = DwPwDesc(B, H, W, Cin, cout, _dtype_code(x), int(relu))
-    check(lib.hrf_dwpw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    no = out.shape[0] * out.shape[1] * out.shape[2]
+    with _timed('dwpw', C=Cin, launches=1,
+                bytes=float((B * H * W * Cin + no * cout) * x.element_size()),
+                flops=float(no * (18 * Cin + 2 * Cin * cout))):
+        check(lib.hrf_dwpw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(),
+                               _stream()))
     return out
 
 
@@ -180,8 +246,14 @@ def fuse_sum(x, ups=(), sames=(), relu=True, nchw_out=False):
     d.n_same, d.relu = len(sames), int(relu)
     out = torch.empty_like(x)
     nchw = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device) if nchw_out else None
-    check(lib.hrf_fuse_sum_fwd(C.byref(d), x.data_ptr(), _ptr_array(ups), _ptr_array(sames),
-                               out.data_ptr(), nchw.data_ptr() if nchw_out else None, _stream()))
+    s_ = x.element_size()
+    nbytes = x.numel() * s_ * (2 + len(sames)) + sum(u.numel() for u in ups) * s_ + \
+        (x.numel() * 4 if nchw_out else 0)
+    with _timed('fuse_sum', C=Cc, launches=1, bytes=float(nbytes),
+                flops=float(x.numel() * (1 + len(sames) + 8 * len(ups)))):
+        check(lib.hrf_fuse_sum_fwd(C.byref(d), x.data_ptr(), _ptr_array(ups), _ptr_array(sames),
+                                   out.data_ptr(), nchw.data_ptr() if nchw_out else None,
+                                   _stream()))
     return (out, nchw) if nchw_out else out
 
 
