@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "hrfuse.cuh"
 #include "mixffn.cuh"
+#include "umma_selftest.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -297,6 +298,12 @@ int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
   if (d->dtype == HRF_F32) return launch_fuse<float>(p, (cudaStream_t)stream);
   if (d->dtype == HRF_BF16) return launch_fuse<__nv_bfloat16>(p, (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "fuse_fwd: dtype");
+}
+
+int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t b_mn_major,
+                      void* stream) {
+  HRF_REQUIRE(A && B && D, HRF_EINVAL, "selftest: null pointer");
+  return launch_umma_selftest(A, B, D, N, K, b_mn_major, (cudaStream_t)stream);
 }
 
 int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, const void* src,

@@ -156,6 +156,13 @@ typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_
 int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
                      const void* const* same, void* out, float* out_nchw_f32, void* stream);
 
+/* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
+ * through the same descriptor helpers the fused kernels use.  B is [N][K]
+ * (b_mn_major = 0, K-major operand) or [K][N] (b_mn_major = 1, MN-major operand).
+ * N, K multiples of 16, <= 256.  Device pointers. */
+int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K,
+                      int32_t b_mn_major, void* stream);
+
 /* Layout converters at the boundary of the path. */
 int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t src_dtype,
                      const void* src, int32_t dst_dtype, void* dst, void* stream);
