@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -12,6 +13,7 @@
 #include "hrfuse.cuh"
 #include "mixffn.cuh"
 #include "umma_selftest.cuh"
+#include "window_attn_tc.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -39,7 +41,23 @@ cudaError_t ensure_smem(const void* kern, size_t bytes) {
   if (e == cudaSuccess) done[kern] = bytes;
   return e;
 }
+// HRF_DISABLE_TC=1 routes bf16 problems to the SIMT kernels (A/B comparisons)
+bool tc_disabled() {
+  static const bool off = [] {
+    const char* e = std::getenv("HRF_DISABLE_TC");
+    return e && e[0] == '1';
+  }();
+  return off;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// round-to-nearest-even fp32 -> bf16 bits (finite inputs)
+static inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
 
 // eval-mode BatchNorm as y = x*scale + shift
 static void bn_affine(const float* const bn[4], int n, float eps, std::vector<float>& scale,
@@ -144,6 +162,32 @@ int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b
   if (rpb_table)
     for (int h = 0; h < L.heads; ++h)
       for (int t = 0; t < L.T; ++t) blob[L.o_rpb + (size_t)h * L.T + t] = rpb_table[(size_t)t * L.heads + h];
+  // ---- tensor-core sections (bf16 operand tiles, head-padded) -------------------
+  {
+    const int HDP = L.tc_HDP, KC = L.tc_KC, NQ = L.tc_NQ, NOUT = L.tc_NOUT;
+    float* bias = blob + L.o_tc_bias;
+    uint16_t* tq = reinterpret_cast<uint16_t*>(blob + L.o_tc_wq);
+    uint16_t* tk = reinterpret_cast<uint16_t*>(blob + L.o_tc_wk);
+    uint16_t* tv = reinterpret_cast<uint16_t*>(blob + L.o_tc_wv);
+    uint16_t* to = reinterpret_cast<uint16_t*>(blob + L.o_tc_wo);
+    for (int h = 0; h < L.heads; ++h)
+      for (int dd = 0; dd < L.hd; ++dd) {
+        const int n = h * L.hd + dd, np = h * HDP + dd;      // feature, head-padded feature
+        bias[np] = (bq ? bq[n] : 0.f) * scale;
+        bias[NQ + np] = bk ? bk[n] : 0.f;
+        bias[2 * NQ + np] = bv ? bv[n] : 0.f;
+        for (int k = 0; k < C; ++k) {
+          const size_t e = umma::tile_off(np, k, NQ) / 2;
+          tq[e] = f32_to_bf16(wq[(size_t)n * C + k] * scale);
+          tk[e] = f32_to_bf16(wk[(size_t)n * C + k]);
+          tv[e] = f32_to_bf16(wv[(size_t)n * C + k]);
+        }
+        for (int n2 = 0; n2 < C; ++n2)                       // out_proj: rows = out feature, K = padded O
+          to[umma::tile_off(n2, np, NOUT) / 2] = f32_to_bf16(wo[(size_t)n2 * C + n]);
+      }
+    for (int c = 0; c < C; ++c) bias[3 * NQ + c] = bo ? bo[c] : 0.f;
+    (void)KC;
+  }
   return HRF_OK;
 }
 
@@ -166,8 +210,11 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
     HRF_REQUIRE(p.z && p.blob, HRF_EINVAL, "attn_fwd: null kv/blob %d", k);
     p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.heads = d->heads; p.win = d->win;
     p.cross = d->n_kv > 0; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
-    rc = d->dtype == HRF_F32 ? launch_window_attn<float>(p, st)
-                             : launch_window_attn<__nv_bfloat16>(p, st);
+    if (d->dtype == HRF_BF16 && attn_tc_supported(p) && !tc_disabled())
+      rc = launch_window_attn_tc(p, st);
+    else
+      rc = d->dtype == HRF_F32 ? launch_window_attn<float>(p, st)
+                               : launch_window_attn<__nv_bfloat16>(p, st);
     if (rc) return rc;
   }
   return HRF_OK;

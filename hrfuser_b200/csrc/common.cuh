@@ -14,6 +14,7 @@ constexpr int kWarp = 32;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+bool tc_disabled();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (kept out of
 // CUDA-graph capture after the first, warm-up, call)
 cudaError_t ensure_smem(const void* kern, size_t bytes);

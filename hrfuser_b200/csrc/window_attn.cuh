@@ -17,6 +17,10 @@ struct AttnLayout {
   int C, heads, hd, hdp, Cp, KO, S, T;  // T = (2*win-1)^2 table rows
   int o_lnq_w, o_lnq_b, o_lnkv_w, o_lnkv_b;
   int o_wq, o_bq, o_wk, o_bk, o_wv, o_bv, o_wo, o_bo, o_rpb;
+  // tensor-core (bf16) sections: head-padded fp32 biases, then bf16 operand
+  // tiles in the chunk-major layout of umma.cuh (offsets in floats)
+  int tc_HDP, tc_KC, tc_NQ, tc_NOUT;
+  int o_tc_bias, o_tc_wq, o_tc_wk, o_tc_wv, o_tc_wo;
   int total;
   // shared-memory strides
   int ldx, ldq;
@@ -31,6 +35,12 @@ struct AttnLayout {
     o_wv = o; o += Cp * C; o = round_up(o, 4); o_bv = o; o += c4;
     o_wo = o; o += KO * C; o = round_up(o, 4); o_bo = o; o += c4;
     o_rpb = o; o += round_up(heads * T, 4);
+    tc_HDP = round_up(hd, 16); tc_KC = round_up(C, 16); tc_NQ = heads * tc_HDP; tc_NOUT = tc_KC;
+    o_tc_bias = o; o += 3 * tc_NQ + tc_NOUT;                 // bq|bk|bv (head padded), bo
+    o_tc_wq = o; o += tc_NQ * tc_KC / 2;                     // bf16 [KC/8][NQ][8]
+    o_tc_wk = o; o += tc_NQ * tc_KC / 2;
+    o_tc_wv = o; o += tc_NQ * tc_KC / 2;
+    o_tc_wo = o; o += tc_NOUT * tc_NQ / 2;                   // bf16 [KO/8][NOUT][8], KO == NQ
     total = o;
     ldx = stride4odd(Cp);
     ldq = stride4odd(KO);

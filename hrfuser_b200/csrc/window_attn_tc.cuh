@@ -1,0 +1,444 @@
+// Fused window attention (LSA / MWCA) on the tcgen05 tensor cores -- bf16 mode.
+//
+// One CTA (128 threads) owns a PAIR of windows per iteration: thread r is row r of
+// every M=128 tile, rows 0-63 = window A slots (49 real + 15 dead), rows 64-127 =
+// window B.  Per pair:
+//
+//   LN prologue       per-thread LayerNorm of its own token (no shuffles), written
+//                     as bf16 into the XN (and ZN) operand tile; pad slots -> zeros
+//   QKV  (UMMA)       [128 x KC] x Wq/Wk/Wv^T  -> TMEM  (N = heads*32 each)
+//   epilogue          + bias, bf16 -> Q / K / V operand tiles per head (hd 18 -> 32)
+//   per head:
+//     S  (UMMA)       Q_h [128x32] x [K_A;K_B]^T -> TMEM 128 cols; each row reads only
+//                     the 64 columns of its own window
+//     softmax         in registers: + rel-pos bias (table lookups with immediate
+//                     offsets), max, ex2, sum; P (unnormalised, bf16) -> 128x64 tile
+//     PV (UMMA)       P x V_A and P x V_B (MN-major V, K = 64 keys) -> 2x32 TMEM cols;
+//                     each row keeps the product with its own window's V
+//     epilogue        x 1/sum, bf16 -> O operand tile
+//   out-proj (UMMA)   O [128 x heads*32] x Wo^T -> TMEM
+//   epilogue          + bias + residual (+ kv residual), bf16 -> global
+//
+// Pad / partition / merge / crop are address arithmetic (same closed forms as
+// window_attn.cuh).  Accumulation, LayerNorm statistics and softmax are fp32.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+#include "window_attn.cuh"
+
+namespace hrf {
+
+template <int C, int HEADS, bool CROSS>
+struct AttnTc {
+  static constexpr int HD = C / HEADS;
+  static constexpr int HDP = (HD + 15) / 16 * 16;
+  static constexpr int KC = (C + 15) / 16 * 16;
+  static constexpr int NQ = HEADS * HDP;
+  static constexpr int NOUT = KC;
+  static constexpr int WIN = 7, S = 49;
+  static_assert(HDP == 32, "tensor-core attention kernel is written for head_dim <= 32");
+  static_assert(NQ <= 256 && NOUT <= 256, "one UMMA per projection");
+  static constexpr int XT = 128 * (KC > NQ ? KC : NQ) * 2;   // XN tile, later aliased by the O tile
+  static constexpr int WQ_B = NQ * KC * 2, WO_B = NOUT * NQ * 2;
+  static constexpr int HT = 128 * HDP * 2;                    // one head's Q / K / V tile
+  // shared-memory map (bytes)
+  static constexpr int o_wq = 0, o_wk = o_wq + WQ_B, o_wv = o_wk + WQ_B, o_wo = o_wv + WQ_B;
+  static constexpr int o_xn = o_wo + WO_B;
+  static constexpr int o_zn = o_xn + XT;
+  static constexpr int o_q = o_zn + (CROSS ? 128 * KC * 2 : 0);
+  static constexpr int o_k = o_q + HEADS * HT, o_v = o_k + HEADS * HT;
+  static constexpr int o_p = o_v + HEADS * HT;                // 128 x 64 bf16
+  static constexpr int o_bias = o_p + 128 * 64 * 2;           // fp32: bq|bk|bv|bo
+  static constexpr int o_rpb = o_bias + (3 * NQ + NOUT) * 4;  // fp32 [HEADS][169]
+  static constexpr int o_ln = o_rpb + ((HEADS * 169 + 3) / 4 * 4) * 4;   // fp32 4 x C4
+  static constexpr int C4 = (C + 3) / 4 * 4;
+  static constexpr int SMEM = o_ln + 4 * C4 * 4;
+  static constexpr int TMEM_COLS = (3 * NQ <= 128) ? 128 : (3 * NQ <= 256 ? 256 : 512);
+};
+
+// one token row: C bf16 -> fp32 registers, widest aligned vector loads
+template <int C>
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, float* x) {
+  if constexpr ((C * 2) % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        x[i * 8 + j * 2] = f.x; x[i * 8 + j * 2 + 1] = f.y;
+      }
+    }
+  } else if constexpr ((C * 2) % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(src) + i);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      x[i * 4] = a.x; x[i * 4 + 1] = a.y; x[i * 4 + 2] = b.x; x[i * 4 + 3] = b.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+      x[i * 2] = a.x; x[i * 2 + 1] = a.y;
+    }
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float* x) {
+  uint32_t w[C / 2];
+#pragma unroll
+  for (int i = 0; i < C / 2; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if constexpr ((C * 2) % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i)
+      reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  } else if constexpr ((C * 2) % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) reinterpret_cast<uint2*>(dst)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) reinterpret_cast<uint32_t*>(dst)[i] = w[i];
+  }
+}
+
+// LayerNorm of one row held in registers -> bf16 chunks of an R=128 operand tile
+template <int C, int KC>
+__device__ __forceinline__ void ln_row_to_tile(const float* x, const float* gamma,
+                                               const float* beta, float eps, unsigned char* tile,
+                                               int row) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) s += x[c];
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) { const float d = x[c] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+  for (int ch = 0; ch < KC / 8; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      v[j] = (c < C) ? fmaf((x[c < C ? c : 0] - mean) * rstd, gamma[c < C ? c : 0], beta[c < C ? c : 0]) : 0.f;
+    }
+    umma::st_chunk(tile, row, ch, 128, v);
+  }
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int C, int HEADS, bool CROSS>
+__global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
+  using namespace umma;
+  using K = AttnTc<C, HEADS, CROSS>;
+  constexpr int HDP = K::HDP, KC = K::KC, NQ = K::NQ, NOUT = K::NOUT, WIN = K::WIN, S = K::S;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t valid_bits[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = tid >> 6, i = tid & 63;            // window of the pair, slot in the window
+  const AttnLayout L(C, HEADS, WIN);
+  const float* blob = p.blob;
+  float* sBias = reinterpret_cast<float*>(sm + K::o_bias);
+  float* sRpb = reinterpret_cast<float*>(sm + K::o_rpb);
+  float* sLn = reinterpret_cast<float*>(sm + K::o_ln);
+
+  // ---- one-time setup: weights + small tables -> smem, TMEM, barrier -----------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_wq);   // wq|wk|wv|wo contiguous
+    uint4* dst = reinterpret_cast<uint4*>(sm + K::o_wq);
+    constexpr int n16 = (3 * K::WQ_B + K::WO_B) / 16;
+    for (int e = tid; e < n16; e += 128) dst[e] = __ldg(src + e);
+    for (int e = tid; e < 3 * NQ + NOUT; e += 128) sBias[e] = __ldg(blob + L.o_tc_bias + e);
+    for (int e = tid; e < HEADS * 169; e += 128) sRpb[e] = __ldg(blob + L.o_rpb + e);
+    for (int e = tid; e < K::C4; e += 128) {
+      sLn[e] = __ldg(blob + L.o_lnq_w + e);
+      sLn[K::C4 + e] = __ldg(blob + L.o_lnq_b + e);
+      sLn[2 * K::C4 + e] = __ldg(blob + L.o_lnkv_w + e);
+      sLn[3 * K::C4 + e] = __ldg(blob + L.o_lnkv_b + e);
+    }
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);   // this thread's TMEM lane
+  uint32_t phase = 0;
+
+  const uint32_t a_wq = smem_u32(sm + K::o_wq), a_wk = smem_u32(sm + K::o_wk);
+  const uint32_t a_wv = smem_u32(sm + K::o_wv), a_wo = smem_u32(sm + K::o_wo);
+  const uint32_t a_xn = smem_u32(sm + K::o_xn), a_zn = smem_u32(sm + K::o_zn);
+  const uint32_t a_q = smem_u32(sm + K::o_q), a_k = smem_u32(sm + K::o_k);
+  const uint32_t a_v = smem_u32(sm + K::o_v), a_p = smem_u32(sm + K::o_p);
+
+  const int nWh = ceil_div(p.H, WIN), nWw = ceil_div(p.W, WIN);
+  const int pad_h = nWh * WIN - p.H, pad_w = nWw * WIN - p.W;
+  const int pad_t = pad_h / 2, pad_l = pad_w / 2;
+  const bool use_mask = p.pad_mask && pad_h > 0 && pad_w > 0;
+  const int n_windows = p.B * nWh * nWw;
+  const int n_tiles = (n_windows + 1) / 2;
+  const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(p.xq);
+  const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(p.z);
+  const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(p.resid);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+
+  // relative-position bias: value for (query slot i, key slot j) is
+  // table[(ih-jh+6)*13 + (iw-jw+6)] = table[rp_base - (jh*13+jw)]
+  const int ic = i < S ? i : S - 1;
+  const int rp_base = (ic / WIN + WIN - 1) * (2 * WIN - 1) + (ic % WIN) + WIN - 1;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- token of this row ----------------------------------------------------
+    const int wdx = tile * 2 + g;
+    int tok = -1;
+    if (wdx < n_windows && i < S) {
+      const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
+      const int h = wy * WIN + i / WIN - pad_t, w = wx * WIN + i % WIN - pad_l;
+      if (h >= 0 && h < p.H && w >= 0 && w < p.W) tok = (b * p.H + h) * p.W + w;
+    }
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, tok >= 0);
+      if (lane == 0) valid_bits[warp] = bal;
+    }
+    // ---- LN prologue -------------------------------------------------------------
+    if (tok >= 0) {
+      float x[C];
+      load_row_bf16<C>(xq + (size_t)tok * C, x);
+      ln_row_to_tile<C, KC>(x, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+      if (CROSS) {
+        load_row_bf16<C>(zz + (size_t)tok * C, x);
+        ln_row_to_tile<C, KC>(x, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps, sm + K::o_zn, tid);
+      }
+    } else {
+      const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < KC / 8; ++ch) {
+        st_chunk(sm + K::o_xn, tid, ch, 128, zero);
+        if (CROSS) st_chunk(sm + K::o_zn, tid, ch, 128, zero);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- q / k / v projections ------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idq = idesc_bf16(128, NQ, false, false);
+      const uint32_t a_kv = CROSS ? a_zn : a_xn;
+#pragma unroll
+      for (int s = 0; s < KC / 16; ++s)
+        mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wq, NQ, s), idq, s > 0);
+#pragma unroll
+      for (int s = 0; s < KC / 16; ++s)
+        mma_bf16(tmem + NQ, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wk, NQ, s), idq, s > 0);
+#pragma unroll
+      for (int s = 0; s < KC / 16; ++s)
+        mma_bf16(tmem + 2 * NQ, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wv, NQ, s), idq, s > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+      unsigned char* base = sm + (part == 0 ? K::o_q : part == 1 ? K::o_k : K::o_v);
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        float v[32];
+        tmem_ld32(trow + part * NQ + h * HDP, v);
+        tmem_ld_wait();
+        const float* bs = sBias + part * NQ + h * HDP;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] += bs[c];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) st_chunk(base + h * K::HT, tid, ch, 128, v + 8 * ch);
+      }
+    }
+
+    const unsigned long long vmask =
+        (unsigned long long)valid_bits[2 * g] | ((unsigned long long)valid_bits[2 * g + 1] << 32);
+    const bool mask_me = use_mask && wdx < n_windows;
+    float inv_sum[HEADS];
+
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) {
+      // ---- S = Q_h [K_A;K_B]^T -------------------------------------------------------
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t ids = idesc_bf16(128, 128, false, false);
+#pragma unroll
+        for (int s = 0; s < HDP / 16; ++s)
+          mma_bf16(tmem, desc_kmajor(a_q + h * K::HT, 128, s), desc_kmajor(a_k + h * K::HT, 128, s),
+                   ids, s > 0);
+        mma_commit(&bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+
+      // ---- softmax over the 49 keys of this row's window ---------------------------
+      float sc[56];
+      const uint32_t scol = trow + g * 64;
+      tmem_ld32(scol, sc);
+      tmem_ld16(scol + 32, sc + 32);
+      tmem_ld8(scol + 48, sc + 48);
+      tmem_ld_wait();
+      const float* tb = sRpb + h * 169 + rp_base;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        float v = sc[j] + tb[-((j / WIN) * (2 * WIN - 1) + (j % WIN))];
+        if (mask_me && !((vmask >> j) & 1ull)) v = -INFINITY;
+        sc[j] = v;
+        mx = fmaxf(mx, v);
+      }
+      float sum = 0.f;
+      const float mxl = mx * 1.4426950408889634f;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const float e = fast_exp2(fmaf(sc[j], 1.4426950408889634f, -mxl));
+        sc[j] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int j = S; j < 56; ++j) sc[j] = 0.f;
+      inv_sum[h] = 1.0f / sum;
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) st_chunk(sm + K::o_p, tid, ch, 128, sc + 8 * ch);
+      {
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        st_chunk(sm + K::o_p, tid, 7, 128, zero);
+      }
+
+      // ---- O = P V (both windows' V; each row keeps its own) -------------------------
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t ido = idesc_bf16(128, HDP, false, true);
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2)
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            mma_bf16(tmem + g2 * HDP, desc_kmajor(a_p, 128, s),
+                     desc_mnmajor(a_v + h * K::HT + g2 * 64 * 16, 128, s), ido, s > 0);
+        mma_commit(&bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        float o[32];
+        tmem_ld32(trow + g * HDP, o);
+        tmem_ld_wait();
+        const float is = inv_sum[h];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] *= is;
+        // O tile aliases the XN tile (dead since the projections completed)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) st_chunk(sm + K::o_xn, tid, h * 4 + ch, 128, o + 8 * ch);
+      }
+    }
+
+    // ---- output projection -------------------------------------------------------------
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idy = idesc_bf16(128, NOUT, false, false);
+#pragma unroll
+      for (int s = 0; s < NQ / 16; ++s)
+        mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wo, NOUT, s), idy, s > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      float y[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + c0, y + c0);
+      tmem_ld_wait();
+      if (tok >= 0) {
+        float r[C];
+        load_row_bf16<C>(rs + (size_t)tok * C, r);
+        const float* bo = sBias + 3 * NQ;
+#pragma unroll
+        for (int c = 0; c < C; ++c) y[c] += bo[c] + r[c];
+        if (CROSS) {
+          load_row_bf16<C>(zz + (size_t)tok * C, r);
+#pragma unroll
+          for (int c = 0; c < C; ++c) y[c] += r[c];
+        }
+        store_row_bf16<C>(out + (size_t)tok * C, y);
+      }
+    }
+    // the next iteration's first barrier orders these TMEM reads before its MMAs
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);
+}
+
+template <int C, int HEADS>
+static int launch_attn_tc_ch(const AttnParams& p, cudaStream_t stream) {
+  const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
+  const int n_tiles = (n_windows + 1) / 2;
+  const int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+  if (p.cross) {
+    using K = AttnTc<C, HEADS, true>;
+    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, true>, K::SMEM));
+    window_attn_tc_kernel<C, HEADS, true><<<grid, 128, K::SMEM, stream>>>(p);
+  } else {
+    using K = AttnTc<C, HEADS, false>;
+    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, false>, K::SMEM));
+    window_attn_tc_kernel<C, HEADS, false><<<grid, 128, K::SMEM, stream>>>(p);
+  }
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// true when the tensor-core kernel covers this problem
+static bool attn_tc_supported(const AttnParams& p) {
+  if (p.win != 7 || p.C % p.heads != 0 || p.C / p.heads != 18) return false;
+  return p.C == 18 || p.C == 36;   // C = 72 / 144 need streamed weights (smem): SIMT kernel for now
+}
+
+static int launch_window_attn_tc(const AttnParams& p, cudaStream_t stream) {
+  switch (p.C) {
+    case 18: return launch_attn_tc_ch<18, 1>(p, stream);
+    case 36: return launch_attn_tc_ch<36, 2>(p, stream);
+  }
+  HRF_REQUIRE(false, HRF_EUNSUPPORTED, "attn_tc: C=%d", p.C);
+}
+
+}  // namespace hrf

@@ -43,6 +43,17 @@ class AttnLayout:
         o += c4
         names['rpb'] = o
         o += _ru(heads * self.T, 4)
+        # tensor-core sections (bf16 operand tiles; checked on the GPU, skipped here)
+        HDP, KC = _ru(self.hd, 16), _ru(C, 16)
+        NQ = heads * HDP
+        names['tc_bias'] = o
+        o += 3 * NQ + KC
+        for w in ('tc_wq', 'tc_wk', 'tc_wv'):
+            names[w] = o
+            o += NQ * KC // 2
+        names['tc_wo'] = o
+        o += KC * NQ // 2
+        self.tc = dict(HDP=HDP, KC=KC, NQ=NQ, NOUT=KC)
         self.total = o
         self.o = names
 

@@ -99,3 +99,40 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_lib.HrfError, match='not built'):
         _lib.load()
+
+
+def test_attn_packer_tensor_core_tiles(built_lib):
+    """bf16 operand tiles of the tcgen05 kernel: chunk-major [K/8][rows][8], heads
+    padded 18 -> 32, q pre-scaled, out_proj K index = padded O column."""
+    from blob_emul import AttnLayout
+    from hrfuser_b200 import ops
+    Cc, heads = 36, 2
+    g = torch.Generator().manual_seed(1)
+    r = lambda *s: torch.randn(*s, generator=g)
+    ln = (r(Cc), r(Cc))
+    wq, wk, wv, wo = r(Cc, Cc), r(Cc, Cc), r(Cc, Cc), r(Cc, Cc)
+    bq, bk, bv, bo = r(Cc), r(Cc), r(Cc), r(Cc)
+    blob = ops.pack_attn(Cc, heads, 7, ln, ln, wq, bq, wk, bk, wv, bv, wo, bo, r(169, heads))
+    L = AttnLayout(Cc, heads, 7)
+    HDP, KC, NQ, NOUT = (L.tc[k] for k in ('HDP', 'KC', 'NQ', 'NOUT'))
+    hd = Cc // heads
+    scale = hd ** -0.5
+
+    def tile(name, rows, cols):
+        raw = blob[L.o[name]:L.o[name] + rows * cols // 2].view(torch.bfloat16).float()
+        return raw.view(cols // 8, rows, 8).permute(1, 0, 2).reshape(rows, cols)   # -> [row][col]
+    pad_rows = torch.tensor([h * HDP + d for h in range(heads) for d in range(hd)])
+    for name, w, s in (('tc_wq', wq, scale), ('tc_wk', wk, 1.0), ('tc_wv', wv, 1.0)):
+        t = tile(name, NQ, KC)
+        assert torch.equal(t[pad_rows, :Cc], (w * s).bfloat16().float())
+        assert t[:, Cc:].abs().sum() == 0
+        keep = torch.zeros(NQ, dtype=torch.bool)
+        keep[pad_rows] = True
+        assert t[~keep].abs().sum() == 0
+    to = tile('tc_wo', NOUT, NQ)
+    assert torch.equal(to[:Cc][:, pad_rows], wo.bfloat16().float())
+    assert to[Cc:].abs().sum() == 0
+    bias = blob[L.o['tc_bias']:L.o['tc_bias'] + 3 * NQ + NOUT]
+    assert torch.allclose(bias[pad_rows], bq * scale)
+    assert torch.equal(bias[NQ + pad_rows], bk) and torch.equal(bias[2 * NQ + pad_rows], bv)
+    assert torch.equal(bias[3 * NQ:3 * NQ + Cc], bo)
