@@ -14,6 +14,7 @@
 #include "mixffn.cuh"
 #include "umma_selftest.cuh"
 #include "window_attn_tc.cuh"
+#include "mixffn_tc.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -263,6 +264,30 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
     blob[L.o_bd + j] = (bd ? bd[j] : 0.f) * s2[j] + t2[j];
     for (int n = 0; n < C; ++n) blob[L.o_w2 + (size_t)j * C + n] = w2[(size_t)n * Hd + j] * s3[n];
   }
+  // ---- tensor-core sections ------------------------------------------------------
+  if (L.tc_nchunk > 0) {
+    const int KC = L.tc_KC, NOUT = L.tc_NOUT;
+    float* f = blob + L.o_tc_f32;
+    uint16_t* tile1 = reinterpret_cast<uint16_t*>(blob + L.o_tc_w1);
+    uint16_t* tile2 = reinterpret_cast<uint16_t*>(blob + L.o_tc_w2);
+    for (int ch = 0; ch < L.tc_nchunk; ++ch) {
+      float* fb = f + (size_t)ch * 880;                       // b1[80] | wd[9][80] | bd[80]
+      uint16_t* w1t = tile1 + (size_t)ch * 80 * KC;           // B of fc1: rows = hidden ch, K = C
+      uint16_t* w2t = tile2 + (size_t)ch * NOUT * 80;         // B of fc2: rows = out ch, K = hidden ch
+      for (int jj = 0; jj < 72; ++jj) {
+        const int j = ch * 72 + jj;
+        fb[jj] = (b1 ? b1[j] : 0.f) * s1[j] + t1[j];
+        for (int t = 0; t < 9; ++t) fb[80 + t * 80 + jj] = wd[(size_t)j * 9 + t] * s2[j];
+        fb[800 + jj] = (bd ? bd[j] : 0.f) * s2[j] + t2[j];
+        for (int k = 0; k < C; ++k)
+          w1t[umma::tile_off(jj, k, 80) / 2] = f32_to_bf16(w1[(size_t)j * C + k] * s1[j]);
+        for (int n = 0; n < C; ++n)
+          w2t[umma::tile_off(n, jj, NOUT) / 2] = f32_to_bf16(w2[(size_t)n * Hd + j] * s3[n]);
+      }
+    }
+    float* b2p = f + (size_t)L.tc_nchunk * 880;
+    for (int c = 0; c < C; ++c) b2p[c] = (b2 ? b2[c] : 0.f) * s3[c] + t3[c];
+  }
   return HRF_OK;
 }
 
@@ -272,6 +297,8 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
   HRF_REQUIRE(x && blob && out, HRF_EINVAL, "ffn_fwd: null pointer");
   HRF_REQUIRE(x != out, HRF_EINVAL, "ffn_fwd: out must not alias x (3x3 halo reads)");
   FfnParams p{x, blob, out, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps};
+  if (d->dtype == HRF_BF16 && ffn_tc_supported(p) && !tc_disabled())
+    return launch_mixffn_tc(p, (cudaStream_t)stream);
   return d->dtype == HRF_F32 ? launch_mixffn<float>(p, (cudaStream_t)stream)
                              : launch_mixffn<__nv_bfloat16>(p, (cudaStream_t)stream);
 }

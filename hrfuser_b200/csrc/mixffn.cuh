@@ -31,10 +31,21 @@ struct FfnLayout {
     o_wd = o; o += 9 * hidden; o_bd = o; o += hidden;      // Wd  [9][hidden]
     o_w2 = o; o += hidden * C; o = round_up(o, 4);         // W2t [hidden][C]
     o_b2 = o; o += c4;
+    // tensor-core (bf16) sections, present when hidden splits into chunks of 72
+    // channels (every HRFuser-T width): per chunk, fp32 b1[80] | wd[9][80] | bd[80]
+    // (zero padded 72 -> 80), then b2[NOUT]; then bf16 operand tiles in the
+    // chunk-major layout of umma.cuh: W1 [KC/8][80][8] and W2 [80/8][NOUT][8] per chunk.
+    tc_KC = round_up(C, 16); tc_NOUT = tc_KC;
+    tc_nchunk = (hidden % 72 == 0) ? hidden / 72 : 0;
+    o_tc_f32 = o; o += tc_nchunk * (11 * 80) + (tc_nchunk ? tc_NOUT : 0);
+    o = round_up(o, 4);
+    o_tc_w1 = o; o += tc_nchunk * 80 * tc_KC / 2;
+    o_tc_w2 = o; o += tc_nchunk * tc_NOUT * 80 / 2;
     total = o;
     ldx = stride4odd(Cp);
     ldh = stride4odd(HC);
   }
+  int tc_KC, tc_NOUT, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2;
 };
 
 constexpr int kFfnThreads = 256;

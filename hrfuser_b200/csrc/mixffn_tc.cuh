@@ -1,0 +1,286 @@
+// Fused MixFFN on the tcgen05 tensor cores -- bf16 mode.
+//
+//   out = x + GELU(BN3(W2 * GELU(BN2(dw3x3(GELU(BN1(W1*LN(x)+b1)))+bd)) + b2))
+//
+// One CTA (256 threads) owns an 8 x 16 tile of output tokens per iteration:
+//   LN prologue   the 10 x 18 halo (180 tokens) is LayerNormed one token per thread
+//                 and written as two bf16 M=128 operand tiles
+//   per chunk of 72 hidden channels (hidden = 4C = 72 * nchunk):
+//     fc1 (UMMA)  2 x [128 x KC] x W1c^T -> TMEM (N = 80)
+//     epilogue    + b1, GELU, zero outside the image (that is what the reference's
+//                 zero-padded depthwise conv sees), bf16 -> H1 [9 chunks][180 tok][8]
+//     dw 3x3      SIMT on H1 (16-byte shared loads, fp32 accumulate), + bd, GELU,
+//                 bf16 -> H2 operand tile [128 x 80]
+//     fc2 (UMMA)  H2 x W2c^T accumulated over the chunks in TMEM (N = NOUT)
+//   epilogue      + b2, GELU, + residual, bf16 -> global
+// The 4C-wide hidden activation never leaves the SM.  BN is folded (eval mode).
+#pragma once
+#include "common.cuh"
+#include "mixffn.cuh"
+#include "umma.cuh"
+#include "window_attn_tc.cuh"   // load_row_bf16 / store_row_bf16 / ln_row_to_tile
+
+namespace hrf {
+
+template <int C>
+struct FfnTc {
+  static constexpr int HID = 4 * C, NCH = HID / 72;
+  static_assert(HID % 72 == 0, "hidden must split into 72-channel chunks");
+  static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
+  static constexpr int TH = 8, TW = 16, HH = TH + 2, HW = TW + 2, NHALO = HH * HW;   // 180
+  static constexpr int XT = 128 * KC * 2;            // one XN operand tile
+  static constexpr int H1R = 184;                    // rows per 8-channel chunk of H1 (>= 180)
+  // shared-memory map (bytes)
+  static constexpr int o_w1 = 0;                               // NCH tiles [80 x KC]
+  static constexpr int o_w2 = o_w1 + NCH * N1 * KC * 2;        // NCH tiles [NOUT x 80]
+  static constexpr int o_xn = o_w2 + NCH * NOUT * N1 * 2;      // 2 tiles
+  static constexpr int o_h1 = o_xn + 2 * XT;                   // 9 x H1R x 16
+  static constexpr int o_h2 = o_h1 + 9 * H1R * 16;             // 10 x 128 x 16
+  static constexpr int o_f32 = o_h2 + 10 * 128 * 16;           // per chunk 880 floats, then b2[NOUT]
+  static constexpr int o_ln = o_f32 + (NCH * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
+  static constexpr int C4 = (C + 3) / 4 * 4;
+  static constexpr int o_in = o_ln + 2 * C4 * 4;               // inside flags [256] bytes
+  static constexpr int SMEM = o_in + 256;
+  static constexpr int D_COLS = 2 * N1;                        // fc1 accumulators (two M tiles)
+  static constexpr int Y_COL = D_COLS;                         // fc2 accumulator
+  static constexpr int TMEM_COLS = (D_COLS + NOUT <= 256) ? 256 : 512;
+};
+
+// erf-form GELU from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the
+// hardware reciprocal / ex2; the negative branch avoids the 1 - (1 - tiny) cancellation.
+__device__ __forceinline__ float gelu_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float pe = poly * fast_exp2(-1.4426950408889634f * z * z);   // 1 - erf(|z|)
+  return 0.5f * x * (x >= 0.f ? 2.0f - pe : pe);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
+  using namespace umma;
+  using K = FfnTc<C>;
+  constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, q = warp & 3;          // warpgroup (M tile / channel parity), TMEM quadrant
+  const int row = q * 32 + lane;                   // TMEM lane == row of the M=128 tiles
+  const FfnLayout L(C, K::HID);
+  const float* blob = p.blob;
+  float* sF = reinterpret_cast<float*>(sm + K::o_f32);
+  float* sLn = reinterpret_cast<float*>(sm + K::o_ln);
+  unsigned char* sIn = sm + K::o_in;
+
+  // ---- one-time setup ---------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_w1);    // w1 | w2 contiguous
+    uint4* dst = reinterpret_cast<uint4*>(sm + K::o_w1);
+    constexpr int n16 = (NCH * N1 * KC * 2 + NCH * NOUT * N1 * 2) / 16;
+    for (int e = tid; e < n16; e += 256) dst[e] = __ldg(src + e);
+    for (int e = tid; e < NCH * 880 + NOUT; e += 256) sF[e] = __ldg(blob + L.o_tc_f32 + e);
+    for (int e = tid; e < K::C4; e += 256) {
+      sLn[e] = __ldg(blob + L.o_ln_w + e);
+      sLn[K::C4 + e] = __ldg(blob + L.o_ln_b + e);
+    }
+    // zero both XN tiles (rows 52..127 of tile 1 are never written again) and H2
+    // (its 10th chunk, channels 72..79, stays zero)
+    uint4* z = reinterpret_cast<uint4*>(sm + K::o_xn);
+    for (int e = tid; e < 2 * K::XT / 16; e += 256) z[e] = make_uint4(0, 0, 0, 0);
+    z = reinterpret_cast<uint4*>(sm + K::o_h2);
+    for (int e = tid; e < 10 * 128; e += 256) z[e] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  uint32_t phase = 0;
+  const uint32_t a_w1 = smem_u32(sm + K::o_w1), a_w2 = smem_u32(sm + K::o_w2);
+  const uint32_t a_xn = smem_u32(sm + K::o_xn), a_h2 = smem_u32(sm + K::o_h2);
+
+  const int tiles_x = ceil_div(p.W, K::TW), tiles_y = ceil_div(p.H, K::TH);
+  const int n_tiles = p.B * tiles_x * tiles_y;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y);
+    const int ty0 = ((tile / tiles_x) % tiles_y) * K::TH, tx0 = (tile % tiles_x) * K::TW;
+
+    // ---- LN prologue: halo token `tid` ---------------------------------------------
+    if (tid < K::NHALO) {
+      const int h = ty0 - 1 + tid / K::HW, w = tx0 - 1 + tid % K::HW;
+      const bool in = h >= 0 && h < p.H && w >= 0 && w < p.W;
+      sIn[tid] = in ? 1 : 0;
+      unsigned char* xt = sm + K::o_xn + (tid >> 7) * K::XT;
+      if (in) {
+        float v[C];
+        load_row_bf16<C>(x + ((size_t)(b * p.H + h) * p.W + w) * C, v);
+        ln_row_to_tile<C, KC>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+      } else {
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < KC / 8; ++ch) st_chunk(xt, tid & 127, ch, 128, zero);
+      }
+    }
+
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      // ---- fc1 on both halo M tiles ---------------------------------------------------
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t id1 = idesc_bf16(128, N1, false, false);
+        const uint32_t w1c = a_w1 + c * (N1 * KC * 2);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int s = 0; s < KC / 16; ++s)
+            mma_bf16(tmem + t * N1, desc_kmajor(a_xn + t * K::XT, 128, s), desc_kmajor(w1c, N1, s),
+                     id1, s > 0);
+        mma_commit(&bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+
+      // ---- epilogue 1: warpgroup wg owns M tile wg ----------------------------------
+      const float* fb = sF + c * 880;
+      {
+        const int t = wg * 128 + row;               // halo token
+        if (wg * 128 + q * 32 < K::NHALO) {         // warp-uniform: tcgen05.ld is warp-collective
+          float v[72];
+          const uint32_t col = trow + wg * N1;
+          tmem_ld32(col, v);
+          tmem_ld32(col + 32, v + 32);
+          tmem_ld8(col + 64, v + 64);
+          tmem_ld_wait();
+          if (t < K::NHALO) {
+            const bool in = sIn[t] != 0;
+#pragma unroll
+            for (int j = 0; j < 72; ++j) v[j] = in ? gelu_as(v[j] + fb[j]) : 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 9; ++ch) st_chunk(sm + K::o_h1, t, ch, K::H1R, v + 8 * ch);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+
+      // ---- depthwise 3x3 + GELU: thread = (output token, every other channel chunk) --
+      {
+        const int o = tid & 127, oy = o >> 4, ox = o & 15;
+        const float* wd = fb + 80;
+        const float* bd = fb + 800;
+        for (int ch = wg; ch < 9; ch += 2) {
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = bd[ch * 8 + j];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int tt = (oy + dy) * K::HW + ox + dx;
+              const uint4 u = *reinterpret_cast<const uint4*>(sm + K::o_h1 + (size_t)ch * (K::H1R * 16) + tt * 16);
+              const float* wt = wd + (dy * 3 + dx) * 80 + ch * 8;
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                acc[2 * j] = fmaf(f.x, wt[2 * j], acc[2 * j]);
+                acc[2 * j + 1] = fmaf(f.y, wt[2 * j + 1], acc[2 * j + 1]);
+              }
+            }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = gelu_as(acc[j]);
+          st_chunk(sm + K::o_h2, o, ch, 128, acc);
+        }
+      }
+
+      // ---- fc2 partial product over this chunk's 72 (padded 80) channels --------------
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t id2 = idesc_bf16(128, NOUT, false, false);
+        const uint32_t w2c = a_w2 + c * (NOUT * N1 * 2);
+#pragma unroll
+        for (int s = 0; s < N1 / 16; ++s)
+          mma_bf16(tmem + K::Y_COL, desc_kmajor(a_h2, 128, s), desc_kmajor(w2c, NOUT, s), id2,
+                   (c > 0) || (s > 0));
+        mma_commit(&bar);
+      }
+      mbar_wait(&bar, phase);       // H2 / XN free again, Y complete after the last chunk
+      phase ^= 1;
+      tc_fence_after();
+    }
+
+    // ---- epilogue 2 (warpgroup 0): + b2, GELU, + residual ----------------------------
+    if (wg == 0) {
+      float y[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + K::Y_COL + c0, y + c0);
+      tmem_ld_wait();
+      const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
+      if (h < p.H && w < p.W) {
+        const size_t off = ((size_t)(b * p.H + h) * p.W + w) * C;
+        float r[C];
+        load_row_bf16<C>(x + off, r);
+        const float* b2 = sF + NCH * 880;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) y[cc] = r[cc] + gelu_as(y[cc] + b2[cc]);
+        store_row_bf16<C>(out + off, y);
+      }
+    }
+    // next iteration: its first barrier (after the LN prologue) orders these TMEM reads
+    // before the next fc1 / fc2 MMAs; the XN tiles were released by the fc2 wait above.
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);
+}
+
+static bool ffn_tc_supported(const FfnParams& p) {
+  return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72);
+}
+
+template <int C>
+static int launch_ffn_tc_c(const FfnParams& p, cudaStream_t stream) {
+  using K = FfnTc<C>;
+  const int n_tiles = p.B * ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW);
+  const int grid = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
+  HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C>, K::SMEM));
+  mixffn_tc_kernel<C><<<grid, 256, K::SMEM, stream>>>(p);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+static int launch_mixffn_tc(const FfnParams& p, cudaStream_t stream) {
+  switch (p.C) {
+    case 18: return launch_ffn_tc_c<18>(p, stream);
+    case 36: return launch_ffn_tc_c<36>(p, stream);
+    case 72: return launch_ffn_tc_c<72>(p, stream);
+  }
+  HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_tc: C=%d", p.C);
+}
+
+}  // namespace hrf

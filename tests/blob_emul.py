@@ -120,6 +120,14 @@ class FfnLayout:
         self.bd = o; o += hidden
         self.w2 = o; o = _ru(o + hidden * C, 4)
         self.b2 = o; o += c4
+        # tensor-core sections (bf16 tiles; exercised on the GPU)
+        KC = _ru(C, 16)
+        nch = hidden // 72 if hidden % 72 == 0 else 0
+        self.tc_f32 = o
+        o = _ru(o + nch * 880 + (KC if nch else 0), 4)
+        self.tc_w1 = o; o += nch * 80 * KC // 2
+        self.tc_w2 = o; o += nch * KC * 80 // 2
+        self.tc = dict(KC=KC, NOUT=KC, nchunk=nch)
         self.total = o
 
 

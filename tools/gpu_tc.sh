@@ -2,7 +2,7 @@
 # tensor-core attention: parity tests (bf16 paths), then bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -p no:cacheprovider -k "lsa or mwca" --maxfail=8 2>&1 | tail -40 > gpurun_out/tc_ops.log
+timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -p no:cacheprovider --maxfail=8 2>&1 | tail -40 > gpurun_out/tc_ops.log
 tail -15 gpurun_out/tc_ops.log
 timeout 900 python -m pytest tests/test_gpu_backbone.py -m gpu -q -p no:cacheprovider --maxfail=4 2>&1 | tail -25 > gpurun_out/tc_e2e.log
 tail -8 gpurun_out/tc_e2e.log
