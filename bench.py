@@ -249,6 +249,7 @@ def run_ours(args):
     kernels, roof = {}, None
     if rank == 0:
         pk = peaks()
+        was_concurrent, engine.concurrent = engine.concurrent, False   # isolate every kernel
         with torch.no_grad():
             engine.forward(dev_sets[0][0], dev_sets[0][1:])
             torch.cuda.synchronize()
@@ -258,6 +259,7 @@ def run_ours(args):
                 engine.forward(dev_sets[1 % R][0], dev_sets[1 % R][1:])
                 ev1.record()
             torch.cuda.synchronize()
+        engine.concurrent = was_concurrent
         eager_ms = ev0.elapsed_time(ev1)
         summ = rec.summary()
         ours_ms = sum(g['total_ms'] for g in summ.values())
@@ -283,7 +285,8 @@ def run_ours(args):
                     algorithmic_bytes_per_call=per_launch_bytes, avg_call_ms=top['avg_ms'],
                     share_of_step=round(g['total_ms'] / eager_ms, 4),
                     hrf_kernels_share_of_step=round(ours_ms / eager_ms, 4),
-                    eager_step_ms=round(eager_ms, 3))
+                    eager_step_ms=round(eager_ms, 3),
+                    note='per-kernel times from one serial (single-stream, un-graphed) step')
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.isfile(tp):
             roof['traffic'] = json.load(open(tp)).get(top_key)

@@ -13,6 +13,7 @@ The wiring follows the reference forward (hrfuser_hrformer_based.py:522-627),
 including the `transition1[i][0]` quirk (:550-551).
 """
 import contextlib
+import os
 
 import torch
 import torch.nn as nn
@@ -111,6 +112,9 @@ class BackboneEngine:
         self.stage_mod = {l: [self._stage(getattr(m, f'stage_{l}')[k]) for k in range(self.M)]
                           for l in letters[1:]}
         self.pre_neck_fusion = m.pre_neck_fusion
+        # independent branches / streams run on forked CUDA streams (see _par)
+        self.concurrent = device_ops is None and os.environ.get('HRF_SERIAL', '0') != '1'
+        self._free_streams, self._keep = [], []
         self._upload()
 
     # ---------------------------------------------------------------- packing
@@ -212,40 +216,67 @@ class BackboneEngine:
         """(B,H,W,C) contiguous -> (B,C,H,W) channels_last view"""
         return t.permute(0, 3, 1, 2)
 
+    # -- stream-level concurrency --------------------------------------------------
+    # Branches of an HR module, the camera / modality streams and the rows of the
+    # exchange step are independent; the low-resolution ones launch grids far
+    # smaller than 148 SMs.  `_par` runs independent thunks on forked CUDA streams
+    # (fork = side.wait_stream(cur), join = cur.wait_stream(side)); under CUDA-graph
+    # capture the forks become parallel graph branches.  Results are kept alive
+    # until the forward ends so the caching allocator never recycles a block that
+    # another stream may still read.
+    def _par(self, thunks):
+        if not self.concurrent or len(thunks) <= 1:
+            return [t() for t in thunks]
+        cur = torch.cuda.current_stream()
+        outs, used = [None] * len(thunks), []
+        for idx in range(1, len(thunks)):
+            side = self._free_streams.pop() if self._free_streams else torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                outs[idx] = thunks[idx]()
+            used.append(side)
+        outs[0] = thunks[0]()
+        for side in used:
+            cur.wait_stream(side)
+            self._free_streams.append(side)
+        self._keep.append(outs)
+        return outs
+
     def _run_block(self, blk, x, kv=None):
         y = self.ops.window_attention(x, kv, [s.t for s in blk['attn']], blk['heads'], blk['win'],
-                                 blk['pad_mask'], blk['eps'])
+                                      blk['pad_mask'], blk['eps'])
         f = blk['ffn']
         return self.ops.mixffn(y, f['blob'].t, f['hidden'], f['eps'])
+
+    def _run_branch(self, blocks, x):
+        for blk in blocks:
+            x = self._run_block(blk, x)
+        return x
+
+    def _exchange_row(self, i, ups, downs, ys, want_nchw):
+        up_t = [self.ops.pointwise(ys[j], blob.t, cout) for j, blob, cout in ups]
+        same_t = []
+        for j, chain in downs:
+            t = ys[j]
+            for blob, cout, relu in chain:
+                t = self.ops.dw_down(t, blob.t, cout, relu)
+            same_t.append(t)
+        return self.ops.fuse_sum(ys[i], up_t, same_t, relu=True, nchw_out=want_nchw)
 
     def _run_stage(self, mods, xs, final_nchw=False):
         nchw = None
         for mi, (branches, rows) in enumerate(mods):
-            ys = []
-            for br, x in zip(branches, xs):
-                for blk in br:
-                    x = self._run_block(blk, x)
-                ys.append(x)
+            ys = self._par([lambda br=br, x=x: self._run_branch(br, x) for br, x in zip(branches, xs)])
             if rows is None:
                 xs = ys
                 continue
             want_nchw = final_nchw and mi == len(mods) - 1
-            outs, nchw = [], []
-            for i, (ups, downs) in enumerate(rows):
-                up_t = [self.ops.pointwise(ys[j], blob.t, cout) for j, blob, cout in ups]
-                same_t = []
-                for j, chain in downs:
-                    t = ys[j]
-                    for blob, cout, relu in chain:
-                        t = self.ops.dw_down(t, blob.t, cout, relu)
-                    same_t.append(t)
-                r = self.ops.fuse_sum(ys[i], up_t, same_t, relu=True, nchw_out=want_nchw)
-                if want_nchw:
-                    outs.append(r[0])
-                    nchw.append(r[1])
-                else:
-                    outs.append(r)
-            xs = outs
+            res = self._par([lambda i=i, u=u, d=d: self._exchange_row(i, u, d, ys, want_nchw)
+                             for i, (u, d) in enumerate(rows)])
+            if want_nchw:
+                xs, nchw = [r[0] for r in res], [r[1] for r in res]
+            else:
+                xs = res
         return (xs, nchw) if final_nchw else xs
 
     def _apply_chain(self, chain, x_img):
@@ -253,18 +284,18 @@ class BackboneEngine:
             x_img = c(x_img)
         return x_img
 
-    def _fuse(self, letter, cams, stream):
-        outs, firsts = [], None
-        for i, cam in enumerate(cams):
+    def _fuse(self, letter, cam_thunks, stream):
+        """cam_thunks[i]() -> camera tokens of branch i.  Returns the fused branches
+        and the modality tensors of branch 0 (inputs of the next modality stage)."""
+        def branch(i):
             ms = []
             for k in range(self.M):
                 tr = self.trans_mod[letter][k][i]
                 ms.append(stream[k] if tr is None else
                           self._tokens(self._apply_chain(tr, self._image(stream[k]))))
-            if i == 0:
-                firsts = ms
-            outs.append(self._run_block(self.fusion[letter][i], cam, ms))
-        return outs, firsts
+            return self._run_block(self.fusion[letter][i], cam_thunks[i](), ms), ms
+        res = self._par([lambda i=i: branch(i) for i in range(len(cam_thunks))])
+        return [r[0] for r in res], res[0][1]
 
     def _prep(self, t):
         return t.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
@@ -278,36 +309,47 @@ class BackboneEngine:
             if fp32_cuda else contextlib.nullcontext()
         dctx = torch.cuda.device(self.device) if self.device.type == 'cuda' \
             else contextlib.nullcontext()
+        self._keep = []
+        M = self.M
         with ctx, dctx:
-            x = self._apply_chain(self.stem, self._prep(x))
-            stream = [self._tokens(self._apply_chain(self.stem_mod[k], self._prep(mods[k])))
-                      for k in range(self.M)]
-            cams = [self._tokens(t(x)) for t in self.trans1]
-            xs, firsts = self._fuse('a', cams, stream)
-            ys = self._run_stage(self.stage[2], xs)
-            stream = [self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0] for k in range(self.M)]
+            stems = self._par(
+                [lambda: self._apply_chain(self.stem, self._prep(x))] +
+                [lambda k=k: self._tokens(self._apply_chain(self.stem_mod[k], self._prep(mods[k])))
+                 for k in range(M)])
+            x, stream = stems[0], stems[1:]
+            xs, firsts = self._fuse('a', [lambda t=t: self._tokens(t(x)) for t in self.trans1], stream)
+            res = self._par([lambda: self._run_stage(self.stage[2], xs)] +
+                            [lambda k=k: self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0]
+                             for k in range(M)])
+            ys, stream = res[0], res[1:]
 
+            nchw = None
             for idx, letter, nxt in ((2, 'b', 'c'), (3, 'c', 'd')):
-                cams = list(ys)
+                cam_thunks = []
                 for i, tr in enumerate(self.trans_cam[idx]):
-                    if tr is not None:
-                        t = self._tokens(self._apply_chain(tr, self._image(ys[-1])))
-                        if i < len(cams):
-                            cams[i] = t
-                        else:
-                            cams.append(t)
-                xs, firsts = self._fuse(letter, cams, stream)
+                    if tr is None:
+                        cam_thunks.append(lambda i=i: ys[i])
+                    else:
+                        cam_thunks.append(lambda tr=tr: self._tokens(
+                            self._apply_chain(tr, self._image(ys[-1]))))
+                xs, firsts = self._fuse(letter, cam_thunks, stream)
                 last = idx == 3
-                if last:
-                    ys, nchw = self._run_stage(self.stage[4], xs, final_nchw=True)
-                else:
-                    ys = self._run_stage(self.stage[3], xs)
+                thunks = [lambda last=last: self._run_stage(self.stage[4 if last else 3], xs,
+                                                            final_nchw=last)]
                 if nxt in self.stage_mod:
-                    stream = [self._run_stage(self.stage_mod[nxt][k], [firsts[k]])[0]
-                              for k in range(self.M)]
+                    thunks += [lambda k=k: self._run_stage(self.stage_mod[nxt][k], [firsts[k]])[0]
+                               for k in range(M)]
+                res = self._par(thunks)
+                if last:
+                    ys, nchw = res[0]
+                else:
+                    ys = res[0]
+                if nxt in self.stage_mod:
+                    stream = res[1:]
             if self.pre_neck_fusion:
-                xs, _ = self._fuse('d', ys, stream)
+                xs, _ = self._fuse('d', [lambda i=i: ys[i] for i in range(len(ys))], stream)
                 nchw = [self.ops.fuse_sum(t, relu=True, nchw_out=True)[1] for t in xs]
+            self._keep = []
             return nchw
 
 
