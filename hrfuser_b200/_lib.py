@@ -73,6 +73,8 @@ SIGNATURES = {
                                C.c_void_p]),
     'hrf_fuse_sum_fwd': (C.c_int, [C.POINTER(FuseDesc), C.c_void_p, _VPP, _VPP, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'hrf_bias_act_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p]),
     'hrf_nchw_to_nhwc': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,

@@ -374,6 +374,17 @@ int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
   HRF_REQUIRE(false, HRF_EINVAL, "fuse_fwd: dtype");
 }
 
+int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, void* y,
+                     const float* bias, const void* residual, void* stream) {
+  HRF_REQUIRE(y && bias && n_tokens > 0 && C > 0, HRF_EINVAL, "bias_act: args");
+  if (dtype == HRF_F32)
+    return launch_bias_act<float>(y, bias, residual, (size_t)n_tokens, C, relu, (cudaStream_t)stream);
+  if (dtype == HRF_BF16)
+    return launch_bias_act<__nv_bfloat16>(y, bias, residual, (size_t)n_tokens, C, relu,
+                                          (cudaStream_t)stream);
+  HRF_REQUIRE(false, HRF_EINVAL, "bias_act: dtype");
+}
+
 int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t b_mn_major,
                       void* stream) {
   HRF_REQUIRE(A && B && D, HRF_EINVAL, "selftest: null pointer");

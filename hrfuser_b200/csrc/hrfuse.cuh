@@ -259,3 +259,75 @@ static int launch_layout(int B, int C, int H, int W, int sdt, const void* src, i
 }
 
 }  // namespace hrf
+
+// ---------------------------------------------------------------------------
+// Conv epilogue for the cuDNN-side layers (stems / Bottlenecks / transitions):
+//   y = act(y + bias[c] (+ residual)),  in place on a channels-last tensor.
+// One pass instead of the bias-add, residual-add and ReLU passes torch issues
+// after a convolution (the BN affine is already folded into the conv weights).
+// ---------------------------------------------------------------------------
+namespace hrf {
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(T* y, const float* __restrict__ bias,
+                                                       const T* __restrict__ res, size_t n_vec,
+                                                       int C, int relu) {
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = v * VEC;
+    const int c0 = (int)(e0 % (size_t)C);
+    float f[VEC];
+    if constexpr (sizeof(T) * VEC == 16) {
+      const uint4 u = *reinterpret_cast<const uint4*>(y + e0);
+      const T* p = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) f[i] = (float)p[i];
+      if (res) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + e0));
+        const T* q = reinterpret_cast<const T*>(&r);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) f[i] += (float)q[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) f[i] = (float)y[e0 + i] + (res ? (float)res[e0 + i] : 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      f[i] += __ldg(bias + c0 + i);
+      if (relu) f[i] = fmaxf(f[i], 0.f);
+    }
+    if constexpr (sizeof(T) * VEC == 16) {
+      uint4 u;
+      T* p = reinterpret_cast<T*>(&u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) p[i] = (T)f[i];
+      *reinterpret_cast<uint4*>(y + e0) = u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) y[e0 + i] = (T)f[i];
+    }
+  }
+}
+
+template <typename T>
+static int launch_bias_act(void* y, const float* bias, const void* res, size_t n_tok, int C,
+                           int relu, cudaStream_t stream) {
+  constexpr int V16 = 16 / (int)sizeof(T);
+  const size_t total = n_tok * (size_t)C;
+  const bool wide = (C % V16 == 0) && ((uintptr_t)y % 16 == 0) && (!res || (uintptr_t)res % 16 == 0);
+  const int vec = wide ? V16 : (C % 2 == 0 ? 2 : 1);
+  const size_t n_vec = total / vec;
+  const int grid = (int)((n_vec + 255) / 256 < 148 * 16 ? (n_vec + 255) / 256 : 148 * 16);
+  if (vec == V16)
+    bias_act_kernel<T, V16><<<grid, 256, 0, stream>>>((T*)y, bias, (const T*)res, n_vec, C, relu);
+  else if (vec == 2)
+    bias_act_kernel<T, 2><<<grid, 256, 0, stream>>>((T*)y, bias, (const T*)res, n_vec, C, relu);
+  else
+    bias_act_kernel<T, 1><<<grid, 256, 0, stream>>>((T*)y, bias, (const T*)res, n_vec, C, relu);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+}  // namespace hrf

@@ -34,13 +34,37 @@ def _fold_conv_bn(conv, bn, dtype):
 
 
 class _Conv:
-    """Folded conv+BN(+ReLU) executed by cuDNN (channels-last)."""
+    """Folded conv+BN(+ReLU)(+residual) executed by cuDNN, channels-last.  On CUDA the
+    bias / residual / ReLU epilogue is fused into the convolution
+    (`cudnn_convolution_relu`, `cudnn_convolution_add_relu`): torch's separate
+    broadcast-add and clamp passes cost 3-4x the convolution itself on the
+    256-channel stem tensors (profiles/r01_v1_simt_launches.txt)."""
 
-    def __init__(self, conv, bn, relu, dtype):
-        self.w, self.b = _fold_conv_bn(conv, bn, dtype)
+    def __init__(self, conv, bn, relu, dtype, extra_bias=None, use_bias=True):
+        self.w, b = _fold_conv_bn(conv, bn, dtype)
+        if extra_bias is not None:
+            b = b + extra_bias
+        self.has_bias = use_bias and (conv.bias is not None or bn is not None or extra_bias is not None)
+        self.b = b if self.has_bias else None
+        self.b32 = b.float() if self.has_bias else None
         self.stride, self.padding, self.groups, self.relu = conv.stride, conv.padding, conv.groups, relu
 
     def __call__(self, x, residual=None):
+        if x.is_cuda and self.relu and self.has_bias:
+            if residual is None:
+                return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding,
+                                                    (1, 1), self.groups)
+            return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, self.stride,
+                                                    self.padding, (1, 1), self.groups)
+        if x.is_cuda and (self.has_bias or residual is not None or self.relu):
+            y = F.conv2d(x, self.w, None, self.stride, self.padding, 1, self.groups)
+            t = y.permute(0, 2, 3, 1)
+            if t.is_contiguous():
+                r = residual.permute(0, 2, 3, 1) if residual is not None else None
+                bias = self.b32 if self.has_bias else torch.zeros(y.shape[1], device=y.device)
+                ops.bias_act_(t, bias, r if r is None or r.is_contiguous() else r.contiguous(),
+                              self.relu)
+                return y
         y = F.conv2d(x, self.w, self.b, self.stride, self.padding, 1, self.groups)
         if residual is not None:
             y += residual
@@ -55,12 +79,18 @@ def _seq(mods, dtype):
 
 
 class _Bottleneck:
+    """conv1-bn-relu, conv2-bn-relu, conv3-bn (+ downsample conv-bn) + add + relu
+    (reference resnet.py:263-302).  The downsample branch runs bias-free and its
+    folded BN shift moves into conv3's bias, so the add + ReLU fuse into conv3."""
+
     def __init__(self, m, dtype):
         self.c1 = _Conv(m.conv1, m.bn1, True, dtype)
         self.c2 = _Conv(m.conv2, m.bn2, True, dtype)
-        self.c3 = _Conv(m.conv3, m.bn3, True, dtype)     # ReLU after the residual add
-        self.down = _Conv(m.downsample[0], m.downsample[1], False, dtype) \
-            if m.downsample is not None else None
+        self.down, extra = None, None
+        if m.downsample is not None:
+            _, extra = _fold_conv_bn(m.downsample[0], m.downsample[1], dtype)
+            self.down = _Conv(m.downsample[0], m.downsample[1], False, dtype, use_bias=False)
+        self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra)   # ReLU after the add
 
     def __call__(self, x):
         idt = x if self.down is None else self.down(x)

@@ -257,6 +257,24 @@ def fuse_sum(x, ups=(), sames=(), relu=True, nchw_out=False):
     return (out, nchw) if nchw_out else out
 
 
+def bias_act_(y, bias, residual=None, relu=True):
+    """in place: y = act(y + bias[c] (+ residual)) on a channels-last (B,H,W,C) tensor"""
+    lib = _lib.load()
+    _check_act(y, 'y')
+    B, H, W, Cc = y.shape
+    assert bias.dtype == torch.float32 and bias.numel() == Cc
+    if residual is not None:
+        _check_act(residual, 'residual')
+        assert residual.shape == y.shape and residual.dtype == y.dtype
+    with _timed('bias_act', C=Cc, launches=1,
+                bytes=float(y.numel() * y.element_size() * (3 if residual is not None else 2)),
+                flops=float(y.numel() * 2)):
+        check(lib.hrf_bias_act_fwd(B * H * W, Cc, _dtype_code(y), int(relu), y.data_ptr(),
+                                   bias.data_ptr(), residual.data_ptr() if residual is not None
+                                   else None, _stream()))
+    return y
+
+
 def nchw_to_nhwc(x, dtype=None):
     lib = _lib.load()
     assert x.is_cuda and x.dim() == 4 and x.is_contiguous()

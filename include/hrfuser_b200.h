@@ -156,6 +156,13 @@ typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_
 int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
                      const void* const* same, void* out, float* out_nchw_f32, void* stream);
 
+/* Epilogue of the cuDNN-side convolutions (stems, Bottlenecks, transitions:
+ * hrnet.py:341-371,419-463, resnet.py:263-302 with the BatchNorm folded into the
+ * conv): y = act(y + bias[c] (+ residual)) in place, one pass, channels-last.
+ * bias is fp32 [C] (device); residual may be NULL. */
+int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, void* y,
+                     const float* bias, const void* residual, void* stream);
+
 /* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
  * through the same descriptor helpers the fused kernels use.  B is [N][K]
  * (b_mn_major = 0, K-major operand) or [K][N] (b_mn_major = 1, MN-major operand).

@@ -177,3 +177,19 @@ def test_error_paths(built_lib):
         ops.window_attention(xw, None, [blob], heads=16)
     with pytest.raises(_lib.HrfError, match='alias'):
         ops.mixffn(x, blob, 72, out=x)
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,with_res,relu', [(64, False, True), (256, True, True), (18, False, False),
+                                             (36, True, True), (3, False, True)])
+def test_bias_act(built_lib, C, with_res, relu, dt):
+    from hrfuser_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    y = torch.randn(2, 9, 13, C, generator=g).to(dt).cuda()
+    r = torch.randn(2, 9, 13, C, generator=g).to(dt).cuda() if with_res else None
+    b = torch.randn(C, generator=g).cuda()
+    ref = y.float() + b + (r.float() if with_res else 0)
+    ref = (ref.relu() if relu else ref).to(dt)
+    ops.bias_act_(y, b, r, relu)
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
