@@ -188,7 +188,7 @@ def test_bias_act(built_lib, C, with_res, relu, dt):
     y = torch.randn(2, 9, 13, C, generator=g).to(dt).cuda()
     r = torch.randn(2, 9, 13, C, generator=g).to(dt).cuda() if with_res else None
     b = torch.randn(C, generator=g).cuda()
-    ref = y.float() + b + (r.float() if with_res else 0)
+    ref = (y.float() + r.float() if with_res else y.float()) + b      # kernel's order of adds
     ref = (ref.relu() if relu else ref).to(dt)
     ops.bias_act_(y, b, r, relu)
     torch.cuda.synchronize()
