@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 HRF_F32, HRF_BF16 = 0, 1
 MAX_FUSE_TERMS = 4
@@ -57,13 +57,15 @@ SIGNATURES = {
     'hrf_launch_count': (C.c_ulonglong, []),
     'hrf_attn_blob_floats': (C.c_size_t, [C.POINTER(AttnDesc)]),
     'hrf_attn_pack': (C.c_int, [C.POINTER(AttnDesc)] + [_F] * 13 + [_F]),
+    'hrf_attn_workspace_bytes': (C.c_size_t, [C.POINTER(AttnDesc)]),
     'hrf_window_attn_fwd': (C.c_int, [C.POINTER(AttnDesc), C.c_void_p, _VPP, _VPP, C.c_void_p,
-                                      C.c_void_p]),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     'hrf_ffn_blob_floats': (C.c_size_t, [C.POINTER(FfnDesc)]),
     'hrf_ffn_pack': (C.c_int, [C.POINTER(FfnDesc), _F, _F, _F, _F, _FP4, _F, _F, _FP4, _F, _F,
                                _FP4, C.c_float, _F]),
+    'hrf_ffn_workspace_bytes': (C.c_size_t, [C.POINTER(FfnDesc)]),
     'hrf_mixffn_fwd': (C.c_int, [C.POINTER(FfnDesc), C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]),
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     'hrf_pw_blob_floats': (C.c_size_t, [C.POINTER(PwDesc)]),
     'hrf_pw_pack': (C.c_int, [C.POINTER(PwDesc), _F, _F, _FP4, C.c_float, _F]),
     'hrf_pw_fwd': (C.c_int, [C.POINTER(PwDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -192,10 +192,21 @@ int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b
   return HRF_OK;
 }
 
+size_t hrf_attn_workspace_bytes(const HrfAttnDesc* d) {
+  if (!d || d->heads <= 0 || d->C <= 0 || d->dtype != HRF_BF16 || d->win != 7 || tc_disabled())
+    return 0;
+  return attn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->heads);
+}
+
 int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
-                        const float* const* blobs, void* out, void* stream) {
+                        const float* const* blobs, void* out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   int rc = check_attn(d);
   if (rc) return rc;
+  HRF_REQUIRE(workspace_bytes >= hrf_attn_workspace_bytes(d) &&
+                  (workspace != nullptr || hrf_attn_workspace_bytes(d) == 0),
+              HRF_EINVAL, "attn_fwd: workspace of %zu bytes required, %zu given",
+              hrf_attn_workspace_bytes(d), workspace_bytes);
   HRF_REQUIRE(x && blobs && out, HRF_EINVAL, "attn_fwd: null pointer");
   HRF_REQUIRE(x != out, HRF_EINVAL, "attn_fwd: out must not alias x");
   HRF_REQUIRE(d->n_kv == 0 || kv, HRF_EINVAL, "attn_fwd: kv list missing");
@@ -208,6 +219,7 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
     p.z = d->n_kv > 0 ? kv[k] : x;
     p.blob = blobs[k];
     p.out = out;
+    p.ws = workspace;
     HRF_REQUIRE(p.z && p.blob, HRF_EINVAL, "attn_fwd: null kv/blob %d", k);
     p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.heads = d->heads; p.win = d->win;
     p.cross = d->n_kv > 0; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
@@ -291,12 +303,22 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
   return HRF_OK;
 }
 
-int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out, void* stream) {
+size_t hrf_ffn_workspace_bytes(const HrfFfnDesc* d) {
+  if (!d || d->C <= 0 || d->dtype != HRF_BF16 || tc_disabled()) return 0;
+  return ffn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->hidden);
+}
+
+int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out,
+                   void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_ffn(d);
   if (rc) return rc;
   HRF_REQUIRE(x && blob && out, HRF_EINVAL, "ffn_fwd: null pointer");
   HRF_REQUIRE(x != out, HRF_EINVAL, "ffn_fwd: out must not alias x (3x3 halo reads)");
-  FfnParams p{x, blob, out, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps};
+  HRF_REQUIRE(workspace_bytes >= hrf_ffn_workspace_bytes(d) &&
+                  (workspace != nullptr || hrf_ffn_workspace_bytes(d) == 0),
+              HRF_EINVAL, "ffn_fwd: workspace of %zu bytes required, %zu given",
+              hrf_ffn_workspace_bytes(d), workspace_bytes);
+  FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps};
   if (d->dtype == HRF_BF16 && ffn_tc_supported(p) && !tc_disabled())
     return launch_mixffn_tc(p, (cudaStream_t)stream);
   return d->dtype == HRF_F32 ? launch_mixffn<float>(p, (cudaStream_t)stream)

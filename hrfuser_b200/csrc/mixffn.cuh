@@ -62,6 +62,7 @@ struct FfnParams {
   const void* x;
   const float* blob;
   void* out;
+  void* ws;           // fp32 workspace (split tensor-core variant) or nullptr
   int B, H, W, C, hidden;
   float eps;
 };

@@ -22,28 +22,34 @@
 
 namespace hrf {
 
-template <int C>
+// CPG = hidden chunks handled by one CTA.  CPG == NCH: the CTA finishes the block.
+// CPG < NCH (C = 144: 1 920 tokens but 8 chunks): NCH/CPG CTAs share a token tile,
+// each writes its fp32 partial fc2 product to a workspace and `ffn_reduce_kernel`
+// applies b2 / GELU / residual to the fixed-order sum.
+template <int C, int CPG>
 struct FfnTc {
-  static constexpr int HID = 4 * C, NCH = HID / 72;
-  static_assert(HID % 72 == 0, "hidden must split into 72-channel chunks");
+  static constexpr int HID = 4 * C, NCH = HID / 72, NG = NCH / CPG;
+  static constexpr bool SPLIT = CPG < NCH, BIGC = C > 40;
+  static_assert(HID % 72 == 0 && NCH % CPG == 0, "hidden must split into 72-channel chunks");
   static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
   static constexpr int TH = 8, TW = 16, HH = TH + 2, HW = TW + 2, NHALO = HH * HW;   // 180
   static constexpr int XT = 128 * KC * 2;            // one XN operand tile
   static constexpr int H1R = 184;                    // rows per 8-channel chunk of H1 (>= 180)
   // shared-memory map (bytes)
-  static constexpr int o_w1 = 0;                               // NCH tiles [80 x KC]
-  static constexpr int o_w2 = o_w1 + NCH * N1 * KC * 2;        // NCH tiles [NOUT x 80]
-  static constexpr int o_xn = o_w2 + NCH * NOUT * N1 * 2;      // 2 tiles
+  static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
+  static constexpr int o_w2 = o_w1 + CPG * N1 * KC * 2;        // CPG tiles [NOUT x 80]
+  static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;      // 2 tiles
   static constexpr int o_h1 = o_xn + 2 * XT;                   // 9 x H1R x 16
   static constexpr int o_h2 = o_h1 + 9 * H1R * 16;             // 10 x 128 x 16
   static constexpr int o_f32 = o_h2 + 10 * 128 * 16;           // per chunk 880 floats, then b2[NOUT]
-  static constexpr int o_ln = o_f32 + (NCH * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
+  static constexpr int o_ln = o_f32 + (CPG * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
   static constexpr int C4 = (C + 3) / 4 * 4;
   static constexpr int o_in = o_ln + 2 * C4 * 4;               // inside flags [256] bytes
   static constexpr int SMEM = o_in + 256;
   static constexpr int D_COLS = 2 * N1;                        // fc1 accumulators (two M tiles)
   static constexpr int Y_COL = D_COLS;                         // fc2 accumulator
   static constexpr int TMEM_COLS = (D_COLS + NOUT <= 256) ? 256 : 512;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 // erf-form GELU from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the
@@ -61,11 +67,11 @@ __device__ __forceinline__ float gelu_as(float x) {
   return 0.5f * x * (x >= 0.f ? 2.0f - pe : pe);
 }
 
-template <int C>
+template <int C, int CPG>
 __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
   using namespace umma;
-  using K = FfnTc<C>;
-  constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH;
+  using K = FfnTc<C, CPG>;
+  constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH, NG = K::NG;
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -73,6 +79,7 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, q = warp & 3;          // warpgroup (M tile / channel parity), TMEM quadrant
   const int row = q * 32 + lane;                   // TMEM lane == row of the M=128 tiles
+  const int cg = blockIdx.x % NG;                  // chunk group of this CTA
   const FfnLayout L(C, K::HID);
   const float* blob = p.blob;
   float* sF = reinterpret_cast<float*>(sm + K::o_f32);
@@ -81,11 +88,15 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
 
   // ---- one-time setup ---------------------------------------------------------------
   {
-    const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_w1);    // w1 | w2 contiguous
-    uint4* dst = reinterpret_cast<uint4*>(sm + K::o_w1);
-    constexpr int n16 = (NCH * N1 * KC * 2 + NCH * NOUT * N1 * 2) / 16;
-    for (int e = tid; e < n16; e += 256) dst[e] = __ldg(src + e);
-    for (int e = tid; e < NCH * 880 + NOUT; e += 256) sF[e] = __ldg(blob + L.o_tc_f32 + e);
+    // this group's chunks are contiguous in each blob section
+    const uint4* s1 = reinterpret_cast<const uint4*>(blob + L.o_tc_w1) + (size_t)cg * CPG * (N1 * KC * 2 / 16);
+    const uint4* s2 = reinterpret_cast<const uint4*>(blob + L.o_tc_w2) + (size_t)cg * CPG * (NOUT * N1 * 2 / 16);
+    uint4* d1 = reinterpret_cast<uint4*>(sm + K::o_w1);
+    uint4* d2 = reinterpret_cast<uint4*>(sm + K::o_w2);
+    for (int e = tid; e < CPG * N1 * KC * 2 / 16; e += 256) d1[e] = __ldg(s1 + e);
+    for (int e = tid; e < CPG * NOUT * N1 * 2 / 16; e += 256) d2[e] = __ldg(s2 + e);
+    for (int e = tid; e < CPG * 880; e += 256) sF[e] = __ldg(blob + L.o_tc_f32 + cg * CPG * 880 + e);
+    for (int e = tid; e < NOUT; e += 256) sF[CPG * 880 + e] = __ldg(blob + L.o_tc_f32 + NCH * 880 + e);
     for (int e = tid; e < K::C4; e += 256) {
       sLn[e] = __ldg(blob + L.o_ln_w + e);
       sLn[K::C4 + e] = __ldg(blob + L.o_ln_b + e);
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += gridDim.x / NG) {
     const int b = tile / (tiles_x * tiles_y);
     const int ty0 = ((tile / tiles_x) % tiles_y) * K::TH, tx0 = (tile % tiles_x) * K::TW;
 
@@ -128,9 +139,8 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
       sIn[tid] = in ? 1 : 0;
       unsigned char* xt = sm + K::o_xn + (tid >> 7) * K::XT;
       if (in) {
-        float v[C];
-        load_row_bf16<C>(x + ((size_t)(b * p.H + h) * p.W + w) * C, v);
-        ln_row_to_tile<C, KC>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+        ln_token<C, KC, K::BIGC>(x + ((size_t)(b * p.H + h) * p.W + w) * C, sLn, sLn + K::C4, p.eps,
+                                 xt, tid & 127);
       } else {
         const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
     }
 
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
+    for (int c = 0; c < CPG; ++c) {
       // ---- fc1 on both halo M tiles ---------------------------------------------------
       fence_proxy_async();
       tc_fence_before();
@@ -233,7 +243,25 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
     }
 
     // ---- epilogue 2 (warpgroup 0): + b2, GELU, + residual ----------------------------
-    if (wg == 0) {
+    if constexpr (K::SPLIT) {
+      if (wg == 0) {      // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
+        const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
+        const bool in = h < p.H && w < p.W;
+        const size_t n_tok = (size_t)p.B * p.H * p.W;
+        float* wrow = static_cast<float*>(p.ws) +
+                      ((size_t)cg * n_tok + (in ? (size_t)(b * p.H + h) * p.W + w : 0)) * C;
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 8) {
+          float y[8];
+          tmem_ld8(trow + K::Y_COL + c0, y);
+          tmem_ld_wait();
+          if (in) {
+            *reinterpret_cast<float4*>(wrow + c0) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          }
+        }
+      }
+    } else if (wg == 0) {
       float y[NOUT];
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + K::Y_COL + c0, y + c0);
@@ -243,7 +271,7 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
         const size_t off = ((size_t)(b * p.H + h) * p.W + w) * C;
         float r[C];
         load_row_bf16<C>(x + off, r);
-        const float* b2 = sF + NCH * 880;
+        const float* b2 = sF + CPG * 880;
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) y[cc] = r[cc] + gelu_as(y[cc] + b2[cc]);
         store_row_bf16<C>(out + off, y);
@@ -258,27 +286,72 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
   if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
-static bool ffn_tc_supported(const FfnParams& p) {
-  return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72);
+// out = x + GELU(b2 + sum_g partial[g])   (fixed summation order)
+template <int C>
+__global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng, size_t n_tok,
+                                                         const __nv_bfloat16* x,
+                                                         const float* __restrict__ b2,
+                                                         __nv_bfloat16* out) {
+  const size_t n_vec = n_tok * (C / 8);
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = v * 8;
+    const int c0 = (int)(e0 % C);
+    float acc[8], r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __ldg(b2 + c0 + j);
+    for (int gi = 0; gi < ng; ++gi) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0 + 4));
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    load_row_bf16<8>(x + e0, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = r[j] + gelu_as(acc[j]);
+    store_row_bf16<8>(out + e0, acc);
+  }
 }
 
-template <int C>
+static bool ffn_tc_supported(const FfnParams& p) {
+  return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144);
+}
+static size_t ffn_tc_workspace_bytes(int B, int H, int W, int C, int hidden) {
+  if (hidden != 4 * C || C != 144) return 0;
+  return (size_t)8 * B * H * W * C * sizeof(float);
+}
+
+template <int C, int CPG>
 static int launch_ffn_tc_c(const FfnParams& p, cudaStream_t stream) {
-  using K = FfnTc<C>;
+  using K = FfnTc<C, CPG>;
   const int n_tiles = p.B * ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW);
-  const int grid = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
-  HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C>, K::SMEM));
-  mixffn_tc_kernel<C><<<grid, 256, K::SMEM, stream>>>(p);
+  const int cap = 148 * 2 / K::NG > 0 ? 148 * 2 / K::NG : 1;
+  const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
+  if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
+  HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C, CPG>, K::SMEM));
+  mixffn_tc_kernel<C, CPG><<<grid, 256, K::SMEM, stream>>>(p);
   count_launch();
   HRF_CUDA(cudaGetLastError());
+  if constexpr (K::SPLIT) {
+    const FfnLayout L(C, K::HID);
+    const size_t n_tok = (size_t)p.B * p.H * p.W;
+    const size_t n_vec = n_tok * (C / 8);
+    const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
+    ffn_reduce_kernel<C><<<rgrid, 256, 0, stream>>>(
+        static_cast<const float*>(p.ws), K::NG, n_tok, static_cast<const __nv_bfloat16*>(p.x),
+        p.blob + L.o_tc_f32 + K::NCH * 880, static_cast<__nv_bfloat16*>(p.out));
+    count_launch();
+    HRF_CUDA(cudaGetLastError());
+  }
   return HRF_OK;
 }
 
 static int launch_mixffn_tc(const FfnParams& p, cudaStream_t stream) {
   switch (p.C) {
-    case 18: return launch_ffn_tc_c<18>(p, stream);
-    case 36: return launch_ffn_tc_c<36>(p, stream);
-    case 72: return launch_ffn_tc_c<72>(p, stream);
+    case 18: return launch_ffn_tc_c<18, 1>(p, stream);
+    case 36: return launch_ffn_tc_c<36, 2>(p, stream);
+    case 72: return launch_ffn_tc_c<72, 4>(p, stream);
+    case 144: return launch_ffn_tc_c<144, 1>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_tc: C=%d", p.C);
 }

@@ -58,6 +58,7 @@ struct AttnParams {
   const void* z;      // key/value source tokens (== xq for self-attention)
   const float* blob;
   void* out;
+  void* ws;           // fp32 workspace (split-head tensor-core variants) or nullptr
   int B, H, W, C, heads, win;
   int cross, pad_mask;
   float eps;

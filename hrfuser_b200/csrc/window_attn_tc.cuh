@@ -28,32 +28,43 @@
 
 namespace hrf {
 
-template <int C, int HEADS, bool CROSS>
+// HG = heads handled by one CTA.  HG == HEADS: the CTA finishes the block (bias,
+// residuals, bf16 store).  HG < HEADS (wide, low-resolution branches: few windows,
+// many heads): HEADS/HG CTAs share a window pair, each writes its fp32 partial
+// out-projection to a workspace and `attn_reduce_kernel` sums them in fixed order.
+template <int C, int HEADS, int HG, bool CROSS>
 struct AttnTc {
   static constexpr int HD = C / HEADS;
   static constexpr int HDP = (HD + 15) / 16 * 16;
   static constexpr int KC = (C + 15) / 16 * 16;
-  static constexpr int NQ = HEADS * HDP;
+  static constexpr int NQ = HEADS * HDP;       // all heads (blob tiles)
+  static constexpr int NQG = HG * HDP;         // this CTA's heads
+  static constexpr int NG = HEADS / HG;
   static constexpr int NOUT = KC;
   static constexpr int WIN = 7, S = 49;
+  static constexpr bool SPLIT = HG < HEADS;
+  static constexpr bool BIGC = C > 40;         // LayerNorm streams the row instead of holding it
+  static_assert(HEADS % HG == 0, "head groups");
   static_assert(HDP == 32, "tensor-core attention kernel is written for head_dim <= 32");
-  static_assert(NQ <= 256 && NOUT <= 256, "one UMMA per projection");
-  static constexpr int XT = 128 * (KC > NQ ? KC : NQ) * 2;   // XN tile, later aliased by the O tile
-  static constexpr int WQ_B = NQ * KC * 2, WO_B = NOUT * NQ * 2;
+  static_assert(NQG <= 256 && NOUT <= 256, "one UMMA per projection");
+  static constexpr int XT = 128 * (KC > NQG ? KC : NQG) * 2;   // XN tile, later aliased by the O tile
+  static constexpr int WQ_B = NQG * KC * 2, WO_B = NOUT * NQG * 2;
   static constexpr int HT = 128 * HDP * 2;                    // one head's Q / K / V tile
   // shared-memory map (bytes)
   static constexpr int o_wq = 0, o_wk = o_wq + WQ_B, o_wv = o_wk + WQ_B, o_wo = o_wv + WQ_B;
   static constexpr int o_xn = o_wo + WO_B;
   static constexpr int o_zn = o_xn + XT;
   static constexpr int o_q = o_zn + (CROSS ? 128 * KC * 2 : 0);
-  static constexpr int o_k = o_q + HEADS * HT, o_v = o_k + HEADS * HT;
-  static constexpr int o_p = o_v + HEADS * HT;                // 128 x 64 bf16
-  static constexpr int o_bias = o_p + 128 * 64 * 2;           // fp32: bq|bk|bv|bo
-  static constexpr int o_rpb = o_bias + (3 * NQ + NOUT) * 4;  // fp32 [HEADS][169]
-  static constexpr int o_ln = o_rpb + ((HEADS * 169 + 3) / 4 * 4) * 4;   // fp32 4 x C4
+  static constexpr int o_k = o_q + HG * HT, o_v = o_k + HG * HT;
+  static constexpr int o_p = o_v + HG * HT;                   // 128 x 64 bf16
+  static constexpr int o_bias = o_p + 128 * 64 * 2;           // fp32: bq|bk|bv (this group) | bo
+  static constexpr int o_rpb = o_bias + (3 * NQG + NOUT) * 4; // fp32 [HG][169]
+  static constexpr int o_ln = o_rpb + ((HG * 169 + 3) / 4 * 4) * 4;   // fp32 4 x C4
   static constexpr int C4 = (C + 3) / 4 * 4;
   static constexpr int SMEM = o_ln + 4 * C4 * 4;
-  static constexpr int TMEM_COLS = (3 * NQ <= 128) ? 128 : (3 * NQ <= 256 ? 256 : 512);
+  static constexpr int PROJ_COLS = 3 * NQG > NOUT ? 3 * NQG : NOUT;
+  static constexpr int TMEM_COLS = (PROJ_COLS <= 128) ? 128 : (PROJ_COLS <= 256 ? 256 : 512);
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 // one token row: C bf16 -> fp32 registers, widest aligned vector loads
@@ -140,11 +151,64 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-template <int C, int HEADS, bool CROSS>
+// LayerNorm of one token row straight from global memory (three cached passes) for
+// wide C, where holding the row in registers would spill
+template <int C, int KC>
+__device__ __forceinline__ void ln_row_streamed(const __nv_bfloat16* src, const float* gamma,
+                                                const float* beta, float eps, unsigned char* tile,
+                                                int row) {
+  static_assert(C % 8 == 0, "streamed LN needs 16-byte rows");
+  float s = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < C / 8; ++ch) {
+    float v[8];
+    load_row_bf16<8>(src + ch * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < C / 8; ++ch) {
+    float v[8];
+    load_row_bf16<8>(src + ch * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+  }
+  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+  for (int ch = 0; ch < KC / 8; ++ch) {
+    float v[8];
+    if (ch < C / 8) {
+      load_row_bf16<8>(src + ch * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mean) * rstd, gamma[ch * 8 + j], beta[ch * 8 + j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    umma::st_chunk(tile, row, ch, 128, v);
+  }
+}
+
+template <int C, int KC, bool BIGC>
+__device__ __forceinline__ void ln_token(const __nv_bfloat16* src, const float* gamma,
+                                         const float* beta, float eps, unsigned char* tile, int row) {
+  if constexpr (BIGC) {
+    ln_row_streamed<C, KC>(src, gamma, beta, eps, tile, row);
+  } else {
+    float x[C];
+    load_row_bf16<C>(src, x);
+    ln_row_to_tile<C, KC>(x, gamma, beta, eps, tile, row);
+  }
+}
+
+template <int C, int HEADS, int HG, bool CROSS>
 __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   using namespace umma;
-  using K = AttnTc<C, HEADS, CROSS>;
-  constexpr int HDP = K::HDP, KC = K::KC, NQ = K::NQ, NOUT = K::NOUT, WIN = K::WIN, S = K::S;
+  using K = AttnTc<C, HEADS, HG, CROSS>;
+  constexpr int HDP = K::HDP, KC = K::KC, NQ = K::NQ, NQG = K::NQG, NOUT = K::NOUT;
+  constexpr int WIN = K::WIN, S = K::S, NG = K::NG;
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -152,20 +216,36 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = tid >> 6, i = tid & 63;            // window of the pair, slot in the window
+  const int hg = blockIdx.x % NG;                  // head group of this CTA
+  const int h0 = hg * HG;                          // first (absolute) head
   const AttnLayout L(C, HEADS, WIN);
   const float* blob = p.blob;
   float* sBias = reinterpret_cast<float*>(sm + K::o_bias);
   float* sRpb = reinterpret_cast<float*>(sm + K::o_rpb);
   float* sLn = reinterpret_cast<float*>(sm + K::o_ln);
 
-  // ---- one-time setup: weights + small tables -> smem, TMEM, barrier -----------
+  // ---- one-time setup: this group's weight slices + small tables -> smem -----------
   {
-    const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_wq);   // wq|wk|wv|wo contiguous
-    uint4* dst = reinterpret_cast<uint4*>(sm + K::o_wq);
-    constexpr int n16 = (3 * K::WQ_B + K::WO_B) / 16;
-    for (int e = tid; e < n16; e += 128) dst[e] = __ldg(src + e);
-    for (int e = tid; e < 3 * NQ + NOUT; e += 128) sBias[e] = __ldg(blob + L.o_tc_bias + e);
-    for (int e = tid; e < HEADS * 169; e += 128) sRpb[e] = __ldg(blob + L.o_rpb + e);
+    // q/k/v tiles in the blob are [KC/8][NQ rows][16 B]; take rows h0*32 .. +NQG
+    for (int part = 0; part < 3; ++part) {
+      const uint4* src = reinterpret_cast<const uint4*>(
+          blob + (part == 0 ? L.o_tc_wq : part == 1 ? L.o_tc_wk : L.o_tc_wv));
+      uint4* dst = reinterpret_cast<uint4*>(sm + (part == 0 ? K::o_wq : part == 1 ? K::o_wk : K::o_wv));
+      for (int e = tid; e < (KC / 8) * NQG; e += 128) {
+        const int ch = e / NQG, r = e - ch * NQG;
+        dst[e] = __ldg(src + (size_t)ch * NQ + h0 * HDP + r);
+      }
+    }
+    // out-proj tile [NQ/8][NOUT rows][16 B]: this group's K chunks are contiguous
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_wo) + (size_t)(h0 * HDP / 8) * NOUT;
+      uint4* dst = reinterpret_cast<uint4*>(sm + K::o_wo);
+      for (int e = tid; e < (NQG / 8) * NOUT; e += 128) dst[e] = __ldg(src + e);
+    }
+    for (int e = tid; e < 3 * NQG; e += 128)
+      sBias[e] = __ldg(blob + L.o_tc_bias + (e / NQG) * NQ + h0 * HDP + (e % NQG));
+    for (int e = tid; e < NOUT; e += 128) sBias[3 * NQG + e] = __ldg(blob + L.o_tc_bias + 3 * NQ + e);
+    for (int e = tid; e < HG * 169; e += 128) sRpb[e] = __ldg(blob + L.o_rpb + h0 * 169 + e);
     for (int e = tid; e < K::C4; e += 128) {
       sLn[e] = __ldg(blob + L.o_lnq_w + e);
       sLn[K::C4 + e] = __ldg(blob + L.o_lnq_b + e);
@@ -198,6 +278,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   const bool use_mask = p.pad_mask && pad_h > 0 && pad_w > 0;
   const int n_windows = p.B * nWh * nWw;
   const int n_tiles = (n_windows + 1) / 2;
+  const size_t n_tok = (size_t)p.B * p.H * p.W;
   const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(p.xq);
   const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(p.z);
   const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(p.resid);
@@ -208,7 +289,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   const int ic = i < S ? i : S - 1;
   const int rp_base = (ic / WIN + WIN - 1) * (2 * WIN - 1) + (ic % WIN) + WIN - 1;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += gridDim.x / NG) {
     // ---- token of this row ----------------------------------------------------
     const int wdx = tile * 2 + g;
     int tok = -1;
@@ -223,13 +304,10 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     }
     // ---- LN prologue -------------------------------------------------------------
     if (tok >= 0) {
-      float x[C];
-      load_row_bf16<C>(xq + (size_t)tok * C, x);
-      ln_row_to_tile<C, KC>(x, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
-      if (CROSS) {
-        load_row_bf16<C>(zz + (size_t)tok * C, x);
-        ln_row_to_tile<C, KC>(x, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps, sm + K::o_zn, tid);
-      }
+      ln_token<C, KC, K::BIGC>(xq + (size_t)tok * C, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+      if (CROSS)
+        ln_token<C, KC, K::BIGC>(zz + (size_t)tok * C, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps,
+                                 sm + K::o_zn, tid);
     } else {
       const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -242,20 +320,20 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     tc_fence_before();
     __syncthreads();
 
-    // ---- q / k / v projections ------------------------------------------------------
+    // ---- q / k / v projections of this head group --------------------------------------
     if (tid == 0) {
       tc_fence_after();
-      constexpr uint32_t idq = idesc_bf16(128, NQ, false, false);
+      constexpr uint32_t idq = idesc_bf16(128, NQG, false, false);
       const uint32_t a_kv = CROSS ? a_zn : a_xn;
 #pragma unroll
       for (int s = 0; s < KC / 16; ++s)
-        mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wq, NQ, s), idq, s > 0);
+        mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wq, NQG, s), idq, s > 0);
 #pragma unroll
       for (int s = 0; s < KC / 16; ++s)
-        mma_bf16(tmem + NQ, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wk, NQ, s), idq, s > 0);
+        mma_bf16(tmem + NQG, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wk, NQG, s), idq, s > 0);
 #pragma unroll
       for (int s = 0; s < KC / 16; ++s)
-        mma_bf16(tmem + 2 * NQ, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wv, NQ, s), idq, s > 0);
+        mma_bf16(tmem + 2 * NQG, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wv, NQG, s), idq, s > 0);
       mma_commit(&bar);
     }
     mbar_wait(&bar, phase);
@@ -265,11 +343,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     for (int part = 0; part < 3; ++part) {
       unsigned char* base = sm + (part == 0 ? K::o_q : part == 1 ? K::o_k : K::o_v);
 #pragma unroll
-      for (int h = 0; h < HEADS; ++h) {
+      for (int h = 0; h < HG; ++h) {
         float v[32];
-        tmem_ld32(trow + part * NQ + h * HDP, v);
+        tmem_ld32(trow + part * NQG + h * HDP, v);
         tmem_ld_wait();
-        const float* bs = sBias + part * NQ + h * HDP;
+        const float* bs = sBias + part * NQG + h * HDP;
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += bs[c];
 #pragma unroll
@@ -280,10 +358,10 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     const unsigned long long vmask =
         (unsigned long long)valid_bits[2 * g] | ((unsigned long long)valid_bits[2 * g + 1] << 32);
     const bool mask_me = use_mask && wdx < n_windows;
-    float inv_sum[HEADS];
+    float inv_sum[HG];
 
 #pragma unroll
-    for (int h = 0; h < HEADS; ++h) {
+    for (int h = 0; h < HG; ++h) {
       // ---- S = Q_h [K_A;K_B]^T -------------------------------------------------------
       fence_proxy_async();
       tc_fence_before();
@@ -366,7 +444,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       }
     }
 
-    // ---- output projection -------------------------------------------------------------
+    // ---- output projection (this group's K slice) --------------------------------------
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -374,14 +452,14 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       tc_fence_after();
       constexpr uint32_t idy = idesc_bf16(128, NOUT, false, false);
 #pragma unroll
-      for (int s = 0; s < NQ / 16; ++s)
+      for (int s = 0; s < NQG / 16; ++s)
         mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wo, NOUT, s), idy, s > 0);
       mma_commit(&bar);
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
-    {
+    if constexpr (!K::SPLIT) {
       float y[NOUT];
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + c0, y + c0);
@@ -389,7 +467,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       if (tok >= 0) {
         float r[C];
         load_row_bf16<C>(rs + (size_t)tok * C, r);
-        const float* bo = sBias + 3 * NQ;
+        const float* bo = sBias + 3 * NQG;
 #pragma unroll
         for (int c = 0; c < C; ++c) y[c] += bo[c] + r[c];
         if (CROSS) {
@@ -398,6 +476,20 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
           for (int c = 0; c < C; ++c) y[c] += r[c];
         }
         store_row_bf16<C>(out + (size_t)tok * C, y);
+      }
+    } else {
+      // fp32 partial of this head group -> workspace [NG][n_tok][C]
+      static_assert(!K::SPLIT || C % 16 == 0 || C % 8 == 0, "partial rows are stored 8 floats at a time");
+      float* wrow = static_cast<float*>(p.ws) + ((size_t)hg * n_tok + (size_t)(tok >= 0 ? tok : 0)) * C;
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float y[8];
+        tmem_ld8(trow + c0, y);
+        tmem_ld_wait();
+        if (tok >= 0) {
+          *reinterpret_cast<float4*>(wrow + c0) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
       }
     }
     // the next iteration's first barrier orders these TMEM reads before its MMAs
@@ -408,35 +500,89 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
-template <int C, int HEADS>
+// out = resid (+ z) + bo + sum_g partial[g]   (fixed summation order: deterministic)
+template <int C>
+__global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int ng, size_t n_tok,
+                                                          const __nv_bfloat16* rs,
+                                                          const __nv_bfloat16* zz,
+                                                          const float* __restrict__ bo,
+                                                          __nv_bfloat16* out) {
+  const size_t n_vec = n_tok * (C / 8);
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = v * 8;
+    const int c0 = (int)(e0 % C);
+    float acc[8], t[8];
+    load_row_bf16<8>(rs + e0, acc);
+    if (zz) {
+      load_row_bf16<8>(zz + e0, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bo + c0 + j);
+    for (int gi = 0; gi < ng; ++gi) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0 + 4));
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    store_row_bf16<8>(out + e0, acc);
+  }
+}
+
+template <int C, int HEADS, int HG>
 static int launch_attn_tc_ch(const AttnParams& p, cudaStream_t stream) {
+  constexpr int NG = HEADS / HG;
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
-  const int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+  const int per_group = n_tiles < 148 * 4 / NG ? n_tiles : 148 * 4 / NG;
+  const int grid = per_group * NG;
+  if (NG > 1) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn_tc: workspace required for C=%d", C);
   if (p.cross) {
-    using K = AttnTc<C, HEADS, true>;
-    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, true>, K::SMEM));
-    window_attn_tc_kernel<C, HEADS, true><<<grid, 128, K::SMEM, stream>>>(p);
+    using K = AttnTc<C, HEADS, HG, true>;
+    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, HG, true>, K::SMEM));
+    window_attn_tc_kernel<C, HEADS, HG, true><<<grid, 128, K::SMEM, stream>>>(p);
   } else {
-    using K = AttnTc<C, HEADS, false>;
-    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, false>, K::SMEM));
-    window_attn_tc_kernel<C, HEADS, false><<<grid, 128, K::SMEM, stream>>>(p);
+    using K = AttnTc<C, HEADS, HG, false>;
+    HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, HG, false>, K::SMEM));
+    window_attn_tc_kernel<C, HEADS, HG, false><<<grid, 128, K::SMEM, stream>>>(p);
   }
   count_launch();
   HRF_CUDA(cudaGetLastError());
+  if constexpr (NG > 1) {
+    const AttnLayout L(C, HEADS, 7);
+    const size_t n_tok = (size_t)p.B * p.H * p.W;
+    const size_t n_vec = n_tok * (C / 8);
+    const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
+    attn_reduce_kernel<C><<<rgrid, 256, 0, stream>>>(
+        static_cast<const float*>(p.ws), NG, n_tok, static_cast<const __nv_bfloat16*>(p.resid),
+        p.cross ? static_cast<const __nv_bfloat16*>(p.z) : nullptr, p.blob + L.o_tc_bias + 3 * L.tc_NQ,
+        static_cast<__nv_bfloat16*>(p.out));
+    count_launch();
+    HRF_CUDA(cudaGetLastError());
+  }
   return HRF_OK;
 }
 
 // true when the tensor-core kernel covers this problem
 static bool attn_tc_supported(const AttnParams& p) {
   if (p.win != 7 || p.C % p.heads != 0 || p.C / p.heads != 18) return false;
-  return p.C == 18 || p.C == 36;   // C = 72 / 144 need streamed weights (smem): SIMT kernel for now
+  return p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144;
+}
+// fp32 workspace bytes of the split-head variants (0 when the CTA finishes the block itself)
+static size_t attn_tc_workspace_bytes(int B, int H, int W, int C, int heads) {
+  if (C / heads != 18) return 0;
+  const int ng = C == 72 ? 2 : C == 144 ? 4 : 0;
+  return (size_t)ng * B * H * W * C * sizeof(float);
 }
 
 static int launch_window_attn_tc(const AttnParams& p, cudaStream_t stream) {
   switch (p.C) {
-    case 18: return launch_attn_tc_ch<18, 1>(p, stream);
-    case 36: return launch_attn_tc_ch<36, 2>(p, stream);
+    case 18: return launch_attn_tc_ch<18, 1, 1>(p, stream);
+    case 36: return launch_attn_tc_ch<36, 2, 2>(p, stream);
+    case 72: return launch_attn_tc_ch<72, 4, 2>(p, stream);
+    case 144: return launch_attn_tc_ch<144, 8, 2>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "attn_tc: C=%d", p.C);
 }

@@ -181,8 +181,11 @@ def window_attention(x, kv, blobs, heads, win=7, with_pad_mask=False, eps=1e-6, 
     with _timed('mwca' if kv else 'lsa', C=Cc, launches=passes,
                 bytes=float(n * passes * (3 if kv else 2) * Cc * s),
                 flops=float(n * passes * (8 * Cc * Cc + 4 * S * Cc))):
+        ws_bytes = lib.hrf_attn_workspace_bytes(C.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         check(lib.hrf_window_attn_fwd(C.byref(d), x.data_ptr(), _ptr_array(kv), _ptr_array(blobs),
-                                      out.data_ptr(), _stream()))
+                                      out.data_ptr(), ws.data_ptr() if ws_bytes else None,
+                                      ws_bytes, _stream()))
     return out
 
 
@@ -195,8 +198,10 @@ def mixffn(x, blob, hidden, eps=1e-6, out=None):
     n = B * H * W
     with _timed('mixffn', C=Cc, launches=1, bytes=float(n * 2 * Cc * x.element_size()),
                 flops=float(n * (4 * Cc * hidden + 18 * hidden))):
+        ws_bytes = lib.hrf_ffn_workspace_bytes(C.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         check(lib.hrf_mixffn_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(),
-                                 _stream()))
+                                 ws.data_ptr() if ws_bytes else None, ws_bytes, _stream()))
     return out
 
 

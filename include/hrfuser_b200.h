@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 2
+#define HRF_ABI_VERSION 3
 
 enum { HRF_F32 = 0, HRF_BF16 = 1 };
 enum {
@@ -83,11 +83,17 @@ int hrf_attn_pack(const HrfAttnDesc* d,
                   const float* wq, const float* bq, const float* wk, const float* bk,
                   const float* wv, const float* bv, const float* wo, const float* bo,
                   const float* rpb_table, float* blob_out);
+/* Scratch the call needs (device bytes; 0 for most shapes).  Wide low-resolution
+ * branches (C = 72, 144 in bf16) split the heads of a window pair over several
+ * CTAs and sum their fp32 partial out-projections from this workspace. */
+size_t hrf_attn_workspace_bytes(const HrfAttnDesc* d);
 /* kv: array of n_kv device pointers (ignored when n_kv == 0);
- * blobs: array of max(1, n_kv) device pointers to packed blobs.
- * out may alias x only when n_kv == 0 is false ... no aliasing is allowed. */
+ * blobs: array of max(1, n_kv) device pointers to packed blobs;
+ * workspace: >= hrf_attn_workspace_bytes(d) bytes (may be NULL when that is 0).
+ * out must not alias x or any kv. */
 int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
-                        const float* const* blobs, void* out, void* stream);
+                        const float* const* blobs, void* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * MixFFN (CrossFFN, hrformer.py:267-295) fused with the LayerNorm in front and
@@ -109,8 +115,10 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b,
                  const float* wd, const float* bd, const float* const bn2[4],
                  const float* w2, const float* b2, const float* const bn3[4],
                  float bn_eps, float* blob_out);
+/* scratch bytes (0 except C = 144 in bf16, whose 8 hidden chunks are split over CTAs) */
+size_t hrf_ffn_workspace_bytes(const HrfFfnDesc* d);
 int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Multi-resolution exchange (HRModule.forward hrnet.py:184-207 with the fuse

@@ -47,9 +47,9 @@ def test_validation_errors_are_codes_with_messages(built_lib):
     assert built_lib.hrf_attn_pack(C.byref(d), *([buf] * 13), buf) == -2
     assert built_lib.hrf_attn_blob_floats(None) == 0
     f = _lib.FfnDesc(1, 8, 8, 18, 70, 0, 1e-6)                   # hidden not a multiple of 4
-    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None) == -2
+    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None, 0, None) == -2
     f = _lib.FfnDesc(1, 8, 8, 18, 72, 0, 1e-6)
-    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None) == -1   # null pointers
+    assert built_lib.hrf_mixffn_fwd(C.byref(f), None, None, None, None, 0, None) == -1   # null pointers
 
 
 def test_attn_packer_layout(built_lib):
