@@ -67,17 +67,25 @@ __device__ __forceinline__ float gelu_as(float x) {
   return 0.5f * x * (x >= 0.f ? 2.0f - pe : pe);
 }
 
+constexpr int kFfnTcThreads = 512;
+
+// 512 threads = 16 warps: warp w reads TMEM lanes 32*(w%4).. (its quadrant q) and
+// belongs to group gq = w/4.  Epilogue and depthwise work is dealt out in units of
+// (row, 8-channel chunk) so all four groups of a quadrant stay busy and no thread
+// holds more than 8 accumulators (<= 64 registers -> 2 CTAs = 32 warps per SM).
 template <int C, int CPG>
-__global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
+__global__ void __launch_bounds__(kFfnTcThreads, (FfnTc<C, CPG>::SMEM * 2 <= 226 * 1024) ? 2 : 1)
+mixffn_tc_kernel(FfnParams p) {
   using namespace umma;
   using K = FfnTc<C, CPG>;
   constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH, NG = K::NG;
+  constexpr int NT = kFfnTcThreads;
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, q = warp & 3;          // warpgroup (M tile / channel parity), TMEM quadrant
+  const int gq = warp >> 2, q = warp & 3;          // work group, TMEM quadrant
   const int row = q * 32 + lane;                   // TMEM lane == row of the M=128 tiles
   const int cg = blockIdx.x % NG;                  // chunk group of this CTA
   const FfnLayout L(C, K::HID);
@@ -93,20 +101,20 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
     const uint4* s2 = reinterpret_cast<const uint4*>(blob + L.o_tc_w2) + (size_t)cg * CPG * (NOUT * N1 * 2 / 16);
     uint4* d1 = reinterpret_cast<uint4*>(sm + K::o_w1);
     uint4* d2 = reinterpret_cast<uint4*>(sm + K::o_w2);
-    for (int e = tid; e < CPG * N1 * KC * 2 / 16; e += 256) d1[e] = __ldg(s1 + e);
-    for (int e = tid; e < CPG * NOUT * N1 * 2 / 16; e += 256) d2[e] = __ldg(s2 + e);
-    for (int e = tid; e < CPG * 880; e += 256) sF[e] = __ldg(blob + L.o_tc_f32 + cg * CPG * 880 + e);
-    for (int e = tid; e < NOUT; e += 256) sF[CPG * 880 + e] = __ldg(blob + L.o_tc_f32 + NCH * 880 + e);
-    for (int e = tid; e < K::C4; e += 256) {
+    for (int e = tid; e < CPG * N1 * KC * 2 / 16; e += NT) d1[e] = __ldg(s1 + e);
+    for (int e = tid; e < CPG * NOUT * N1 * 2 / 16; e += NT) d2[e] = __ldg(s2 + e);
+    for (int e = tid; e < CPG * 880; e += NT) sF[e] = __ldg(blob + L.o_tc_f32 + cg * CPG * 880 + e);
+    for (int e = tid; e < NOUT; e += NT) sF[CPG * 880 + e] = __ldg(blob + L.o_tc_f32 + NCH * 880 + e);
+    for (int e = tid; e < K::C4; e += NT) {
       sLn[e] = __ldg(blob + L.o_ln_w + e);
       sLn[K::C4 + e] = __ldg(blob + L.o_ln_b + e);
     }
     // zero both XN tiles (rows 52..127 of tile 1 are never written again) and H2
     // (its 10th chunk, channels 72..79, stays zero)
     uint4* z = reinterpret_cast<uint4*>(sm + K::o_xn);
-    for (int e = tid; e < 2 * K::XT / 16; e += 256) z[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < 2 * K::XT / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
     z = reinterpret_cast<uint4*>(sm + K::o_h2);
-    for (int e = tid; e < 10 * 128; e += 256) z[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < 10 * 128; e += NT) z[e] = make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   if (tid == 0) {
@@ -127,6 +135,9 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
   const int n_tiles = p.B * tiles_x * tiles_y;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+  // epilogue-1 units of this quadrant: (M tile 0, chunk 0..8) and, where tile 1 has
+  // live rows in this quadrant (halo tokens 128..179), (M tile 1, chunk 0..8)
+  const int n_units = (128 + q * 32 < K::NHALO) ? 18 : 9;
 
   for (int tile = blockIdx.x / NG; tile < n_tiles; tile += gridDim.x / NG) {
     const int b = tile / (tiles_x * tiles_y);
@@ -170,35 +181,32 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
       phase ^= 1;
       tc_fence_after();
 
-      // ---- epilogue 1: warpgroup wg owns M tile wg ----------------------------------
+      // ---- epilogue 1: + b1, GELU, zero outside the image -> H1 -----------------------
       const float* fb = sF + c * 880;
-      {
-        const int t = wg * 128 + row;               // halo token
-        if (wg * 128 + q * 32 < K::NHALO) {         // warp-uniform: tcgen05.ld is warp-collective
-          float v[72];
-          const uint32_t col = trow + wg * N1;
-          tmem_ld32(col, v);
-          tmem_ld32(col + 32, v + 32);
-          tmem_ld8(col + 64, v + 64);
-          tmem_ld_wait();
-          if (t < K::NHALO) {
-            const bool in = sIn[t] != 0;
+#pragma unroll 1
+      for (int u = gq; u < n_units; u += 4) {         // warp-uniform trip count
+        const int mt = u >= 9 ? 1 : 0, ch = u - mt * 9;
+        float v[8];
+        tmem_ld8(trow + mt * N1 + ch * 8, v);
+        tmem_ld_wait();
+        const int t = mt * 128 + row;                 // halo token
+        if (t < K::NHALO) {
+          const bool in = sIn[t] != 0;
 #pragma unroll
-            for (int j = 0; j < 72; ++j) v[j] = in ? gelu_as(v[j] + fb[j]) : 0.f;
-#pragma unroll
-            for (int ch = 0; ch < 9; ++ch) st_chunk(sm + K::o_h1, t, ch, K::H1R, v + 8 * ch);
-          }
+          for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + fb[ch * 8 + j]) : 0.f;
+          st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
         }
       }
       tc_fence_before();
       __syncthreads();
 
-      // ---- depthwise 3x3 + GELU: thread = (output token, every other channel chunk) --
+      // ---- depthwise 3x3 + GELU: unit = (output token, 8-channel chunk) ---------------
       {
         const int o = tid & 127, oy = o >> 4, ox = o & 15;
         const float* wd = fb + 80;
         const float* bd = fb + 800;
-        for (int ch = wg; ch < 9; ch += 2) {
+#pragma unroll 1
+        for (int ch = gq; ch < 9; ch += 4) {
           float acc[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = bd[ch * 8 + j];
@@ -242,39 +250,38 @@ __global__ void __launch_bounds__(256) mixffn_tc_kernel(FfnParams p) {
       tc_fence_after();
     }
 
-    // ---- epilogue 2 (warpgroup 0): + b2, GELU, + residual ----------------------------
-    if constexpr (K::SPLIT) {
-      if (wg == 0) {      // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
-        const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
-        const bool in = h < p.H && w < p.W;
-        const size_t n_tok = (size_t)p.B * p.H * p.W;
-        float* wrow = static_cast<float*>(p.ws) +
-                      ((size_t)cg * n_tok + (in ? (size_t)(b * p.H + h) * p.W + w : 0)) * C;
+    // ---- epilogue 2: unit = (output token, 8-channel chunk of the C outputs) ----------
+    {
+      const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
+      const bool in = h < p.H && w < p.W;
+      const size_t tok = in ? (size_t)(b * p.H + h) * p.W + w : 0;
+      const float* b2 = sF + CPG * 880;
+#pragma unroll 1
+      for (int cc = gq; cc * 8 < C; cc += 4) {        // warp-uniform trip count
+        float y[8];
+        tmem_ld8(trow + K::Y_COL + cc * 8, y);
+        tmem_ld_wait();
+        if (!in) continue;
+        if constexpr (K::SPLIT) {      // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
+          const size_t n_tok = (size_t)p.B * p.H * p.W;
+          float* wrow = static_cast<float*>(p.ws) + ((size_t)cg * n_tok + tok) * C + cc * 8;
+          *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else {                       // + b2, GELU, + residual; rows are only 4-byte aligned
+          const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + tok * C + cc * 8);
+          uint32_t* orow = reinterpret_cast<uint32_t*>(out + tok * C + cc * 8);
 #pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 8) {
-          float y[8];
-          tmem_ld8(trow + K::Y_COL + c0, y);
-          tmem_ld_wait();
-          if (in) {
-            *reinterpret_cast<float4*>(wrow + c0) = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          for (int j = 0; j < 4; ++j) {
+            if (cc * 8 + 2 * j < C) {
+              const uint32_t u = __ldg(xr + j);
+              const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+              const float a0 = r.x + gelu_as(y[2 * j] + b2[cc * 8 + 2 * j]);
+              const float a1 = r.y + gelu_as(y[2 * j + 1] + b2[cc * 8 + 2 * j + 1]);
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+              orow[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
           }
         }
-      }
-    } else if (wg == 0) {
-      float y[NOUT];
-#pragma unroll
-      for (int c0 = 0; c0 < NOUT; c0 += 16) tmem_ld16(trow + K::Y_COL + c0, y + c0);
-      tmem_ld_wait();
-      const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
-      if (h < p.H && w < p.W) {
-        const size_t off = ((size_t)(b * p.H + h) * p.W + w) * C;
-        float r[C];
-        load_row_bf16<C>(x + off, r);
-        const float* b2 = sF + CPG * 880;
-#pragma unroll
-        for (int cc = 0; cc < C; ++cc) y[cc] = r[cc] + gelu_as(y[cc] + b2[cc]);
-        store_row_bf16<C>(out + off, y);
       }
     }
     // next iteration: its first barrier (after the LN prologue) orders these TMEM reads
@@ -329,7 +336,7 @@ static int launch_ffn_tc_c(const FfnParams& p, cudaStream_t stream) {
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
   HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C, CPG>, K::SMEM));
-  mixffn_tc_kernel<C, CPG><<<grid, 256, K::SMEM, stream>>>(p);
+  mixffn_tc_kernel<C, CPG><<<grid, kFfnTcThreads, K::SMEM, stream>>>(p);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   if constexpr (K::SPLIT) {

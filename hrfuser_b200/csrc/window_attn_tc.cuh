@@ -54,10 +54,12 @@ struct AttnTc {
   static constexpr int o_wq = 0, o_wk = o_wq + WQ_B, o_wv = o_wk + WQ_B, o_wo = o_wv + WQ_B;
   static constexpr int o_xn = o_wo + WO_B;
   static constexpr int o_zn = o_xn + XT;
-  static constexpr int o_q = o_zn + (CROSS ? 128 * KC * 2 : 0);
-  static constexpr int o_k = o_q + HG * HT, o_v = o_k + HG * HT;
-  static constexpr int o_p = o_v + HG * HT;                   // 128 x 64 bf16
-  static constexpr int o_bias = o_p + 128 * 64 * 2;           // fp32: bq|bk|bv (this group) | bo
+  // per head [Q_h | K_h] (2 x HT); the 128 x 64 bf16 P tile of head h reuses exactly
+  // these 16 KB once S = Q_h K_h^T has completed
+  static constexpr int o_qk = o_zn + (CROSS ? 128 * KC * 2 : 0);
+  static constexpr int o_v = o_qk + HG * 2 * HT;
+  static constexpr int o_bias = o_v + HG * HT;                // fp32: bq|bk|bv (this group) | bo
+  static_assert(2 * HT == 128 * 64 * 2, "P tile must fit the Q_h|K_h pair");
   static constexpr int o_rpb = o_bias + (3 * NQG + NOUT) * 4; // fp32 [HG][169]
   static constexpr int o_ln = o_rpb + ((HG * 169 + 3) / 4 * 4) * 4;   // fp32 4 x C4
   static constexpr int C4 = (C + 3) / 4 * 4;
@@ -269,8 +271,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   const uint32_t a_wq = smem_u32(sm + K::o_wq), a_wk = smem_u32(sm + K::o_wk);
   const uint32_t a_wv = smem_u32(sm + K::o_wv), a_wo = smem_u32(sm + K::o_wo);
   const uint32_t a_xn = smem_u32(sm + K::o_xn), a_zn = smem_u32(sm + K::o_zn);
-  const uint32_t a_q = smem_u32(sm + K::o_q), a_k = smem_u32(sm + K::o_k);
-  const uint32_t a_v = smem_u32(sm + K::o_v), a_p = smem_u32(sm + K::o_p);
+  const uint32_t a_qk = smem_u32(sm + K::o_qk), a_v = smem_u32(sm + K::o_v);
 
   const int nWh = ceil_div(p.H, WIN), nWw = ceil_div(p.W, WIN);
   const int pad_h = nWh * WIN - p.H, pad_w = nWw * WIN - p.W;
@@ -341,9 +342,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     tc_fence_after();
 #pragma unroll
     for (int part = 0; part < 3; ++part) {
-      unsigned char* base = sm + (part == 0 ? K::o_q : part == 1 ? K::o_k : K::o_v);
 #pragma unroll
       for (int h = 0; h < HG; ++h) {
+        unsigned char* dst = part == 0 ? sm + K::o_qk + h * 2 * K::HT
+                           : part == 1 ? sm + K::o_qk + h * 2 * K::HT + K::HT
+                                       : sm + K::o_v + h * K::HT;
         float v[32];
         tmem_ld32(trow + part * NQG + h * HDP, v);
         tmem_ld_wait();
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += bs[c];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) st_chunk(base + h * K::HT, tid, ch, 128, v + 8 * ch);
+        for (int ch = 0; ch < 4; ++ch) st_chunk(dst, tid, ch, 128, v + 8 * ch);
       }
     }
 
@@ -371,8 +374,8 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         constexpr uint32_t ids = idesc_bf16(128, 128, false, false);
 #pragma unroll
         for (int s = 0; s < HDP / 16; ++s)
-          mma_bf16(tmem, desc_kmajor(a_q + h * K::HT, 128, s), desc_kmajor(a_k + h * K::HT, 128, s),
-                   ids, s > 0);
+          mma_bf16(tmem, desc_kmajor(a_qk + h * 2 * K::HT, 128, s),
+                   desc_kmajor(a_qk + h * 2 * K::HT + K::HT, 128, s), ids, s > 0);
         mma_commit(&bar);
       }
       mbar_wait(&bar, phase);
@@ -407,10 +410,12 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       for (int j = S; j < 56; ++j) sc[j] = 0.f;
       inv_sum[h] = 1.0f / sum;
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) st_chunk(sm + K::o_p, tid, ch, 128, sc + 8 * ch);
+      unsigned char* sP = sm + K::o_qk + h * 2 * K::HT;     // Q_h | K_h are dead: S is complete
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) st_chunk(sP, tid, ch, 128, sc + 8 * ch);
       {
         const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        st_chunk(sm + K::o_p, tid, 7, 128, zero);
+        st_chunk(sP, tid, 7, 128, zero);
       }
 
       // ---- O = P V (both windows' V; each row keeps its own) -------------------------
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         for (int g2 = 0; g2 < 2; ++g2)
 #pragma unroll
           for (int s = 0; s < 4; ++s)
-            mma_bf16(tmem + g2 * HDP, desc_kmajor(a_p, 128, s),
+            mma_bf16(tmem + g2 * HDP, desc_kmajor(a_qk + h * 2 * K::HT, 128, s),
                      desc_mnmajor(a_v + h * K::HT + g2 * 64 * 16, 128, s), ido, s > 0);
         mma_commit(&bar);
       }
@@ -536,7 +541,7 @@ static int launch_attn_tc_ch(const AttnParams& p, cudaStream_t stream) {
   constexpr int NG = HEADS / HG;
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
-  const int per_group = n_tiles < 148 * 4 / NG ? n_tiles : 148 * 4 / NG;
+  const int per_group = n_tiles < 148 * 4 / NG ? n_tiles : 148 * 4 / NG;   // <= 4 CTAs / SM (TMEM)
   const int grid = per_group * NG;
   if (NG > 1) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn_tc: workspace required for C=%d", C);
   if (p.cross) {
