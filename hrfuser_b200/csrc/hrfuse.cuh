@@ -19,25 +19,47 @@ struct PwLayout {
   }
 };
 constexpr int kPwThreads = 256;
-constexpr int kPwTokens = 64;
+
+// two consecutive channels as one 4-byte (bf16) / 8-byte (fp32) access; channel
+// counts are even, so rows of any token start pair-aligned
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  __device__ static float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ static void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  __device__ static float2 ld(const __nv_bfloat16* p) {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  }
+  __device__ static void st(__nv_bfloat16* p, float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&h);
+  }
+};
 
 struct PwParams {
   const void* x; const float* blob; void* out;
   int ntok, Cin, Cout, relu;
 };
 
-template <typename T, int CT>
+// TOK tokens per CTA: 64 for full-resolution maps, 16 for the low-resolution branches
+// (1 920 tokens at C=144) so that the grid still covers the 148 SMs
+template <typename T, int CT, int TOK>
 __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
   extern __shared__ __align__(16) float smem[];
   const PwLayout L(p.Cin, p.Cout);
   const T* x = static_cast<const T*>(p.x);
   T* out = static_cast<T*>(p.out);
-  const int t0 = blockIdx.x * kPwTokens;
-  const int m = min(kPwTokens, p.ntok - t0);
+  const int t0 = blockIdx.x * TOK;
+  const int m = min(TOK, p.ntok - t0);
   // stage the token tile (contiguous in memory) as fp32, zero-padded to lda
-  for (int e = threadIdx.x; e < kPwTokens * L.lda; e += blockDim.x) {
-    const int r = e / L.lda, c = e - r * L.lda;
-    smem[e] = (r < m && c < p.Cin) ? Elem<T>::ld(x + (size_t)(t0 + r) * p.Cin + c) : 0.f;
+  const int hp = L.lda / 2;
+  for (int e = threadIdx.x; e < TOK * hp; e += blockDim.x) {
+    const int r = e / hp, c = (e - r * hp) * 2;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < m && c < p.Cin) v = Pair<T>::ld(x + (size_t)(t0 + r) * p.Cin + c);
+    *reinterpret_cast<float2*>(smem + r * L.lda + c) = v;
   }
   __syncthreads();
   const float* bias = p.blob + L.o_b;
@@ -49,18 +71,24 @@ __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
   });
 }
 
-template <typename T>
-static int launch_pw(const PwParams& p, cudaStream_t stream) {
+template <typename T, int TOK>
+static int launch_pw_tok(const PwParams& p, cudaStream_t stream) {
   const PwLayout L(p.Cin, p.Cout);
-  const size_t smem = (size_t)kPwTokens * L.lda * sizeof(float);
+  const size_t smem = (size_t)TOK * L.lda * sizeof(float);
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "pw: Cin=%d too wide", p.Cin);
-  HRF_REQUIRE(p.Cout % 2 == 0, HRF_EUNSUPPORTED, "pw: Cout=%d must be even", p.Cout);
-  auto kern = (p.Cout % 4 == 0) ? pw_kernel<T, 4> : pw_kernel<T, 2>;
+  auto kern = (p.Cout % 4 == 0) ? pw_kernel<T, 4, TOK> : pw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
-  kern<<<ceil_div(p.ntok, kPwTokens), kPwThreads, smem, stream>>>(p);
+  kern<<<ceil_div(p.ntok, TOK), kPwThreads, smem, stream>>>(p);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
+}
+
+template <typename T>
+static int launch_pw(const PwParams& p, cudaStream_t stream) {
+  HRF_REQUIRE(p.Cout % 2 == 0 && p.Cin % 2 == 0, HRF_EUNSUPPORTED,
+              "pw: Cin=%d / Cout=%d must be even", p.Cin, p.Cout);
+  return p.ntok >= 148 * 2 * 64 ? launch_pw_tok<T, 64>(p, stream) : launch_pw_tok<T, 16>(p, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -80,7 +108,7 @@ struct DwPwParams {
   int B, H, W, Ho, Wo, Cin, Cout, relu;
 };
 
-template <typename T, int CT>
+template <typename T, int CT, int TOK>
 __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
   extern __shared__ __align__(16) float smem[];
   const DwPwLayout D(p.Cin, p.Cout);
@@ -88,17 +116,18 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
   const T* x = static_cast<const T*>(p.x);
   T* out = static_cast<T*>(p.out);
   const int ntok = p.B * p.Ho * p.Wo;
-  const int t0 = blockIdx.x * kPwTokens;
-  const int m = min(kPwTokens, ntok - t0);
+  const int t0 = blockIdx.x * TOK;
+  const int m = min(TOK, ntok - t0);
   const float* wd = p.blob + D.o_wd;
   const float* bd = p.blob + D.o_bd;
-  for (int e = threadIdx.x; e < kPwTokens * L.lda; e += blockDim.x) {
-    const int r = e / L.lda, c = e - r * L.lda;
-    float s = 0.f;
+  const int hp = L.lda / 2;
+  for (int e = threadIdx.x; e < TOK * hp; e += blockDim.x) {
+    const int r = e / hp, c = (e - r * hp) * 2;
+    float2 s = make_float2(0.f, 0.f);
     if (r < m && c < p.Cin) {
       const int t = t0 + r;
       const int b = t / (p.Ho * p.Wo), oy = (t / p.Wo) % p.Ho, ox = t % p.Wo;
-      s = __ldg(bd + c);
+      s = __ldg(reinterpret_cast<const float2*>(bd + c));
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const int iy = oy * 2 - 1 + dy;
@@ -107,12 +136,14 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
         for (int dx = 0; dx < 3; ++dx) {
           const int ix = ox * 2 - 1 + dx;
           if (ix < 0 || ix >= p.W) continue;
-          s = fmaf(Elem<T>::ld(x + ((size_t)(b * p.H + iy) * p.W + ix) * p.Cin + c),
-                   __ldg(wd + (dy * 3 + dx) * p.Cin + c), s);
+          const float2 v = Pair<T>::ld(x + ((size_t)(b * p.H + iy) * p.W + ix) * p.Cin + c);
+          const float2 w = __ldg(reinterpret_cast<const float2*>(wd + (dy * 3 + dx) * p.Cin + c));
+          s.x = fmaf(v.x, w.x, s.x);
+          s.y = fmaf(v.y, w.y, s.y);
         }
       }
     }
-    smem[e] = s;
+    *reinterpret_cast<float2*>(smem + r * L.lda + c) = s;
   }
   __syncthreads();
   const float* pw = p.blob + D.o_pw;
@@ -125,18 +156,25 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
   });
 }
 
-template <typename T>
-static int launch_dwpw(const DwPwParams& p, cudaStream_t stream) {
+template <typename T, int TOK>
+static int launch_dwpw_tok(const DwPwParams& p, cudaStream_t stream) {
   const PwLayout L(p.Cin, p.Cout);
-  const size_t smem = (size_t)kPwTokens * L.lda * sizeof(float);
+  const size_t smem = (size_t)TOK * L.lda * sizeof(float);
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "dwpw: Cin=%d too wide", p.Cin);
-  HRF_REQUIRE(p.Cout % 2 == 0, HRF_EUNSUPPORTED, "dwpw: Cout=%d must be even", p.Cout);
-  auto kern = (p.Cout % 4 == 0) ? dwpw_kernel<T, 4> : dwpw_kernel<T, 2>;
+  auto kern = (p.Cout % 4 == 0) ? dwpw_kernel<T, 4, TOK> : dwpw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
-  kern<<<ceil_div(p.B * p.Ho * p.Wo, kPwTokens), kPwThreads, smem, stream>>>(p);
+  kern<<<ceil_div(p.B * p.Ho * p.Wo, TOK), kPwThreads, smem, stream>>>(p);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
+}
+
+template <typename T>
+static int launch_dwpw(const DwPwParams& p, cudaStream_t stream) {
+  HRF_REQUIRE(p.Cout % 2 == 0 && p.Cin % 2 == 0, HRF_EUNSUPPORTED,
+              "dwpw: Cin=%d / Cout=%d must be even", p.Cin, p.Cout);
+  return p.B * p.Ho * p.Wo >= 148 * 2 * 64 ? launch_dwpw_tok<T, 64>(p, stream)
+                                           : launch_dwpw_tok<T, 16>(p, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -155,16 +193,20 @@ struct FuseParams {
   int B, H, W, C, n_up, n_same, relu;
 };
 
+// thread = (token, channel pair); 32-bit index math (tensors are < 2^31 elements)
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
-  const size_t total = (size_t)p.B * p.H * p.W * p.C;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % p.C);
-    const size_t t = e / p.C;
-    const int w = (int)(t % p.W), h = (int)((t / p.W) % p.H), b = (int)(t / ((size_t)p.W * p.H));
-    float v = Elem<T>::ld(static_cast<const T*>(p.x) + e);
-    for (int j = 0; j < p.n_same; ++j) v += Elem<T>::ld(static_cast<const T*>(p.same[j]) + e);
+  const int hc = p.C / 2;
+  const int total = p.B * p.H * p.W * hc;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int t = e / hc, c = (e - t * hc) * 2;
+    const int w = t % p.W, hb = t / p.W, h = hb % p.H, b = hb / p.H;
+    const size_t off = (size_t)t * p.C + c;
+    float2 v = Pair<T>::ld(static_cast<const T*>(p.x) + off);
+    for (int j = 0; j < p.n_same; ++j) {
+      const float2 a = Pair<T>::ld(static_cast<const T*>(p.same[j]) + off);
+      v.x += a.x; v.y += a.y;
+    }
     for (int j = 0; j < p.n_up; ++j) {
       const int ih = p.up_H[j], iw = p.up_W[j];
       const T* u = static_cast<const T*>(p.up[j]);
@@ -176,25 +218,30 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
       const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
       const float hy = 1.f - ly, hx = 1.f - lx;
       const size_t base = (size_t)b * ih * iw;
-      const float v00 = Elem<T>::ld(u + ((base + (size_t)y0 * iw + x0) * p.C + c));
-      const float v01 = Elem<T>::ld(u + ((base + (size_t)y0 * iw + x1) * p.C + c));
-      const float v10 = Elem<T>::ld(u + ((base + (size_t)y1 * iw + x0) * p.C + c));
-      const float v11 = Elem<T>::ld(u + ((base + (size_t)y1 * iw + x1) * p.C + c));
-      v += hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      const float2 v00 = Pair<T>::ld(u + ((base + (size_t)y0 * iw + x0) * p.C + c));
+      const float2 v01 = Pair<T>::ld(u + ((base + (size_t)y0 * iw + x1) * p.C + c));
+      const float2 v10 = Pair<T>::ld(u + ((base + (size_t)y1 * iw + x0) * p.C + c));
+      const float2 v11 = Pair<T>::ld(u + ((base + (size_t)y1 * iw + x1) * p.C + c));
+      v.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+      v.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     }
-    if (p.relu) v = fmaxf(v, 0.f);
-    Elem<T>::st(static_cast<T*>(p.out) + e, v);
+    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+    Pair<T>::st(static_cast<T*>(p.out) + off, v.x, v.y);
     if (p.out_nchw) {
       // round through the storage type so both copies hold the same values
-      const float vs = Elem<T>::ld(static_cast<const T*>(p.out) + e);
-      p.out_nchw[(((size_t)b * p.C + c) * p.H + h) * p.W + w] = vs;
+      const float2 vs = Pair<T>::ld(static_cast<const T*>(p.out) + off);
+      const size_t o = (((size_t)b * p.C + c) * p.H + h) * p.W + w;
+      p.out_nchw[o] = vs.x;
+      p.out_nchw[o + (size_t)p.H * p.W] = vs.y;
     }
   }
 }
 
 template <typename T>
 static int launch_fuse(const FuseParams& p, cudaStream_t stream) {
-  const size_t total = (size_t)p.B * p.H * p.W * p.C;
+  const size_t total = (size_t)p.B * p.H * p.W * (p.C / 2);
+  HRF_REQUIRE(p.C % 2 == 0 && total * 2 < ((size_t)1 << 31), HRF_EUNSUPPORTED,
+              "fuse_sum: C=%d must be even and the tensor below 2^31 elements", p.C);
   const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   fuse_sum_kernel<T><<<grid, 256, 0, stream>>>(p);
   count_launch();

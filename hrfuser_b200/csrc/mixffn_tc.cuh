@@ -34,13 +34,17 @@ struct FfnTc {
   static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
   static constexpr int TH = 8, TW = 16, HH = TH + 2, HW = TW + 2, NHALO = HH * HW;   // 180
   static constexpr int XT = 128 * KC * 2;            // one XN operand tile
-  static constexpr int H1R = 184;                    // rows per 8-channel chunk of H1 (>= 180)
+  static constexpr int H1R = 184;                    // rows per 16-byte column group of H1 (>= 180)
+  // H1 (GELU(fc1) on the halo) is kept in fp32 where two CTAs per SM still fit
+  // (no bf16 unpacking in the depthwise loop, no extra rounding); bf16 otherwise
+  static constexpr bool H1F32 = (C == 18) || (CPG < NCH);
+  static constexpr int H1_B = (H1F32 ? 18 : 9) * H1R * 16;
   // shared-memory map (bytes)
   static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
   static constexpr int o_w2 = o_w1 + CPG * N1 * KC * 2;        // CPG tiles [NOUT x 80]
   static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;      // 2 tiles
-  static constexpr int o_h1 = o_xn + 2 * XT;                   // 9 x H1R x 16
-  static constexpr int o_h2 = o_h1 + 9 * H1R * 16;             // 10 x 128 x 16
+  static constexpr int o_h1 = o_xn + 2 * XT;                   // (9 | 18) x H1R x 16
+  static constexpr int o_h2 = o_h1 + H1_B;                     // 10 x 128 x 16
   static constexpr int o_f32 = o_h2 + 10 * 128 * 16;           // per chunk 880 floats, then b2[NOUT]
   static constexpr int o_ln = o_f32 + (CPG * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
   static constexpr int C4 = (C + 3) / 4 * 4;
@@ -52,19 +56,18 @@ struct FfnTc {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-// erf-form GELU from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the
-// hardware reciprocal / ex2; the negative branch avoids the 1 - (1 - tiny) cancellation.
+// GELU for the bf16 mode: x * sigmoid(x (a + b x^2 + c x^4)), coefficients fitted to the
+// exact erf form (max abs error 2.6e-5 over all x, two orders below bf16 resolution;
+// tools/fit_gelu.py), evaluated as x / (1 + 2^w) on the hardware ex2 / rcp units:
+// 9 instructions instead of ~17 for an erf evaluation.  x^2 is clamped at 64, beyond
+// which the result has saturated to x or 0 and the quartic would change sign.
 __device__ __forceinline__ float gelu_as(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float pe = poly * fast_exp2(-1.4426950408889634f * z * z);   // 1 - erf(|z|)
-  return 0.5f * x * (x >= 0.f ? 2.0f - pe : pe);
+  const float x2 = fminf(x * x, 64.0f);
+  float w = fmaf(x2, 0.0010142630198970437f, -0.10677572339773178f);
+  w = fmaf(w, x2, -2.301121234893799f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(w * x)));
+  return x * r;
 }
 
 constexpr int kFfnTcThreads = 512;
@@ -194,7 +197,13 @@ mixffn_tc_kernel(FfnParams p) {
           const bool in = sIn[t] != 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + fb[ch * 8 + j]) : 0.f;
-          st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
+          if constexpr (K::H1F32) {
+            float4* h1 = reinterpret_cast<float4*>(sm + K::o_h1);
+            h1[(2 * ch) * K::H1R + t] = make_float4(v[0], v[1], v[2], v[3]);
+            h1[(2 * ch + 1) * K::H1R + t] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
+          }
         }
       }
       tc_fence_before();
@@ -215,14 +224,26 @@ mixffn_tc_kernel(FfnParams p) {
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
               const int tt = (oy + dy) * K::HW + ox + dx;
-              const uint4 u = *reinterpret_cast<const uint4*>(sm + K::o_h1 + (size_t)ch * (K::H1R * 16) + tt * 16);
               const float* wt = wd + (dy * 3 + dx) * 80 + ch * 8;
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+              const float4 wa = *reinterpret_cast<const float4*>(wt);
+              const float4 wb = *reinterpret_cast<const float4*>(wt + 4);
+              if constexpr (K::H1F32) {
+                const float4* h1 = reinterpret_cast<const float4*>(sm + K::o_h1);
+                const float4 fa = h1[(2 * ch) * K::H1R + tt], fb4 = h1[(2 * ch + 1) * K::H1R + tt];
+                acc[0] = fmaf(fa.x, wa.x, acc[0]); acc[1] = fmaf(fa.y, wa.y, acc[1]);
+                acc[2] = fmaf(fa.z, wa.z, acc[2]); acc[3] = fmaf(fa.w, wa.w, acc[3]);
+                acc[4] = fmaf(fb4.x, wb.x, acc[4]); acc[5] = fmaf(fb4.y, wb.y, acc[5]);
+                acc[6] = fmaf(fb4.z, wb.z, acc[6]); acc[7] = fmaf(fb4.w, wb.w, acc[7]);
+              } else {
+                const uint4 u = *reinterpret_cast<const uint4*>(sm + K::o_h1 + (size_t)ch * (K::H1R * 16) + tt * 16);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
-                acc[2 * j] = fmaf(f.x, wt[2 * j], acc[2 * j]);
-                acc[2 * j + 1] = fmaf(f.y, wt[2 * j + 1], acc[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+                  acc[2 * j] = fmaf(f.x, wv[2 * j], acc[2 * j]);
+                  acc[2 * j + 1] = fmaf(f.y, wv[2 * j + 1], acc[2 * j + 1]);
+                }
               }
             }
 #pragma unroll

@@ -409,7 +409,6 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
 #pragma unroll
       for (int j = S; j < 56; ++j) sc[j] = 0.f;
       inv_sum[h] = 1.0f / sum;
-#pragma unroll
       unsigned char* sP = sm + K::o_qk + h * 2 * K::HT;     // Q_h | K_h are dead: S is complete
 #pragma unroll
       for (int ch = 0; ch < 7; ++ch) st_chunk(sP, tid, ch, 128, sc + 8 * ch);
