@@ -38,6 +38,11 @@ class DwPwDesc(PwDesc):
     pass
 
 
+class StemDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('Cin', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('Cout', C.c_int32), ('relu', C.c_int32)]
+
+
 class FuseDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
                 ('dtype', C.c_int32), ('n_up', C.c_int32),
@@ -75,6 +80,10 @@ SIGNATURES = {
                                C.c_void_p]),
     'hrf_fuse_sum_fwd': (C.c_int, [C.POINTER(FuseDesc), C.c_void_p, _VPP, _VPP, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'hrf_stem_blob_floats': (C.c_size_t, [C.POINTER(StemDesc)]),
+    'hrf_stem_pack': (C.c_int, [C.POINTER(StemDesc), _F, _FP4, C.c_float, _F]),
+    'hrf_stem_conv_fwd': (C.c_int, [C.POINTER(StemDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     'hrf_bias_act_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

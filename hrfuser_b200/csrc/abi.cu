@@ -15,6 +15,7 @@
 #include "umma_selftest.cuh"
 #include "window_attn_tc.cuh"
 #include "mixffn_tc.cuh"
+#include "stem_conv_tc.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -394,6 +395,38 @@ int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
   if (d->dtype == HRF_F32) return launch_fuse<float>(p, (cudaStream_t)stream);
   if (d->dtype == HRF_BF16) return launch_fuse<__nv_bfloat16>(p, (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "fuse_fwd: dtype");
+}
+
+size_t hrf_stem_blob_floats(const HrfStemDesc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
+  return (size_t)StemLayout(d->Cin, d->Cout).total;
+}
+
+int hrf_stem_pack(const HrfStemDesc* d, const float* w, const float* const bn[4], float bn_eps,
+                  float* blob) {
+  HRF_REQUIRE(d && w && blob, HRF_EINVAL, "stem_pack: null pointer");
+  HRF_REQUIRE(d->Cin >= 1 && d->Cin <= 3 && d->Cout % 16 == 0, HRF_EUNSUPPORTED,
+              "stem_pack: Cin=%d Cout=%d", d->Cin, d->Cout);
+  const StemLayout L(d->Cin, d->Cout);
+  std::memset(blob, 0, sizeof(float) * L.total);
+  std::vector<float> sc, sh;
+  bn_affine(bn, d->Cout, bn_eps, sc, sh);
+  uint16_t* wt = reinterpret_cast<uint16_t*>(blob + L.o_w);
+  for (int n = 0; n < d->Cout; ++n) {
+    blob[L.o_bias + n] = sh[n];
+    for (int k = 0; k < d->Cin * 9; ++k)       // (Cout, Cin, 3, 3) row-major: k = (ci*3+ky)*3+kx
+      wt[umma::tile_off(n, k, d->Cout) / 2] = f32_to_bf16(w[(size_t)n * d->Cin * 9 + k] * sc[n]);
+  }
+  return HRF_OK;
+}
+
+int hrf_stem_conv_fwd(const HrfStemDesc* d, const float* x_nchw, const float* blob,
+                      void* out_nhwc_bf16, void* stream) {
+  HRF_REQUIRE(d && x_nchw && blob && out_nhwc_bf16, HRF_EINVAL, "stem_conv: null pointer");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, HRF_EINVAL, "stem_conv: dims");
+  StemParams p{x_nchw, blob, static_cast<__nv_bfloat16*>(out_nhwc_bf16), d->B, d->Cin, d->H, d->W,
+               (d->H + 1) / 2, (d->W + 1) / 2, d->Cout, d->relu};
+  return launch_stem_conv(p, (cudaStream_t)stream);
 }
 
 int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, void* y,

@@ -124,9 +124,9 @@ class BackboneEngine:
         self._host_blobs, self._blob_slots = [], []
         m, dt = module, self.dtype
 
-        self.stem = [_Conv(m.conv1, m.bn1, True, dt), _Conv(m.conv2, m.bn2, True, dt)] + \
+        self.stem = [self._stem_conv(m.conv1, m.bn1), _Conv(m.conv2, m.bn2, True, dt)] + \
                     [_Bottleneck(b, dt) for b in m.layer1]
-        self.stem_mod = [[_Conv(m.conv_a[k], m.norm_a[k], True, dt),
+        self.stem_mod = [[self._stem_conv(m.conv_a[k], m.norm_a[k]),
                           _Conv(m.conv_b[k], m.norm_b[k], True, dt)] +
                          [_Bottleneck(b, dt) for b in m.layer_a[k]] for k in range(self.M)]
         # transition1[i][0]: bare conv on branch 0, full conv-bn-relu on branch 1
@@ -148,6 +148,19 @@ class BackboneEngine:
         self._upload()
 
     # ---------------------------------------------------------------- packing
+    def _stem_conv(self, conv, bn):
+        """First conv of a stream.  bf16 mode: the tcgen05 stem kernel, fed with the
+        caller's fp32 NCHW image (no cast / layout passes); otherwise cuDNN."""
+        tc = (self.ops is ops and self.precision == 'bf16' and conv.in_channels <= 3 and
+              conv.out_channels == 64 and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and
+              conv.padding == (1, 1) and conv.bias is None and conv.groups == 1)
+        if not tc:
+            cv = _Conv(conv, bn, True, self.dtype)
+            return lambda x: cv(self._prep(x))
+        blob = self._blob(ops.pack_stem(conv, bn, bn.eps))
+        return lambda x: self._image(ops.stem_conv(
+            x.to(device=self.device, dtype=torch.float32).contiguous(), blob.t, 64, relu=True))
+
     def _blob(self, host_blob):
         """register a host blob; returns a slot whose .t is the device view after upload"""
         slot = type('Blob', (), {})()
@@ -343,8 +356,8 @@ class BackboneEngine:
         M = self.M
         with ctx, dctx:
             stems = self._par(
-                [lambda: self._apply_chain(self.stem, self._prep(x))] +
-                [lambda k=k: self._tokens(self._apply_chain(self.stem_mod[k], self._prep(mods[k])))
+                [lambda: self._apply_chain(self.stem, x)] +
+                [lambda k=k: self._tokens(self._apply_chain(self.stem_mod[k], mods[k]))
                  for k in range(M)])
             x, stream = stems[0], stems[1:]
             xs, firsts = self._fuse('a', [lambda t=t: self._tokens(t(x)) for t in self.trans1], stream)

@@ -10,7 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, check)
+from ._lib import (AttnDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, StemDesc,
+                   check)
 
 _DT = {torch.float32: HRF_F32, torch.bfloat16: HRF_BF16}
 _F = C.POINTER(C.c_float)
@@ -158,9 +159,36 @@ def pack_dwpw(conv_dw, bn_dw, conv_pw, bn_pw, bn_eps=1e-5):
     return blob
 
 
+def pack_stem(conv, bn, bn_eps=1e-5):
+    lib = _lib.load()
+    cout, cin = conv.weight.shape[:2]
+    d = StemDesc(1, cin, 2, 2, cout, 1)
+    blob = torch.empty(lib.hrf_stem_blob_floats(C.byref(d)), dtype=torch.float32)
+    keep = []
+    w = _host(conv.weight)
+    check(lib.hrf_stem_pack(C.byref(d), _fp(w), _bn4(bn, keep), C.c_float(bn_eps), _fp(blob)))
+    return blob
+
+
 # ----------------------------------------------------------------------------
 # forward ops (device)
 # ----------------------------------------------------------------------------
+def stem_conv(x_nchw, blob, cout, relu=True):
+    """fp32 NCHW image -> bf16 channels-last (B, H/2, W/2, cout): conv3x3 s2 + BN + ReLU"""
+    lib = _lib.load()
+    assert x_nchw.is_cuda and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    B, cin, H, W = x_nchw.shape
+    out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, cout, dtype=torch.bfloat16, device=x_nchw.device)
+    d = StemDesc(B, cin, H, W, cout, int(relu))
+    with _timed('stem_conv', C=cin, launches=1,
+                bytes=float(x_nchw.numel() * 4 + out.numel() * 2),
+                flops=float(out.numel() * 2 * 9 * cin)):
+        check(lib.hrf_stem_conv_fwd(C.byref(d), x_nchw.data_ptr(), blob.data_ptr(), out.data_ptr(),
+                                    _stream()))
+    return out
+
+
+
 def window_attention(x, kv, blobs, heads, win=7, with_pad_mask=False, eps=1e-6, out=None):
     """LSA when `kv` is empty/None (out = x + Attn(LN x)), else MWCA over the
     modalities in `kv` (out = x + sum_k[kv_k + Attn_k(LN1_k x, LN2_k kv_k)])."""

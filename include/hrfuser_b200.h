@@ -164,6 +164,20 @@ typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_
 int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
                      const void* const* same, void* out, float* out_nchw_f32, void* stream);
 
+/* Stem convolution (bf16 mode): conv 3x3 stride 2 pad 1 with Cin <= 3 + folded BN + ReLU
+ * (hrnet.py:341-348 conv1/bn1, hrfuser_hrformer_based.py:380-388 conv_a/norm_a), reading
+ * the caller's fp32 NCHW image and writing bf16 channels-last (B, ceil(H/2), ceil(W/2), Cout).
+ * Implicit GEMM on the tensor cores (K = 9*Cin padded to 32).  Cout = 64. */
+typedef struct HrfStemDesc {
+  int32_t B, Cin, H, W, Cout;
+  int32_t relu;
+} HrfStemDesc;
+size_t hrf_stem_blob_floats(const HrfStemDesc* d);
+int hrf_stem_pack(const HrfStemDesc* d, const float* w /*(Cout,Cin,3,3)*/, const float* const bn[4],
+                  float bn_eps, float* blob_out);
+int hrf_stem_conv_fwd(const HrfStemDesc* d, const float* x_nchw, const float* blob,
+                      void* out_nhwc_bf16, void* stream);
+
 /* Epilogue of the cuDNN-side convolutions (stems, Bottlenecks, transitions:
  * hrnet.py:341-371,419-463, resnet.py:263-302 with the BatchNorm folded into the
  * conv): y = act(y + bias[c] (+ residual)) in place, one pass, channels-last.

@@ -193,3 +193,23 @@ def test_bias_act(built_lib, C, with_res, relu, dt):
     ops.bias_act_(y, b, r, relu)
     torch.cuda.synchronize()
     assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize('cin,H,W', [(3, 64, 96), (2, 34, 50), (1, 33, 47), (3, 384, 640)])
+def test_stem_conv_tc(built_lib, cin, H, W):
+    """tcgen05 stem conv (fp32 NCHW in, bf16 NHWC out) vs conv2d + eval BN + ReLU"""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from hrfuser_b200 import ops
+    from hrfuser_b200.utils import randomize_parameters
+    conv, bn = nn.Conv2d(cin, 64, 3, 2, 1, bias=False), nn.BatchNorm2d(64)
+    randomize_parameters(nn.Sequential(conv, bn), cin)
+    bn.eval()
+    x = torch.randn(2, cin, H, W, generator=torch.Generator().manual_seed(H))
+    with torch.no_grad():
+        ref = F.relu(bn(conv(x))).permute(0, 2, 3, 1)
+    blob = ops.pack_stem(conv, bn, bn.eps).cuda()
+    got = ops.stem_conv(x.cuda(), blob, 64)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == tuple(ref.shape)
+    assert_parity(got, ref, 'bf16', f'stem conv cin={cin}')
