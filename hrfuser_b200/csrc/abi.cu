@@ -340,7 +340,7 @@ int hrf_pw_pack(const HrfPwDesc* d, const float* w, const float* bias, const flo
 int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, void* stream) {
   HRF_REQUIRE(d && x && blob && out, HRF_EINVAL, "pw_fwd: null pointer");
   HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, HRF_EINVAL, "pw_fwd: dims");
-  PwParams p{x, blob, out, d->B * d->H * d->W, d->Cin, d->Cout, d->relu};
+  PwParams p{x, blob, out, d->B * d->H * d->W, d->Cin, d->Cout, d->relu, 0};
   if (d->dtype == HRF_F32) return launch_pw<float>(p, (cudaStream_t)stream);
   if (d->dtype == HRF_BF16) return launch_pw<__nv_bfloat16>(p, (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "pw_fwd: dtype");
@@ -367,7 +367,7 @@ int hrf_dwpw_pack(const HrfDwPwDesc* d, const float* wdw, const float* const bn_
 int hrf_dwpw_fwd(const HrfDwPwDesc* d, const void* x, const float* blob, void* out, void* stream) {
   HRF_REQUIRE(d && x && blob && out, HRF_EINVAL, "dwpw_fwd: null pointer");
   HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, HRF_EINVAL, "dwpw_fwd: dims");
-  DwPwParams p{x, blob, out, d->B, d->H, d->W, (d->H + 1) / 2, (d->W + 1) / 2, d->Cin, d->Cout, d->relu};
+  DwPwParams p{x, blob, out, d->B, d->H, d->W, (d->H + 1) / 2, (d->W + 1) / 2, d->Cin, d->Cout, d->relu, 0};
   if (d->dtype == HRF_F32) return launch_dwpw<float>(p, (cudaStream_t)stream);
   if (d->dtype == HRF_BF16) return launch_dwpw<__nv_bfloat16>(p, (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "dwpw_fwd: dtype");

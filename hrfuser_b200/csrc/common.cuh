@@ -111,12 +111,12 @@ __device__ inline void warp_layernorm(LoadFn ld, int C, int Cpad, const float* _
 // ---- block-level register-tiled GEMM on a shared-memory A operand -------------
 // out(r, n) = sum_{k<K} A[r*lda + k] * Wt[k*N + n],  r < M, n < N.
 // A: fp32 in shared memory, K a multiple of 4 (caller zero-pads), rows 16-byte
-// aligned.  Wt: fp32 in global memory, k-major (read through L1/L2; every CTA
-// reads the same few KB).  Each thread owns RT x CT output tiles; consecutive
+// aligned.  Wt: fp32, k-major, in shared memory (staged by the caller: one coalesced
+// copy instead of K/4 serialised L2 round trips) or in global memory (read through L1).  Each thread owns RT x CT output tiles; consecutive
 // threads take consecutive column tiles so Wt loads coalesce and A loads
 // broadcast.  epi(r, n, value) is called for every valid output element.
 template <int RT, int CT, typename Epi>
-__device__ inline void block_gemm(const float* A, int lda, int M, const float* __restrict__ Wt,
+__device__ inline void block_gemm(const float* A, int lda, int M, const float* Wt,
                                   int K, int N, Epi epi) {
   static_assert(CT == 2 || CT == 4, "CT");
   const int ntc = N / CT;
@@ -141,10 +141,10 @@ __device__ inline void block_gemm(const float* A, int lda, int M, const float* _
         float w[CT];
         const float* wp = Wt + (size_t)(k + kk) * N + n0;
         if constexpr (CT == 4) {
-          float4 w4 = __ldg(reinterpret_cast<const float4*>(wp));
+          float4 w4 = *reinterpret_cast<const float4*>(wp);     // generic: global or shared
           w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
         } else {
-          float2 w2 = __ldg(reinterpret_cast<const float2*>(wp));
+          float2 w2 = *reinterpret_cast<const float2*>(wp);
           w[0] = w2.x; w[1] = w2.y;
         }
 #pragma unroll

@@ -41,7 +41,16 @@ template <> struct Pair<__nv_bfloat16> {
 struct PwParams {
   const void* x; const float* blob; void* out;
   int ntok, Cin, Cout, relu;
+  int w_smem;     // stage the k-major weight matrix in shared memory first
 };
+
+// one coalesced copy of the weight matrix into shared memory (or pass-through)
+__device__ inline const float* stage_weights(const float* gw, float* sw, int n, int enable) {
+  if (!enable) return gw;
+  for (int e = threadIdx.x * 4; e < n; e += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sw + e) = __ldg(reinterpret_cast<const float4*>(gw + e));
+  return sw;
+}
 
 // TOK tokens per CTA: 64 for full-resolution maps, 16 for the low-resolution branches
 // (1 920 tokens at C=144) so that the grid still covers the 148 SMs
@@ -61,10 +70,11 @@ __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
     if (r < m && c < p.Cin) v = Pair<T>::ld(x + (size_t)(t0 + r) * p.Cin + c);
     *reinterpret_cast<float2*>(smem + r * L.lda + c) = v;
   }
+  const float* Wt = stage_weights(p.blob + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
   __syncthreads();
   const float* bias = p.blob + L.o_b;
   const int relu = p.relu, Cout = p.Cout;
-  block_gemm<4, CT>(smem, L.lda, m, p.blob + L.o_w, L.Kp, Cout, [&](int r, int n, float v) {
+  block_gemm<4, CT>(smem, L.lda, m, Wt, L.Kp, Cout, [&](int r, int n, float v) {
     v += __ldg(bias + n);
     if (relu) v = fmaxf(v, 0.f);
     Elem<T>::st(out + (size_t)(t0 + r) * Cout + n, v);
@@ -72,9 +82,11 @@ __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
 }
 
 template <typename T, int TOK>
-static int launch_pw_tok(const PwParams& p, cudaStream_t stream) {
+static int launch_pw_tok(PwParams p, cudaStream_t stream) {
   const PwLayout L(p.Cin, p.Cout);
-  const size_t smem = (size_t)TOK * L.lda * sizeof(float);
+  size_t smem = (size_t)TOK * L.lda * sizeof(float);
+  p.w_smem = smem + (size_t)L.Kp * p.Cout * sizeof(float) <= 160 * 1024;
+  if (p.w_smem) smem += (size_t)L.Kp * p.Cout * sizeof(float);
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "pw: Cin=%d too wide", p.Cin);
   auto kern = (p.Cout % 4 == 0) ? pw_kernel<T, 4, TOK> : pw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
@@ -106,6 +118,7 @@ struct DwPwLayout {
 struct DwPwParams {
   const void* x; const float* blob; void* out;
   int B, H, W, Ho, Wo, Cin, Cout, relu;
+  int w_smem;
 };
 
 template <typename T, int CT, int TOK>
@@ -128,28 +141,31 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
       const int t = t0 + r;
       const int b = t / (p.Ho * p.Wo), oy = (t / p.Wo) % p.Ho, ox = t % p.Wo;
       s = __ldg(reinterpret_cast<const float2*>(bd + c));
+      // all nine taps are loaded before the first FMA (clamped address, zero weight
+      // outside the image) so the loads overlap instead of serialising on L2 latency
+      float2 v[9], w[9];
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int iy = oy * 2 - 1 + dy;
-        if (iy < 0 || iy >= p.H) continue;
+      for (int k = 0; k < 9; ++k) {
+        const int iy = oy * 2 - 1 + k / 3, ix = ox * 2 - 1 + k % 3;
+        const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const int cy = min(max(iy, 0), p.H - 1), cx = min(max(ix, 0), p.W - 1);
+        v[k] = Pair<T>::ld(x + ((size_t)(b * p.H + cy) * p.W + cx) * p.Cin + c);
+        w[k] = in ? __ldg(reinterpret_cast<const float2*>(wd + k * p.Cin + c)) : make_float2(0.f, 0.f);
+      }
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int ix = ox * 2 - 1 + dx;
-          if (ix < 0 || ix >= p.W) continue;
-          const float2 v = Pair<T>::ld(x + ((size_t)(b * p.H + iy) * p.W + ix) * p.Cin + c);
-          const float2 w = __ldg(reinterpret_cast<const float2*>(wd + (dy * 3 + dx) * p.Cin + c));
-          s.x = fmaf(v.x, w.x, s.x);
-          s.y = fmaf(v.y, w.y, s.y);
-        }
+      for (int k = 0; k < 9; ++k) {
+        s.x = fmaf(v[k].x, w[k].x, s.x);
+        s.y = fmaf(v[k].y, w[k].y, s.y);
       }
     }
     *reinterpret_cast<float2*>(smem + r * L.lda + c) = s;
   }
-  __syncthreads();
   const float* pw = p.blob + D.o_pw;
+  const float* Wt = stage_weights(pw + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
+  __syncthreads();
   const float* bias = pw + L.o_b;
   const int relu = p.relu, Cout = p.Cout;
-  block_gemm<4, CT>(smem, L.lda, m, pw + L.o_w, L.Kp, Cout, [&](int r, int n, float v) {
+  block_gemm<4, CT>(smem, L.lda, m, Wt, L.Kp, Cout, [&](int r, int n, float v) {
     v += __ldg(bias + n);
     if (relu) v = fmaxf(v, 0.f);
     Elem<T>::st(out + (size_t)(t0 + r) * Cout + n, v);
@@ -157,9 +173,11 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
 }
 
 template <typename T, int TOK>
-static int launch_dwpw_tok(const DwPwParams& p, cudaStream_t stream) {
+static int launch_dwpw_tok(DwPwParams p, cudaStream_t stream) {
   const PwLayout L(p.Cin, p.Cout);
-  const size_t smem = (size_t)TOK * L.lda * sizeof(float);
+  size_t smem = (size_t)TOK * L.lda * sizeof(float);
+  p.w_smem = smem + (size_t)L.Kp * p.Cout * sizeof(float) <= 160 * 1024;
+  if (p.w_smem) smem += (size_t)L.Kp * p.Cout * sizeof(float);
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "dwpw: Cin=%d too wide", p.Cin);
   auto kern = (p.Cout % 4 == 0) ? dwpw_kernel<T, 4, TOK> : dwpw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
