@@ -142,24 +142,59 @@ mixffn_tc_kernel(FfnParams p) {
   // live rows in this quadrant (halo tokens 128..179), (M tile 1, chunk 0..8)
   const int n_units = (128 + q * 32 < K::NHALO) ? 18 : 9;
 
-  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += gridDim.x / NG) {
+  // Software pipeline (C <= 40): halo token `tid` of the NEXT tile is requested while the
+  // current tile computes; the residual slice of the first epilogue-2 unit is requested
+  // at the top of the tile.  No thread waits on global memory with the CTA behind it.
+  constexpr bool PIPE = !K::BIGC;
+  constexpr int NW = PIPE ? C / 2 : 1;
+  const int tile_step = gridDim.x / NG;
+  // halo token of this thread in a given tile: global token index or -1 (outside / none)
+  auto halo_token = [&](int tile) -> int {
+    if (tile >= n_tiles || tid >= K::NHALO) return -1;
+    const int b = tile / (tiles_x * tiles_y);
+    const int h = ((tile / tiles_x) % tiles_y) * K::TH - 1 + tid / K::HW;
+    const int w = (tile % tiles_x) * K::TW - 1 + tid % K::HW;
+    return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
+  };
+  uint32_t xr[NW];
+  int htok = halo_token(blockIdx.x / NG);
+  if (PIPE && htok >= 0) load_row_raw<C>(x + (size_t)htok * C, xr);
+
+  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
     const int b = tile / (tiles_x * tiles_y);
     const int ty0 = ((tile / tiles_x) % tiles_y) * K::TH, tx0 = (tile % tiles_x) * K::TW;
 
     // ---- LN prologue: halo token `tid` ---------------------------------------------
     if (tid < K::NHALO) {
-      const int h = ty0 - 1 + tid / K::HW, w = tx0 - 1 + tid % K::HW;
-      const bool in = h >= 0 && h < p.H && w >= 0 && w < p.W;
+      const bool in = htok >= 0;
       sIn[tid] = in ? 1 : 0;
       unsigned char* xt = sm + K::o_xn + (tid >> 7) * K::XT;
       if (in) {
-        ln_token<C, KC, K::BIGC>(x + ((size_t)(b * p.H + h) * p.W + w) * C, sLn, sLn + K::C4, p.eps,
-                                 xt, tid & 127);
+        if constexpr (PIPE) {
+          float v[C];
+          unpack_row<C>(xr, v);
+          ln_row_to_tile<C, KC>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+        } else {
+          ln_token<C, KC, true>(x + (size_t)htok * C, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+        }
       } else {
         const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ch = 0; ch < KC / 8; ++ch) st_chunk(xt, tid & 127, ch, 128, zero);
       }
+    }
+    // requests that complete behind this tile's work
+    const int htok_next = halo_token(tile + tile_step);
+    uint32_t xnext[NW];
+    if (PIPE && htok_next >= 0) load_row_raw<C>(x + (size_t)htok_next * C, xnext);
+    const int oh = ty0 + (row >> 4), ow = tx0 + (row & 15);
+    const bool o_in = oh < p.H && ow < p.W;
+    const size_t o_tok = o_in ? (size_t)(b * p.H + oh) * p.W + ow : 0;
+    uint32_t rres[4] = {0u, 0u, 0u, 0u};           // residual of epilogue-2 unit cc = gq
+    if (!K::SPLIT && o_in && gq * 8 < C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gq * 8 + 2 * j < C) rres[j] = __ldg(reinterpret_cast<const uint32_t*>(x + o_tok * C + gq * 8) + j);
     }
 
 #pragma unroll 1
@@ -273,9 +308,8 @@ mixffn_tc_kernel(FfnParams p) {
 
     // ---- epilogue 2: unit = (output token, 8-channel chunk of the C outputs) ----------
     {
-      const int h = ty0 + (row >> 4), w = tx0 + (row & 15);
-      const bool in = h < p.H && w < p.W;
-      const size_t tok = in ? (size_t)(b * p.H + h) * p.W + w : 0;
+      const bool in = o_in;
+      const size_t tok = o_tok;
       const float* b2 = sF + CPG * 880;
 #pragma unroll 1
       for (int cc = gq; cc * 8 < C; cc += 4) {        // warp-uniform trip count
@@ -289,12 +323,12 @@ mixffn_tc_kernel(FfnParams p) {
           *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
         } else {                       // + b2, GELU, + residual; rows are only 4-byte aligned
-          const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + tok * C + cc * 8);
+          const uint32_t* xr4 = reinterpret_cast<const uint32_t*>(x + tok * C + cc * 8);
           uint32_t* orow = reinterpret_cast<uint32_t*>(out + tok * C + cc * 8);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (cc * 8 + 2 * j < C) {
-              const uint32_t u = __ldg(xr + j);
+              const uint32_t u = (cc == gq) ? rres[j] : __ldg(xr4 + j);
               const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
               const float a0 = r.x + gelu_as(y[2 * j] + b2[cc * 8 + 2 * j]);
               const float a1 = r.y + gelu_as(y[2 * j + 1] + b2[cc * 8 + 2 * j + 1]);
@@ -304,6 +338,12 @@ mixffn_tc_kernel(FfnParams p) {
           }
         }
       }
+    }
+    // rotate the software pipeline
+    htok = htok_next;
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int j = 0; j < NW; ++j) xr[j] = xnext[j];
     }
     // next iteration: its first barrier (after the LN prologue) orders these TMEM reads
     // before the next fc1 / fc2 MMAs; the XN tiles were released by the fc2 wait above.

@@ -101,6 +101,35 @@ __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, float* x
   }
 }
 
+// raw variant: the row as C/2 packed bf16 pairs (kept in registers across a tile)
+template <int C>
+__device__ __forceinline__ void load_row_raw(const __nv_bfloat16* src, uint32_t* w) {
+  if constexpr ((C * 2) % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+    }
+  } else if constexpr ((C * 2) % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(src) + i);
+      w[2 * i] = u.x; w[2 * i + 1] = u.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+  }
+}
+template <int C>
+__device__ __forceinline__ void unpack_row(const uint32_t* w, float* x) {
+#pragma unroll
+  for (int i = 0; i < C / 2; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    x[2 * i] = f.x; x[2 * i + 1] = f.y;
+  }
+}
+
 template <int C>
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float* x) {
   uint32_t w[C / 2];
@@ -290,31 +319,66 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   const int ic = i < S ? i : S - 1;
   const int rp_base = (ic / WIN + WIN - 1) * (2 * WIN - 1) + (ic % WIN) + WIN - 1;
 
-  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += gridDim.x / NG) {
-    // ---- token of this row ----------------------------------------------------
+  // token held by this row in a given tile (-1: pad slot, dead row, no such window)
+  auto row_token = [&](int tile) -> int {
     const int wdx = tile * 2 + g;
-    int tok = -1;
-    if (wdx < n_windows && i < S) {
-      const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
-      const int h = wy * WIN + i / WIN - pad_t, w = wx * WIN + i % WIN - pad_l;
-      if (h >= 0 && h < p.H && w >= 0 && w < p.W) tok = (b * p.H + h) * p.W + w;
-    }
+    if (tile >= n_tiles || wdx >= n_windows || i >= S) return -1;
+    const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
+    const int h = wy * WIN + i / WIN - pad_t, w = wx * WIN + i % WIN - pad_l;
+    return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
+  };
+  // Software pipeline (C <= 40): the raw bf16 rows of the NEXT tile are requested while
+  // the current tile computes, and the current rows stay in registers for the residual
+  // adds, so no thread ever sits on a global-load latency with the CTA waiting behind it.
+  constexpr bool PIPE = !K::BIGC && !K::SPLIT;
+  constexpr int NW = PIPE ? C / 2 : 1;
+  uint32_t xr[NW], zr[NW];
+  const int tile_step = gridDim.x / NG;
+  int tok = row_token(blockIdx.x / NG);
+  if (PIPE && tok >= 0) {
+    load_row_raw<C>(xq + (size_t)tok * C, xr);
+    if (CROSS) load_row_raw<C>(zz + (size_t)tok * C, zr);
+  }
+
+  for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
+    const int wdx = tile * 2 + g;
     {
       const unsigned bal = __ballot_sync(0xffffffffu, tok >= 0);
       if (lane == 0) valid_bits[warp] = bal;
     }
     // ---- LN prologue -------------------------------------------------------------
     if (tok >= 0) {
-      ln_token<C, KC, K::BIGC>(xq + (size_t)tok * C, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
-      if (CROSS)
-        ln_token<C, KC, K::BIGC>(zz + (size_t)tok * C, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps,
-                                 sm + K::o_zn, tid);
+      if constexpr (PIPE) {
+        float x[C];
+        unpack_row<C>(xr, x);
+        ln_row_to_tile<C, KC>(x, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+        if (CROSS) {
+          unpack_row<C>(zr, x);
+          ln_row_to_tile<C, KC>(x, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps, sm + K::o_zn, tid);
+        }
+      } else {
+        ln_token<C, KC, K::BIGC>(xq + (size_t)tok * C, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+        if (CROSS)
+          ln_token<C, KC, K::BIGC>(zz + (size_t)tok * C, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps,
+                                   sm + K::o_zn, tid);
+      }
     } else {
       const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < KC / 8; ++ch) {
         st_chunk(sm + K::o_xn, tid, ch, 128, zero);
         if (CROSS) st_chunk(sm + K::o_zn, tid, ch, 128, zero);
+      }
+    }
+    // requests that complete behind the tile's MMAs / softmax: this tile's residual row
+    // when it is not the query tensor (MWCA accumulation passes), the next tile's rows
+    uint32_t rr[NW], xnext[NW], znext[NW];
+    const int tok_next = row_token(tile + tile_step);
+    if constexpr (PIPE) {
+      if (tok >= 0 && rs != xq) load_row_raw<C>(rs + (size_t)tok * C, rr);
+      if (tok_next >= 0) {
+        load_row_raw<C>(xq + (size_t)tok_next * C, xnext);
+        if (CROSS) load_row_raw<C>(zz + (size_t)tok_next * C, znext);
       }
     }
     fence_proxy_async();
@@ -470,12 +534,14 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       tmem_ld_wait();
       if (tok >= 0) {
         float r[C];
-        load_row_bf16<C>(rs + (size_t)tok * C, r);
+        if constexpr (PIPE) unpack_row<C>(rs != xq ? rr : xr, r);
+        else load_row_bf16<C>(rs + (size_t)tok * C, r);
         const float* bo = sBias + 3 * NQG;
 #pragma unroll
         for (int c = 0; c < C; ++c) y[c] += bo[c] + r[c];
         if (CROSS) {
-          load_row_bf16<C>(zz + (size_t)tok * C, r);
+          if constexpr (PIPE) unpack_row<C>(zr, r);
+          else load_row_bf16<C>(zz + (size_t)tok * C, r);
 #pragma unroll
           for (int c = 0; c < C; ++c) y[c] += r[c];
         }
@@ -495,6 +561,12 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
           *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
         }
       }
+    }
+    // rotate the software pipeline
+    tok = tok_next;
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int j = 0; j < NW; ++j) { xr[j] = xnext[j]; zr[j] = znext[j]; }
     }
     // the next iteration's first barrier orders these TMEM reads before its MMAs
   }
