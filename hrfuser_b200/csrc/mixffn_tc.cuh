@@ -215,7 +215,7 @@ mixffn_tc_kernel(FfnParams p) {
                      id1, s > 0);
         mma_commit(&bar);
       }
-      mbar_wait(&bar, phase);
+      cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
 
@@ -301,7 +301,7 @@ mixffn_tc_kernel(FfnParams p) {
                    (c > 0) || (s > 0));
         mma_commit(&bar);
       }
-      mbar_wait(&bar, phase);       // H2 / XN free again, Y complete after the last chunk
+      cta_wait(&bar, phase);       // H2 / XN free again, Y complete after the last chunk
       phase ^= 1;
       tc_fence_after();
     }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
       mma_bf16(tmem, desc_kmajor(a_a, 128, 1), desc_kmajor(a_w, COUT, 1), id, true);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue: + bias, ReLU, bf16, 16-byte stores (one 2*COUT-byte row per thread) --

@@ -43,13 +43,33 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// blocking probe: the hardware suspends the thread until the phase completes or an
+// implementation-defined time limit expires (returns false on the limit)
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a lost commit must become an error (trap), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_test(bar, parity)) return;
+  if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_test(bar, parity)) {
+  while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+// Whole-CTA wait for an MMA commit: only warp 0 watches the mbarrier (suspended in
+// try_wait); every other warp sleeps in the hardware barrier instead of spinning on
+// test_wait and stealing issue slots from the co-resident CTAs.
+__device__ __forceinline__ void cta_wait(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x >> 5) == 0) mbar_wait(bar, parity);
+  __syncthreads();
 }
 
 // ---- fences --------------------------------------------------------------------

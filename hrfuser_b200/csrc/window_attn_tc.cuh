@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         mma_bf16(tmem + 2 * NQG, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wv, NQG, s), idq, s > 0);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
 #pragma unroll
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
                    desc_kmajor(a_qk + h * 2 * K::HT + K::HT, 128, s), ids, s > 0);
         mma_commit(&bar);
       }
-      mbar_wait(&bar, phase);
+      cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
 
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
                      desc_mnmajor(a_v + h * K::HT + g2 * 64 * 16, 128, s), ido, s > 0);
         mma_commit(&bar);
       }
-      mbar_wait(&bar, phase);
+      cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
       {
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wo, NOUT, s), idy, s > 0);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
     if constexpr (!K::SPLIT) {
