@@ -319,7 +319,7 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
                   (workspace != nullptr || hrf_ffn_workspace_bytes(d) == 0),
               HRF_EINVAL, "ffn_fwd: workspace of %zu bytes required, %zu given",
               hrf_ffn_workspace_bytes(d), workspace_bytes);
-  FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps};
+  FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
   if (d->dtype == HRF_BF16 && ffn_tc_supported(p) && !tc_disabled())
     return launch_mixffn_tc(p, (cudaStream_t)stream);
   return d->dtype == HRF_F32 ? launch_mixffn<float>(p, (cudaStream_t)stream)

@@ -44,6 +44,28 @@ __host__ __device__ inline int stride4odd(int n) {
   return q * 4;
 }
 
+// Division of a non-negative int (< 2^31) by a launch-constant divisor without the
+// ~30-instruction integer-division sequence: q = umulhi(n, m) >> s (round-up method).
+struct FastDiv {
+  unsigned m, s, d;
+  FastDiv() : m(0), s(0), d(1) {}
+  explicit FastDiv(int div) : d((unsigned)div) {
+    s = 0;
+    while ((1u << s) < d) ++s;
+    // m = ceil(2^(32+s) / d) - 2^32  (33-bit magic, "add" form)
+    const unsigned long long t = (((1ull << s) - d) << 32) / d + 1;
+    m = (unsigned)t;
+  }
+  __device__ __forceinline__ int div(int n) const {
+    const unsigned q = __umulhi((unsigned)n, m);
+    return (int)((q + (unsigned)n) >> s);      // n < 2^31: q + n cannot overflow
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = div(n);
+    r = n - q * (int)d;
+  }
+};
+
 // ---- activation element access (storage type T, math in fp32) -----------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {

@@ -65,6 +65,7 @@ struct FfnParams {
   void* ws;           // fp32 workspace (split tensor-core variant) or nullptr
   int B, H, W, C, hidden;
   float eps;
+  FastDiv d_tiles_xy, d_tiles_x;   // tensor-core kernel: tile index -> (image, tile row, tile col)
 };
 
 // MAXT: fc2 output tiles (4 rows x CT cols) per thread = ceil(16 * C/CT / 256)

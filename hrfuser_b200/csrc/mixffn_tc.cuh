@@ -37,7 +37,7 @@ struct FfnTc {
   static constexpr int H1R = 184;                    // rows per 16-byte column group of H1 (>= 180)
   // H1 (GELU(fc1) on the halo) is kept in fp32 where two CTAs per SM still fit
   // (no bf16 unpacking in the depthwise loop, no extra rounding); bf16 otherwise
-  static constexpr bool H1F32 = (C == 18) || (CPG < NCH);
+  static constexpr bool H1F32 = (C == 18) || (C == 144);
   static constexpr int H1_B = (H1F32 ? 18 : 9) * H1R * 16;
   // shared-memory map (bytes)
   static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
@@ -151,9 +151,11 @@ mixffn_tc_kernel(FfnParams p) {
   // halo token of this thread in a given tile: global token index or -1 (outside / none)
   auto halo_token = [&](int tile) -> int {
     if (tile >= n_tiles || tid >= K::NHALO) return -1;
-    const int b = tile / (tiles_x * tiles_y);
-    const int h = ((tile / tiles_x) % tiles_y) * K::TH - 1 + tid / K::HW;
-    const int w = (tile % tiles_x) * K::TW - 1 + tid % K::HW;
+    int b, rem, ty, tx;
+    p.d_tiles_xy.divmod(tile, b, rem);
+    p.d_tiles_x.divmod(rem, ty, tx);
+    const int h = ty * K::TH - 1 + tid / K::HW;
+    const int w = tx * K::TW - 1 + tid % K::HW;
     return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
   };
   uint32_t xr[NW];
@@ -161,8 +163,11 @@ mixffn_tc_kernel(FfnParams p) {
   if (PIPE && htok >= 0) load_row_raw<C>(x + (size_t)htok * C, xr);
 
   for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
-    const int b = tile / (tiles_x * tiles_y);
-    const int ty0 = ((tile / tiles_x) % tiles_y) * K::TH, tx0 = (tile % tiles_x) * K::TW;
+    int b, rem, ty0, tx0;
+    p.d_tiles_xy.divmod(tile, b, rem);
+    p.d_tiles_x.divmod(rem, ty0, tx0);
+    ty0 *= K::TH;
+    tx0 *= K::TW;
 
     // ---- LN prologue: halo token `tid` ---------------------------------------------
     if (tid < K::NHALO) {
@@ -231,7 +236,11 @@ mixffn_tc_kernel(FfnParams p) {
         if (t < K::NHALO) {
           const bool in = sIn[t] != 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + fb[ch * 8 + j]) : 0.f;
+          const float4 ba = *reinterpret_cast<const float4*>(fb + ch * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(fb + ch * 8 + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + bv[j]) : 0.f;
           if constexpr (K::H1F32) {
             float4* h1 = reinterpret_cast<float4*>(sm + K::o_h1);
             h1[(2 * ch) * K::H1R + t] = make_float4(v[0], v[1], v[2], v[3]);
@@ -251,9 +260,9 @@ mixffn_tc_kernel(FfnParams p) {
         const float* bd = fb + 800;
 #pragma unroll 1
         for (int ch = gq; ch < 9; ch += 4) {
-          float acc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = bd[ch * 8 + j];
+          const float4 da = *reinterpret_cast<const float4*>(bd + ch * 8);
+          const float4 db = *reinterpret_cast<const float4*>(bd + ch * 8 + 4);
+          float acc[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -385,14 +394,16 @@ static bool ffn_tc_supported(const FfnParams& p) {
   return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144);
 }
 static size_t ffn_tc_workspace_bytes(int B, int H, int W, int C, int hidden) {
-  if (hidden != 4 * C || C != 144) return 0;
-  return (size_t)8 * B * H * W * C * sizeof(float);
+  if (hidden != 4 * C || (C != 144 && C != 72)) return 0;
+  return (size_t)(C == 144 ? 8 : 2) * B * H * W * C * sizeof(float);
 }
 
 template <int C, int CPG>
-static int launch_ffn_tc_c(const FfnParams& p, cudaStream_t stream) {
+static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
   using K = FfnTc<C, CPG>;
   const int n_tiles = p.B * ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW);
+  p.d_tiles_x = FastDiv(ceil_div(p.W, K::TW));
+  p.d_tiles_xy = FastDiv(ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW));
   const int cap = 148 * 2 / K::NG > 0 ? 148 * 2 / K::NG : 1;
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
@@ -418,7 +429,7 @@ static int launch_mixffn_tc(const FfnParams& p, cudaStream_t stream) {
   switch (p.C) {
     case 18: return launch_ffn_tc_c<18, 1>(p, stream);
     case 36: return launch_ffn_tc_c<36, 2>(p, stream);
-    case 72: return launch_ffn_tc_c<72, 4>(p, stream);
+    case 72: return launch_ffn_tc_c<72, 2>(p, stream);
     case 144: return launch_ffn_tc_c<144, 1>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_tc: C=%d", p.C);

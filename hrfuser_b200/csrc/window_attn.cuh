@@ -62,6 +62,7 @@ struct AttnParams {
   int B, H, W, C, heads, win;
   int cross, pad_mask;
   float eps;
+  FastDiv d_win_img, d_win_row;   // tensor-core kernel: window index -> (image, window row, col)
 };
 
 constexpr int kAttnThreads = 256;

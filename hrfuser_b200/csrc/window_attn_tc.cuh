@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   auto row_token = [&](int tile) -> int {
     const int wdx = tile * 2 + g;
     if (tile >= n_tiles || wdx >= n_windows || i >= S) return -1;
-    const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
+    int b, rem, wy, wx;
+    p.d_win_img.divmod(wdx, b, rem);
+    p.d_win_row.divmod(rem, wy, wx);
     const int h = wy * WIN + i / WIN - pad_t, w = wx * WIN + i % WIN - pad_l;
     return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
   };
@@ -457,10 +459,16 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < S; ++j) {
-        float v = sc[j] + tb[-((j / WIN) * (2 * WIN - 1) + (j % WIN))];
-        if (mask_me && !((vmask >> j) & 1ull)) v = -INFINITY;
-        sc[j] = v;
-        mx = fmaxf(mx, v);
+        sc[j] += tb[-((j / WIN) * (2 * WIN - 1) + (j % WIN))];
+        mx = fmaxf(mx, sc[j]);
+      }
+      if (use_mask) {             // uniform branch: no shipped config masks pad keys
+        mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          if (mask_me && !((vmask >> j) & 1ull)) sc[j] = -INFINITY;
+          mx = fmaxf(mx, sc[j]);
+        }
       }
       float sum = 0.f;
       const float mxl = mx * 1.4426950408889634f;
@@ -608,8 +616,10 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int n
 }
 
 template <int C, int HEADS, int HG>
-static int launch_attn_tc_ch(const AttnParams& p, cudaStream_t stream) {
+static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   constexpr int NG = HEADS / HG;
+  p.d_win_row = FastDiv(ceil_div(p.W, 7));
+  p.d_win_img = FastDiv(ceil_div(p.H, 7) * ceil_div(p.W, 7));
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
   const int per_group = n_tiles < 148 * 4 / NG ? n_tiles : 148 * 4 / NG;   // <= 4 CTAs / SM (TMEM)
