@@ -15,6 +15,8 @@
 //   epilogue      + b2, GELU, + residual, bf16 -> global
 // The 4C-wide hidden activation never leaves the SM.  BN is folded (eval mode).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mixffn.cuh"
 #include "umma.cuh"
@@ -404,7 +406,9 @@ static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
   const int n_tiles = p.B * ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW);
   p.d_tiles_x = FastDiv(ceil_div(p.W, K::TW));
   p.d_tiles_xy = FastDiv(ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW));
-  const int cap = 148 * 2 / K::NG > 0 ? 148 * 2 / K::NG : 1;
+  // debug knob: HRF_FFN_CTAS_PER_SM limits the persistent grid (occupancy experiments)
+  static const int per_sm = [] { const char* e = std::getenv("HRF_FFN_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+  const int cap = 148 * per_sm / K::NG > 0 ? 148 * per_sm / K::NG : 1;
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
   HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C, CPG>, K::SMEM));

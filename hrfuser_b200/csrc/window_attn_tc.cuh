@@ -22,6 +22,8 @@
 // Pad / partition / merge / crop are address arithmetic (same closed forms as
 // window_attn.cuh).  Accumulation, LayerNorm statistics and softmax are fp32.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "window_attn.cuh"
@@ -622,7 +624,9 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   p.d_win_img = FastDiv(ceil_div(p.H, 7) * ceil_div(p.W, 7));
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
-  const int per_group = n_tiles < 148 * 4 / NG ? n_tiles : 148 * 4 / NG;   // <= 4 CTAs / SM (TMEM)
+  // debug knob: HRF_ATTN_CTAS_PER_SM limits the persistent grid (occupancy experiments)
+  static const int per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e ? atoi(e) : 4; }();
+  const int per_group = n_tiles < 148 * per_sm / NG ? n_tiles : 148 * per_sm / NG;   // <= 4 CTAs / SM (TMEM)
   const int grid = per_group * NG;
   if (NG > 1) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn_tc: workspace required for C=%d", C);
   if (p.cross) {
