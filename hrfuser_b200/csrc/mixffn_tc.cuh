@@ -237,7 +237,6 @@ mixffn_tc_kernel(FfnParams p) {
         const int t = mt * 128 + row;                 // halo token
         if (t < K::NHALO) {
           const bool in = sIn[t] != 0;
-#pragma unroll
           const float4 ba = *reinterpret_cast<const float4*>(fb + ch * 8);
           const float4 bb = *reinterpret_cast<const float4*>(fb + ch * 8 + 4);
           const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
