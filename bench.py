@@ -112,9 +112,21 @@ def build_net(workload, precision, device=None, seed=0):
     return cfg, net, (H, W), mod_ch
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_port_fps(workload, budget_s=12.0, max_iters=8):
     """frames/s of the CPU port (oracle) on a bounded sample: batch-1 forwards."""
     from hrfuser_b200.utils import synthetic_inputs
+    use_all_host_threads()
     from oracle import hrfuser_oracle as O
     cfg, net, (H, W), mod_ch = build_net(workload, 'fp32')
     sd = net.state_dict()
@@ -139,6 +151,7 @@ def run_reference(args):
         return
     from hrfuser_b200.utils import synthetic_inputs
     from oracle import hrfuser_oracle as O
+    use_all_host_threads()
     cfg, net, (H, W), mod_ch = build_net(args.workload, 'fp32')
     sd = net.state_dict()
     x, mods = synthetic_inputs(1, H, W, mod_ch, seed=0)
@@ -296,7 +309,7 @@ def run_ours(args):
     total_frames = float(hdist.gather_frames(frames).sum())
 
     if rank == 0:
-        cpu = cpu_port_fps(args.workload) if not args.no_cpu_baseline else None
+        cpu = cpu_port_fps(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
         out = {
             'metric': METRIC, 'value': total_frames / (dev_ms / 1e3), 'unit': 'frames/s',
             'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': dev_ms / K,
