@@ -16,6 +16,7 @@
 #include "window_attn_tc.cuh"
 #include "mixffn_tc.cuh"
 #include "stem_conv_tc.cuh"
+#include "generic.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -115,13 +116,18 @@ static int check_attn(const HrfAttnDesc* d) {
   HRF_REQUIRE(d->win >= 1 && d->win * d->win <= 256, HRF_EUNSUPPORTED, "attn: window %d", d->win);
   HRF_REQUIRE(d->n_kv >= 0 && d->n_kv <= 8, HRF_EINVAL, "attn: n_kv=%d", d->n_kv);
   HRF_REQUIRE(d->dtype == HRF_F32 || d->dtype == HRF_BF16, HRF_EINVAL, "attn: dtype");
-  const AttnLayout L(d->C, d->heads, d->win);
-  HRF_REQUIRE(L.ldx <= 256, HRF_EUNSUPPORTED, "attn: C=%d too wide for the fused kernel", d->C);
-  const size_t smem = L.smem_floats(d->n_kv > 0, kAttnThreads / 32) * sizeof(float);
-  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED,
-              "attn: C=%d heads=%d win=%d needs %zu B shared memory (max 232448)", d->C, d->heads,
-              d->win, smem);
   return HRF_OK;
+}
+
+// which implementation serves a window-attention problem
+enum { PATH_TC = 0, PATH_FUSED_SIMT = 1, PATH_GENERIC = 2 };
+static int attn_path(const HrfAttnDesc* d) {
+  AttnParams p{};
+  p.C = d->C; p.heads = d->heads; p.win = d->win;
+  if (d->dtype == HRF_BF16 && attn_tc_supported(p) && !tc_disabled()) return PATH_TC;
+  const AttnLayout L(d->C, d->heads, d->win);
+  const size_t smem = L.smem_floats(d->n_kv > 0, kAttnThreads / 32) * sizeof(float);
+  return (L.ldx <= 256 && smem <= 227 * 1024) ? PATH_FUSED_SIMT : PATH_GENERIC;
 }
 
 size_t hrf_attn_blob_floats(const HrfAttnDesc* d) {
@@ -194,9 +200,13 @@ int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b
 }
 
 size_t hrf_attn_workspace_bytes(const HrfAttnDesc* d) {
-  if (!d || d->heads <= 0 || d->C <= 0 || d->dtype != HRF_BF16 || d->win != 7 || tc_disabled())
-    return 0;
-  return attn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->heads);
+  if (!d || d->heads <= 0 || d->C <= 0 || d->C % d->heads != 0 || d->win <= 0) return 0;
+  switch (attn_path(d)) {
+    case PATH_TC: return attn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->heads);
+    case PATH_GENERIC:
+      return sizeof(float) * attn_generic_ws_floats(d->B, d->H, d->W, d->C, d->heads, d->win, d->n_kv > 0);
+  }
+  return 0;
 }
 
 int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
@@ -224,11 +234,16 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
     HRF_REQUIRE(p.z && p.blob, HRF_EINVAL, "attn_fwd: null kv/blob %d", k);
     p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.heads = d->heads; p.win = d->win;
     p.cross = d->n_kv > 0; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
-    if (d->dtype == HRF_BF16 && attn_tc_supported(p) && !tc_disabled())
-      rc = launch_window_attn_tc(p, st);
-    else
-      rc = d->dtype == HRF_F32 ? launch_window_attn<float>(p, st)
-                               : launch_window_attn<__nv_bfloat16>(p, st);
+    switch (attn_path(d)) {
+      case PATH_TC: rc = launch_window_attn_tc(p, st); break;
+      case PATH_FUSED_SIMT:
+        rc = d->dtype == HRF_F32 ? launch_window_attn<float>(p, st)
+                                 : launch_window_attn<__nv_bfloat16>(p, st);
+        break;
+      default:
+        rc = d->dtype == HRF_F32 ? launch_window_attn_generic<float>(p, st)
+                                 : launch_window_attn_generic<__nv_bfloat16>(p, st);
+    }
     if (rc) return rc;
   }
   return HRF_OK;
@@ -242,8 +257,19 @@ static int check_ffn(const HrfFfnDesc* d) {
   HRF_REQUIRE(d->C % 2 == 0 && d->hidden % 4 == 0, HRF_EUNSUPPORTED,
               "ffn: C=%d must be even and hidden=%d a multiple of 4", d->C, d->hidden);
   HRF_REQUIRE(d->dtype == HRF_F32 || d->dtype == HRF_BF16, HRF_EINVAL, "ffn: dtype");
-  HRF_REQUIRE(FfnLayout(d->C, d->hidden).ldx <= 256, HRF_EUNSUPPORTED, "ffn: C=%d too wide", d->C);
   return HRF_OK;
+}
+
+static int ffn_path(const HrfFfnDesc* d) {
+  FfnParams p{};
+  p.C = d->C; p.hidden = d->hidden;
+  if (d->dtype == HRF_BF16 && ffn_tc_supported(p) && !tc_disabled()) return PATH_TC;
+  const FfnLayout L(d->C, d->hidden);
+  const int CT = d->C % 4 == 0 ? 4 : 2;
+  const int maxt = ceil_div((kFfnOut / 4) * (d->C / CT), kFfnThreads);
+  const bool fits = L.ldx <= 256 && maxt <= (CT == 4 ? 4 : 3) &&
+                    ffn_smem_floats(L) * sizeof(float) <= 227 * 1024;
+  return fits ? PATH_FUSED_SIMT : PATH_GENERIC;
 }
 
 size_t hrf_ffn_blob_floats(const HrfFfnDesc* d) {
@@ -305,8 +331,12 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
 }
 
 size_t hrf_ffn_workspace_bytes(const HrfFfnDesc* d) {
-  if (!d || d->C <= 0 || d->dtype != HRF_BF16 || tc_disabled()) return 0;
-  return ffn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->hidden);
+  if (!d || d->C <= 0 || d->hidden <= 0) return 0;
+  switch (ffn_path(d)) {
+    case PATH_TC: return ffn_tc_workspace_bytes(d->B, d->H, d->W, d->C, d->hidden);
+    case PATH_GENERIC: return sizeof(float) * ffn_generic_ws_floats(d->B, d->H, d->W, d->C, d->hidden);
+  }
+  return 0;
 }
 
 int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out,
@@ -320,10 +350,14 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
               HRF_EINVAL, "ffn_fwd: workspace of %zu bytes required, %zu given",
               hrf_ffn_workspace_bytes(d), workspace_bytes);
   FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
-  if (d->dtype == HRF_BF16 && ffn_tc_supported(p) && !tc_disabled())
-    return launch_mixffn_tc(p, (cudaStream_t)stream);
-  return d->dtype == HRF_F32 ? launch_mixffn<float>(p, (cudaStream_t)stream)
-                             : launch_mixffn<__nv_bfloat16>(p, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ffn_path(d)) {
+    case PATH_TC: return launch_mixffn_tc(p, st);
+    case PATH_FUSED_SIMT:
+      return d->dtype == HRF_F32 ? launch_mixffn<float>(p, st) : launch_mixffn<__nv_bfloat16>(p, st);
+  }
+  return d->dtype == HRF_F32 ? launch_mixffn_generic<float>(p, st)
+                             : launch_mixffn_generic<__nv_bfloat16>(p, st);
 }
 
 // ------------------------------------------------------------------ exchange

@@ -1,0 +1,290 @@
+// Generic (any width) un-fused path for window attention and MixFFN.
+//
+// The fused kernels keep a whole window / tile in shared memory, which caps the channel
+// count (C <= ~250 for the SIMT kernels, head_dim 18 for the tcgen05 ones).  HRFuser-B's
+// low-resolution branches (C = 312, 624; 16 heads of 39) go through this path instead:
+//   LayerNorm rows -> tiled fp32 GEMMs (+bias, activation, residuals) -> per-(window, head)
+//   attention core that gathers its 49 slots from the token tensors (pad slots contribute
+//   k = b_k, v = b_v exactly like the reference's zero padding after the norm).
+// Same packed fp32 weight sections as the fused SIMT kernels; intermediates live in a
+// caller-provided fp32 workspace.  Accuracy-first (fp32 FFMA, erff, expf).
+#pragma once
+#include "common.cuh"
+#include "mixffn.cuh"
+#include "window_attn.cuh"
+
+namespace hrf {
+
+// ---- LayerNorm of token rows: (n_tok, C) T -> fp32 -------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const T* x, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps,
+                                                      float* out, int n_tok, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_tok) return;
+  const T* src = x + (size_t)warp * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += Elem<T>::ld(src + c);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = Elem<T>::ld(src + c) - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  float* dst = out + (size_t)warp * C;
+  for (int c = lane; c < C; c += 32)
+    dst[c] = (Elem<T>::ld(src + c) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+}
+
+// ---- tiled fp32 GEMM: out = act(A[M,K] * Wt[K,N] + bias) (+ r1) (+ r2) ---------------------
+// A fp32 row-major with leading dimension lda; Wt k-major with leading dimension N.
+// act: 0 none, 1 ReLU, 2 GELU(erf).  out / residuals have leading dimension ldo.
+struct GemmParams {
+  const float* A; const float* Wt; const float* bias;
+  const void* r1; const void* r2; void* out;
+  int M, N, K, lda, ldo, act;
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(256) gemm_bias_act_kernel(GemmParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;      // 4x4 outputs per thread
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    for (int e = tid; e < BM * BK; e += 256) {             // A tile, transposed into smem
+      const int r = e / BK, k = e % BK;
+      As[k][r] = (m0 + r < p.M && k0 + k < p.K) ? __ldg(p.A + (size_t)(m0 + r) * p.lda + k0 + k) : 0.f;
+    }
+    for (int e = tid; e < BK * BN; e += 256) {
+      const int k = e / BN, n = e % BN;
+      Bs[k][n] = (k0 + k < p.K && n0 + n < p.N) ? __ldg(p.Wt + (size_t)(k0 + k) * p.N + n0 + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tc]);
+      const float a[4] = {As[k][tr], As[k][tr + 1], As[k][tr + 2], As[k][tr + 3]};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]); acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  const TO* r1 = static_cast<const TO*>(p.r1);
+  const TO* r2 = static_cast<const TO*>(p.r2);
+  TO* out = static_cast<TO*>(p.out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tr + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tc + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+      if (p.act == 1) v = fmaxf(v, 0.f);
+      else if (p.act == 2) v = gelu_erf(v);
+      const size_t off = (size_t)m * p.ldo + n;
+      if (r1) v += Elem<TO>::ld(r1 + off);
+      if (r2) v += Elem<TO>::ld(r2 + off);
+      Elem<TO>::st(out + off, v);
+    }
+  }
+}
+
+template <typename TO>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64));
+  HRF_REQUIRE(grid.y <= 65535, HRF_EUNSUPPORTED, "gemm: M=%d too large", p.M);
+  gemm_bias_act_kernel<TO><<<grid, 256, 0, stream>>>(p);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// ---- attention core: one CTA (4 warps) per (window, head) ---------------------------------
+// q, k, v: fp32 (n_tok, C) already projected (q pre-scaled); o: fp32 (n_tok, KO) head padded.
+struct CoreParams {
+  const float* q; const float* k; const float* v; float* o;
+  const float* bk; const float* bv;      // projection biases: keys / values of pad slots
+  const float* rpb;                      // (heads, (2w-1)^2)
+  int B, H, W, C, heads, win, KO, hdp, pad_mask;
+};
+
+__global__ void __launch_bounds__(128) attn_core_kernel(CoreParams p) {
+  extern __shared__ __align__(16) float core_sm[];
+  float* sm = core_sm;
+  const int win = p.win, S = win * win, hd = p.C / p.heads;
+  const int ld = hd | 1;                                   // odd stride: conflict-free row walks
+  float* Q = sm; float* Kt = Q + S * ld; float* V = Kt + S * ld;
+  float* P = V + S * ld;                                   // [4 warps][S]
+  int* tok = reinterpret_cast<int*>(P + 4 * S);
+  const int h = blockIdx.y, wdx = blockIdx.x;
+  const int nWh = ceil_div(p.H, win), nWw = ceil_div(p.W, win);
+  const int pad_h = nWh * win - p.H, pad_w = nWw * win - p.W;
+  const bool use_mask = p.pad_mask && pad_h > 0 && pad_w > 0;
+  const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int y = wy * win + s / win - pad_h / 2, x = wx * win + s % win - pad_w / 2;
+    tok[s] = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? (b * p.H + y) * p.W + x : -1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < S * hd; e += blockDim.x) {
+    const int s = e / hd, d = e - s * hd, t = tok[s], c = h * hd + d;
+    Q[s * ld + d] = t >= 0 ? __ldg(p.q + (size_t)t * p.C + c) : 0.f;
+    Kt[s * ld + d] = t >= 0 ? __ldg(p.k + (size_t)t * p.C + c) : __ldg(p.bk + c);
+    V[s * ld + d] = t >= 0 ? __ldg(p.v + (size_t)t * p.C + c) : __ldg(p.bv + c);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Pw = P + warp * S;
+  const float* rp = p.rpb + (size_t)h * (2 * win - 1) * (2 * win - 1);
+  for (int i = warp; i < S; i += 4) {
+    if (tok[i] < 0) continue;                              // pad queries are cropped anyway
+    const int ih = i / win, iw = i - ih * win;
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(Q[i * ld + d], Kt[j * ld + d], s);
+      const int jh = j / win, jw = j - jh * win;
+      s += __ldg(rp + (ih - jh + win - 1) * (2 * win - 1) + (iw - jw + win - 1));
+      if (use_mask && tok[j] < 0) s = -INFINITY;
+      Pw[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = expf(Pw[j] - mx); Pw[j] = e; sum += e; }
+    const float inv = 1.0f / warp_sum(sum);
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < S; ++j) o = fmaf(Pw[j], V[j * ld + d], o);
+      p.o[(size_t)tok[i] * p.KO + h * p.hdp + d] = o * inv;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- depthwise 3x3 (stride 1, pad 1) + bias + GELU on fp32 (n_tok, CH) ------------------------
+__global__ void __launch_bounds__(256) dw3x3_gelu_kernel(const float* x, const float* __restrict__ wd,
+                                                         const float* __restrict__ bd, float* out,
+                                                         int B, int H, int W, int CH) {
+  const size_t total = (size_t)B * H * W * CH;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % CH);
+    const size_t t = e / CH;
+    const int w = (int)(t % W), h = (int)((t / W) % H), b = (int)(t / ((size_t)W * H));
+    float s = __ldg(bd + c);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = h + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = w + dx;
+        if (xx < 0 || xx >= W) continue;
+        s = fmaf(__ldg(x + ((size_t)(b * H + y) * W + xx) * CH + c),
+                 __ldg(wd + (size_t)((dy + 1) * 3 + dx + 1) * CH + c), s);
+      }
+    }
+    out[e] = gelu_erf(s);
+  }
+}
+
+// ---- drivers --------------------------------------------------------------------------------
+static size_t attn_generic_ws_floats(int B, int H, int W, int C, int heads, int win, bool cross) {
+  const AttnLayout L(C, heads, win);
+  const size_t n = (size_t)B * H * W;
+  return n * C * (cross ? 5 : 4) + n * L.KO;      // xn (zn) q k v + o
+}
+
+template <typename T>
+static int launch_window_attn_generic(const AttnParams& p, cudaStream_t st) {
+  const AttnLayout L(p.C, p.heads, p.win);
+  const int n = p.B * p.H * p.W, C = p.C;
+  HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn (generic path): workspace required");
+  float* ws = static_cast<float*>(p.ws);
+  float* xn = ws; ws += (size_t)n * C;
+  float* zn = xn;
+  if (p.cross) { zn = ws; ws += (size_t)n * C; }
+  float* q = ws; ws += (size_t)n * C;
+  float* k = ws; ws += (size_t)n * C;
+  float* v = ws; ws += (size_t)n * C;
+  float* o = ws;
+  const float* blob = p.blob;
+  const int lnb = ceil_div(n * 32, 256);
+  ln_rows_kernel<T><<<lnb, 256, 0, st>>>(static_cast<const T*>(p.xq), blob + L.o_lnq_w,
+                                         blob + L.o_lnq_b, p.eps, xn, n, C);
+  count_launch();
+  if (p.cross) {
+    ln_rows_kernel<T><<<lnb, 256, 0, st>>>(static_cast<const T*>(p.z), blob + L.o_lnkv_w,
+                                           blob + L.o_lnkv_b, p.eps, zn, n, C);
+    count_launch();
+  }
+  HRF_CUDA(cudaGetLastError());
+  int rc;
+  GemmParams g{xn, blob + L.o_wq, blob + L.o_bq, nullptr, nullptr, q, n, C, C, C, C, 0};
+  if ((rc = launch_gemm<float>(g, st))) return rc;
+  g.A = zn; g.Wt = blob + L.o_wk; g.bias = blob + L.o_bk; g.out = k;
+  if ((rc = launch_gemm<float>(g, st))) return rc;
+  g.Wt = blob + L.o_wv; g.bias = blob + L.o_bv; g.out = v;
+  if ((rc = launch_gemm<float>(g, st))) return rc;
+  HRF_CUDA(cudaMemsetAsync(o, 0, (size_t)n * L.KO * sizeof(float), st));   // head-pad lanes
+  CoreParams c{q, k, v, o, blob + L.o_bk, blob + L.o_bv, blob + L.o_rpb,
+               p.B, p.H, p.W, C, p.heads, p.win, L.KO, L.hdp, p.pad_mask};
+  const int S = p.win * p.win, ld = L.hd | 1;
+  const size_t smem = ((size_t)3 * S * ld + 4 * S + S) * sizeof(float);
+  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "attn core: window %d x head_dim %d", p.win, L.hd);
+  HRF_CUDA(ensure_smem((const void*)attn_core_kernel, smem));
+  dim3 grid(p.B * ceil_div(p.H, p.win) * ceil_div(p.W, p.win), p.heads);
+  attn_core_kernel<<<grid, 128, smem, st>>>(c);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  // out = resid (+ z) + o Wo^T + bo
+  GemmParams go{o, blob + L.o_wo, blob + L.o_bo, p.resid, p.cross ? p.z : nullptr, p.out,
+                n, C, L.KO, L.KO, C, 0};
+  return launch_gemm<T>(go, st);
+}
+
+static size_t ffn_generic_ws_floats(int B, int H, int W, int C, int hidden) {
+  const size_t n = (size_t)B * H * W;
+  return n * C + 2 * n * hidden;
+}
+
+template <typename T>
+static int launch_mixffn_generic(const FfnParams& p, cudaStream_t st) {
+  const FfnLayout L(p.C, p.hidden);
+  const int n = p.B * p.H * p.W, C = p.C, Hd = p.hidden;
+  HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn (generic path): workspace required");
+  float* xn = static_cast<float*>(p.ws);
+  float* h1 = xn + (size_t)n * C;
+  float* h2 = h1 + (size_t)n * Hd;
+  const float* blob = p.blob;
+  ln_rows_kernel<T><<<ceil_div(n * 32, 256), 256, 0, st>>>(static_cast<const T*>(p.x), blob + L.o_ln_w,
+                                                           blob + L.o_ln_b, p.eps, xn, n, C);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  int rc;
+  GemmParams g1{xn, blob + L.o_w1, blob + L.o_b1, nullptr, nullptr, h1, n, Hd, C, C, Hd, 2};
+  if ((rc = launch_gemm<float>(g1, st))) return rc;
+  const size_t total = (size_t)n * Hd;
+  const int dgrid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  dw3x3_gelu_kernel<<<dgrid, 256, 0, st>>>(h1, blob + L.o_wd, blob + L.o_bd, h2, p.B, p.H, p.W, Hd);
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  // out = x + GELU(h2 W2^T + b2)
+  GemmParams g2{h2, blob + L.o_w2, blob + L.o_b2, p.x, nullptr, p.out, n, C, Hd, Hd, C, 2};
+  return launch_gemm<T>(g2, st);
+}
+
+}  // namespace hrf

@@ -13,6 +13,7 @@ LN = dict(type='LN', eps=1e-6)
 NUS_T = [(96, 160, 18, 1), (48, 80, 36, 2), (24, 40, 72, 4), (12, 20, 144, 8)]
 STF_T = [(96, 312, 18, 1), (48, 156, 36, 2), (24, 78, 72, 4), (12, 39, 144, 8)]
 NUS_B_FUSED = [(96, 160, 78, 2), (48, 80, 156, 4)]       # widths the fused kernels cover
+NUS_B_WIDE = [(24, 40, 312, 8), (12, 20, 624, 16)]        # generic (un-fused) path
 # small / ragged grids: no padding needed, one-sided padding, tiny maps, single window
 EDGE = [(7, 7, 18, 1), (14, 21, 36, 2), (5, 3, 18, 1), (8, 8, 72, 4), (13, 9, 36, 2), (1, 1, 18, 1)]
 

@@ -28,16 +28,8 @@ def _net(cfg, seed=1):
     return net
 
 
-def test_hrfuser_b_wide_branches_are_refused_not_faked(built_lib):
-    """Round-1 gap: the fused kernels cover C <= 252; HRFuser-B's
-    312/624-wide branches must raise, not silently fall back."""
-    from hrfuser_b200 import _lib
-    net = _net(backbone_cfg('b', 'nus'))
-    with pytest.raises(_lib.HrfError, match='too wide'):
-        BackboneEngine(net, 'fp32', device_ops=blob_emul)
-
-
-@pytest.mark.parametrize('tag,v,d,mc', [('t_nus', 't', 'nus', (3, 3)), ('t_stf', 't', 'stf', (3, 2, 1))])
+@pytest.mark.parametrize('tag,v,d,mc', [('t_nus', 't', 'nus', (3, 3)), ('t_stf', 't', 'stf', (3, 2, 1)),
+                                        ('b_nus', 'b', 'nus', (3, 3))])
 def test_engine_wiring_and_packers_vs_reference_golden(built_lib, tag, v, d, mc):
     net = _net(backbone_cfg(v, d))
     H, W = (int(t) for t in E2E[tag + '_hw'])

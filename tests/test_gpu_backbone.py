@@ -72,6 +72,18 @@ def test_t_stf_4mod_fp32_sparse_and_dropped(built_lib):
         assert_parity(g, r, 'fp32', f'T-stf out{i}')
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_b_nus_all_widths(built_lib, precision):
+    """HRFuser-B (C = 78 / 156 / 312 / 624, head_dim 39): fused SIMT kernels on the two
+    high-resolution branches, the generic un-fused path on the wide ones."""
+    got, ref = _run(backbone_cfg('b', 'nus'), (3, 3), 1, 64, 96, precision)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        if precision == 'fp32':
+            assert_parity(g, r, 'fp32', f'B-nus out{i}')
+        else:
+            assert rel_err(g.cpu(), r) < 3e-2, (i, rel_err(g.cpu(), r))
+
+
 def test_forward_spellings_and_errors(built_lib):
     net = _build(tiny_cfg(2), 'fp32').cuda()
     x, mods = synthetic_inputs(1, 32, 32, (3, 3), device='cuda')
