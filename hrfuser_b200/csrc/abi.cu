@@ -320,6 +320,9 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
         fb[800 + jj] = (bd ? bd[j] : 0.f) * s2[j] + t2[j];
         for (int k = 0; k < C; ++k)
           w1t[umma::tile_off(jj, k, 80) / 2] = f32_to_bf16(w1[(size_t)j * C + k] * s1[j]);
+        // bias row: the kernels that have a spare K column (KC > C) feed a constant 1 in
+        // column C of the activation tile, so b1 rides through the MMA
+        if (KC > C) w1t[umma::tile_off(jj, C, 80) / 2] = f32_to_bf16(fb[jj]);
         for (int n = 0; n < C; ++n)
           w2t[umma::tile_off(n, jj, NOUT) / 2] = f32_to_bf16(w2[(size_t)n * Hd + j] * s3[n]);
       }

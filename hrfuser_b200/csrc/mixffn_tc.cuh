@@ -25,36 +25,56 @@
 namespace hrf {
 
 // CPG = hidden chunks handled by one CTA.  CPG == NCH: the CTA finishes the block.
-// CPG < NCH (C = 144: 1 920 tokens but 8 chunks): NCH/CPG CTAs share a token tile,
+// CPG < NCH (C = 72, 144: few tokens, many chunks): NCH/CPG CTAs share a token tile,
 // each writes its fp32 partial fc2 product to a workspace and `ffn_reduce_kernel`
 // applies b2 / GELU / residual to the fixed-order sum.
+//
+// Two tile geometries:
+//   C = 18 (the 96x160 branch, 77 % of all FFN tokens): 6 x 14 outputs, 8 x 16 = 128 halo
+//       tokens = exactly one M=128 fc1 tile, 256 threads, 128 TMEM columns, ~55 KB smem
+//       -> four CTAs (four independent barrier domains) per SM;
+//   otherwise: 8 x 16 outputs, 10 x 18 = 180 halo tokens in two M tiles, 512 threads.
 template <int C, int CPG>
 struct FfnTc {
   static constexpr int HID = 4 * C, NCH = HID / 72, NG = NCH / CPG;
   static constexpr bool SPLIT = CPG < NCH, BIGC = C > 40;
   static_assert(HID % 72 == 0 && NCH % CPG == 0, "hidden must split into 72-channel chunks");
   static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
-  static constexpr int TH = 8, TW = 16, HH = TH + 2, HW = TW + 2, NHALO = HH * HW;   // 180
+  static constexpr bool SMALL = (C == 18);
+  static constexpr int TH = SMALL ? 6 : 8, TW = SMALL ? 14 : 16;
+  static constexpr int HH = TH + 2, HW = TW + 2, NHALO = HH * HW;      // 128 | 180
+  static constexpr int NTOK = TH * TW;                                  // 84 | 128 outputs
+  static constexpr int NMT = (NHALO + 127) / 128;                       // fc1 M tiles: 1 | 2
+  static constexpr int NT = SMALL ? 256 : 512, NGQ = NT / 128;          // threads, groups per quadrant
   static constexpr int XT = 128 * KC * 2;            // one XN operand tile
-  static constexpr int H1R = 184;                    // rows per 16-byte column group of H1 (>= 180)
-  // H1 (GELU(fc1) on the halo) is kept in fp32 where two CTAs per SM still fit
-  // (no bf16 unpacking in the depthwise loop, no extra rounding); bf16 otherwise
-  static constexpr bool H1F32 = (C == 18) || (C == 144);
+  static constexpr int H1R = (NHALO + 7) / 8 * 8;    // rows per 16-byte column group of H1
+  // fc1 bias through the MMA: XN column C holds 1 for in-image tokens and W1 row C holds b1, so
+  // the epilogue needs neither a bias add nor the outside-the-image select (zero rows give
+  // GELU(0) = 0).  Needs a spare K column (not C = 144).
+  static constexpr bool BIAS_MMA = KC > C;
+  // H1 (GELU(fc1) on the halo) in fp32 where smem allows (C = 144), bf16 otherwise
+  static constexpr bool H1F32 = (C == 144);
   static constexpr int H1_B = (H1F32 ? 18 : 9) * H1R * 16;
+  // H2 = fc2 A operand: NTOK live rows; the M=128 MMA also reads (and ignores) the rows up to
+  // 127, which alias the next chunk / the tables behind the tile
+  static constexpr int H2R = (NTOK + 7) / 8 * 8;                         // 88 | 128
+  static constexpr int H2_B = 9 * H2R * 16 + 128 * 16;
   // shared-memory map (bytes)
   static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
   static constexpr int o_w2 = o_w1 + CPG * N1 * KC * 2;        // CPG tiles [NOUT x 80]
-  static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;      // 2 tiles
-  static constexpr int o_h1 = o_xn + 2 * XT;                   // (9 | 18) x H1R x 16
-  static constexpr int o_h2 = o_h1 + H1_B;                     // 10 x 128 x 16
-  static constexpr int o_f32 = o_h2 + 10 * 128 * 16;           // per chunk 880 floats, then b2[NOUT]
+  static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;      // NMT tiles
+  static constexpr int o_h1 = o_xn + NMT * XT;
+  static constexpr int o_h2 = o_h1 + H1_B;
+  static constexpr int o_f32 = o_h2 + H2_B;                    // per chunk 880 floats, then b2[NOUT]
   static constexpr int o_ln = o_f32 + (CPG * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
   static constexpr int C4 = (C + 3) / 4 * 4;
   static constexpr int o_in = o_ln + 2 * C4 * 4;               // inside flags [256] bytes
   static constexpr int SMEM = o_in + 256;
-  static constexpr int D_COLS = 2 * N1;                        // fc1 accumulators (two M tiles)
+  static constexpr int D_COLS = NMT * N1;                      // fc1 accumulators
   static constexpr int Y_COL = D_COLS;                         // fc2 accumulator
-  static constexpr int TMEM_COLS = (D_COLS + NOUT <= 256) ? 256 : 512;
+  static constexpr int TMEM_COLS = (D_COLS + NOUT <= 128) ? 128 : (D_COLS + NOUT <= 256) ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (SMEM + 1024) * 4 <= 227 * 1024 && TMEM_COLS <= 128 ? 4
+                                   : (SMEM + 1024) * 2 <= 227 * 1024 && TMEM_COLS <= 256 ? 2 : 1;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -74,19 +94,16 @@ __device__ __forceinline__ float gelu_as(float x) {
   return fmaf(hx, t, hx);
 }
 
-constexpr int kFfnTcThreads = 512;
-
-// 512 threads = 16 warps: warp w reads TMEM lanes 32*(w%4).. (its quadrant q) and
-// belongs to group gq = w/4.  Epilogue and depthwise work is dealt out in units of
-// (row, 8-channel chunk) so all four groups of a quadrant stay busy and no thread
-// holds more than 8 accumulators (<= 64 registers -> 2 CTAs = 32 warps per SM).
+// Warp w reads TMEM lanes 32*(w%4).. (its quadrant q) and belongs to group gq = w/4.
+// Epilogue and depthwise work is dealt out in units of (row, 8-channel chunk) so all groups of
+// a quadrant stay busy and no thread holds more than 8 accumulators (<= 64 registers).
 template <int C, int CPG>
-__global__ void __launch_bounds__(kFfnTcThreads, (FfnTc<C, CPG>::SMEM * 2 <= 226 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(FfnTc<C, CPG>::NT, FfnTc<C, CPG>::CTAS_PER_SM)
 mixffn_tc_kernel(FfnParams p) {
   using namespace umma;
   using K = FfnTc<C, CPG>;
   constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH, NG = K::NG;
-  constexpr int NT = kFfnTcThreads;
+  constexpr int NT = K::NT, NGQ = K::NGQ, NMT = K::NMT;
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -116,12 +133,12 @@ mixffn_tc_kernel(FfnParams p) {
       sLn[e] = __ldg(blob + L.o_ln_w + e);
       sLn[K::C4 + e] = __ldg(blob + L.o_ln_b + e);
     }
-    // zero both XN tiles (rows 52..127 of tile 1 are never written again) and H2
+    // zero the XN tiles (dead rows of the last M tile are never written again) and H2
     // (its 10th chunk, channels 72..79, stays zero)
     uint4* z = reinterpret_cast<uint4*>(sm + K::o_xn);
-    for (int e = tid; e < 2 * K::XT / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < NMT * K::XT / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
     z = reinterpret_cast<uint4*>(sm + K::o_h2);
-    for (int e = tid; e < 10 * 128; e += NT) z[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < K::H2_B / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   if (tid == 0) {
@@ -142,9 +159,9 @@ mixffn_tc_kernel(FfnParams p) {
   const int n_tiles = p.B * tiles_x * tiles_y;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
-  // epilogue-1 units of this quadrant: (M tile 0, chunk 0..8) and, where tile 1 has
-  // live rows in this quadrant (halo tokens 128..179), (M tile 1, chunk 0..8)
-  const int n_units = (128 + q * 32 < K::NHALO) ? 18 : 9;
+  // epilogue-1 units of this quadrant: (M tile mt, chunk 0..8) for every M tile that has live
+  // halo rows in this quadrant
+  const int n_units = 9 * ((K::NHALO - q * 32 + 127) / 128);
 
   // Software pipeline (C <= 40): halo token `tid` of the NEXT tile is requested while the
   // current tile computes; the residual slice of the first epilogue-2 unit is requested
@@ -182,9 +199,9 @@ mixffn_tc_kernel(FfnParams p) {
         if constexpr (PIPE) {
           float v[C];
           unpack_row<C>(xr, v);
-          ln_row_to_tile<C, KC>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+          ln_row_to_tile<C, KC, K::BIAS_MMA>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
         } else {
-          ln_token<C, KC, true>(x + (size_t)htok * C, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+          ln_token<C, KC, true, K::BIAS_MMA>(x + (size_t)htok * C, sLn, sLn + K::C4, p.eps, xt, tid & 127);
         }
       } else {
         const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -196,8 +213,8 @@ mixffn_tc_kernel(FfnParams p) {
     const int htok_next = halo_token(tile + tile_step);
     uint32_t xnext[NW];
     if (PIPE && htok_next >= 0) load_row_raw<C>(x + (size_t)htok_next * C, xnext);
-    const int oh = ty0 + (row >> 4), ow = tx0 + (row & 15);
-    const bool o_in = oh < p.H && ow < p.W;
+    const int oh = ty0 + row / K::TW, ow = tx0 + row % K::TW;
+    const bool o_in = row < K::NTOK && oh < p.H && ow < p.W;
     const size_t o_tok = o_in ? (size_t)(b * p.H + oh) * p.W + ow : 0;
     uint32_t rres[4] = {0u, 0u, 0u, 0u};           // residual of epilogue-2 unit cc = gq
     if (!K::SPLIT && o_in && gq * 8 < C) {
@@ -208,7 +225,7 @@ mixffn_tc_kernel(FfnParams p) {
 
 #pragma unroll 1
     for (int c = 0; c < CPG; ++c) {
-      // ---- fc1 on both halo M tiles ---------------------------------------------------
+      // ---- fc1 on the halo M tile(s) ---------------------------------------------------
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -217,7 +234,7 @@ mixffn_tc_kernel(FfnParams p) {
         constexpr uint32_t id1 = idesc_bf16(128, N1, false, false);
         const uint32_t w1c = a_w1 + c * (N1 * KC * 2);
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NMT; ++t)
 #pragma unroll
           for (int s = 0; s < KC / 16; ++s)
             mma_bf16(tmem + t * N1, desc_kmajor(a_xn + t * K::XT, 128, s), desc_kmajor(w1c, N1, s),
@@ -228,22 +245,27 @@ mixffn_tc_kernel(FfnParams p) {
       phase ^= 1;
       tc_fence_after();
 
-      // ---- epilogue 1: + b1, GELU, zero outside the image -> H1 -----------------------
+      // ---- epilogue 1: (+ b1,) GELU, zero outside the image -> H1 -----------------------
       const float* fb = sF + c * 880;
 #pragma unroll 1
-      for (int u = gq; u < n_units; u += 4) {         // warp-uniform trip count
+      for (int u = gq; u < n_units; u += NGQ) {       // warp-uniform trip count
         const int mt = u >= 9 ? 1 : 0, ch = u - mt * 9;
         float v[8];
         tmem_ld8(trow + mt * N1 + ch * 8, v);
         tmem_ld_wait();
         const int t = mt * 128 + row;                 // halo token
         if (t < K::NHALO) {
-          const bool in = sIn[t] != 0;
-          const float4 ba = *reinterpret_cast<const float4*>(fb + ch * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(fb + ch * 8 + 4);
-          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          if constexpr (K::BIAS_MMA) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + bv[j]) : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = gelu_as(v[j]);
+          } else {
+            const bool in = sIn[t] != 0;
+            const float4 ba = *reinterpret_cast<const float4*>(fb + ch * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(fb + ch * 8 + 4);
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + bv[j]) : 0.f;
+          }
           if constexpr (K::H1F32) {
             float4* h1 = reinterpret_cast<float4*>(sm + K::o_h1);
             h1[(2 * ch) * K::H1R + t] = make_float4(v[0], v[1], v[2], v[3]);
@@ -256,13 +278,14 @@ mixffn_tc_kernel(FfnParams p) {
       tc_fence_before();
       __syncthreads();
 
-      // ---- depthwise 3x3 + GELU: unit = (output token, 8-channel chunk) ---------------
+      // ---- depthwise 3x3 + GELU: unit = (output token, 8-channel chunk), dealt linearly ---
       {
-        const int o = tid & 127, oy = o >> 4, ox = o & 15;
         const float* wd = fb + 80;
         const float* bd = fb + 800;
 #pragma unroll 1
-        for (int ch = gq; ch < 9; ch += 4) {
+        for (int id = tid; id < K::NTOK * 9; id += NT) {
+          const int ch = id / K::NTOK, o = id - ch * K::NTOK;
+          const int oy = o / K::TW, ox = o - oy * K::TW;
           const float4 da = *reinterpret_cast<const float4*>(bd + ch * 8);
           const float4 db = *reinterpret_cast<const float4*>(bd + ch * 8 + 4);
           float acc[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
@@ -295,7 +318,7 @@ mixffn_tc_kernel(FfnParams p) {
             }
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = gelu_as(acc[j]);
-          st_chunk(sm + K::o_h2, o, ch, 128, acc);
+          st_chunk(sm + K::o_h2, o, ch, K::H2R, acc);
         }
       }
 
@@ -309,11 +332,11 @@ mixffn_tc_kernel(FfnParams p) {
         const uint32_t w2c = a_w2 + c * (NOUT * N1 * 2);
 #pragma unroll
         for (int s = 0; s < N1 / 16; ++s)
-          mma_bf16(tmem + K::Y_COL, desc_kmajor(a_h2, 128, s), desc_kmajor(w2c, NOUT, s), id2,
+          mma_bf16(tmem + K::Y_COL, desc_kmajor(a_h2, K::H2R, s), desc_kmajor(w2c, NOUT, s), id2,
                    (c > 0) || (s > 0));
         mma_commit(&bar);
       }
-      cta_wait(&bar, phase);       // H2 / XN free again, Y complete after the last chunk
+      cta_wait(&bar, phase);        // H2 / XN free again, Y complete after the last chunk
       phase ^= 1;
       tc_fence_after();
     }
@@ -324,7 +347,7 @@ mixffn_tc_kernel(FfnParams p) {
       const size_t tok = o_tok;
       const float* b2 = sF + CPG * 880;
 #pragma unroll 1
-      for (int cc = gq; cc * 8 < C; cc += 4) {        // warp-uniform trip count
+      for (int cc = gq; cc * 8 < C; cc += NGQ) {      // warp-uniform trip count
         float y[8];
         tmem_ld8(trow + K::Y_COL + cc * 8, y);
         tmem_ld_wait();
@@ -408,12 +431,13 @@ static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
   p.d_tiles_x = FastDiv(ceil_div(p.W, K::TW));
   p.d_tiles_xy = FastDiv(ceil_div(p.H, K::TH) * ceil_div(p.W, K::TW));
   // debug knob: HRF_FFN_CTAS_PER_SM limits the persistent grid (occupancy experiments)
-  static const int per_sm = [] { const char* e = std::getenv("HRF_FFN_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+  static const int env_per_sm = [] { const char* e = std::getenv("HRF_FFN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const int per_sm = env_per_sm > 0 ? env_per_sm : K::CTAS_PER_SM;
   const int cap = 148 * per_sm / K::NG > 0 ? 148 * per_sm / K::NG : 1;
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
   HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C, CPG>, K::SMEM));
-  mixffn_tc_kernel<C, CPG><<<grid, kFfnTcThreads, K::SMEM, stream>>>(p);
+  mixffn_tc_kernel<C, CPG><<<grid, K::NT, K::SMEM, stream>>>(p);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   if constexpr (K::SPLIT) {

@@ -153,8 +153,9 @@ __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float* 
   }
 }
 
-// LayerNorm of one row held in registers -> bf16 chunks of an R=128 operand tile
-template <int C, int KC>
+// LayerNorm of one row held in registers -> bf16 chunks of an R=128 operand tile.
+// ONE: column C of the tile is set to 1 (the bias row of the weight tile multiplies it).
+template <int C, int KC, bool ONE = false>
 __device__ __forceinline__ void ln_row_to_tile(const float* x, const float* gamma,
                                                const float* beta, float eps, unsigned char* tile,
                                                int row) {
@@ -172,7 +173,8 @@ __device__ __forceinline__ void ln_row_to_tile(const float* x, const float* gamm
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = ch * 8 + j;
-      v[j] = (c < C) ? fmaf((x[c < C ? c : 0] - mean) * rstd, gamma[c < C ? c : 0], beta[c < C ? c : 0]) : 0.f;
+      v[j] = (c < C) ? fmaf((x[c < C ? c : 0] - mean) * rstd, gamma[c < C ? c : 0], beta[c < C ? c : 0])
+                     : (ONE && c == C) ? 1.f : 0.f;
     }
     umma::st_chunk(tile, row, ch, 128, v);
   }
@@ -186,7 +188,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // LayerNorm of one token row straight from global memory (three cached passes) for
 // wide C, where holding the row in registers would spill
-template <int C, int KC>
+template <int C, int KC, bool ONE = false>
 __device__ __forceinline__ void ln_row_streamed(const __nv_bfloat16* src, const float* gamma,
                                                 const float* beta, float eps, unsigned char* tile,
                                                 int row) {
@@ -218,21 +220,21 @@ __device__ __forceinline__ void ln_row_streamed(const __nv_bfloat16* src, const 
       for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mean) * rstd, gamma[ch * 8 + j], beta[ch * 8 + j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      for (int j = 0; j < 8; ++j) v[j] = (ONE && ch * 8 + j == C) ? 1.f : 0.f;
     }
     umma::st_chunk(tile, row, ch, 128, v);
   }
 }
 
-template <int C, int KC, bool BIGC>
+template <int C, int KC, bool BIGC, bool ONE = false>
 __device__ __forceinline__ void ln_token(const __nv_bfloat16* src, const float* gamma,
                                          const float* beta, float eps, unsigned char* tile, int row) {
   if constexpr (BIGC) {
-    ln_row_streamed<C, KC>(src, gamma, beta, eps, tile, row);
+    ln_row_streamed<C, KC, ONE>(src, gamma, beta, eps, tile, row);
   } else {
     float x[C];
     load_row_bf16<C>(src, x);
-    ln_row_to_tile<C, KC>(x, gamma, beta, eps, tile, row);
+    ln_row_to_tile<C, KC, ONE>(x, gamma, beta, eps, tile, row);
   }
 }
 
