@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libhrfuser_b200.so')
+# HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
+LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
 ABI_VERSION = 3
 
 HRF_F32, HRF_BF16 = 0, 1

@@ -15,6 +15,7 @@
 #include "umma_selftest.cuh"
 #include "window_attn_tc.cuh"
 #include "mixffn_tc.cuh"
+#include "mixffn_tcd.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
 #include "window_attn.cuh"
@@ -328,7 +329,26 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
       }
     }
     float* b2p = f + (size_t)L.tc_nchunk * 880;
-    for (int c = 0; c < C; ++c) b2p[c] = (b2 ? b2[c] : 0.f) * s3[c] + t3[c];
+    for (int c = 0; c < C; ++c) {
+      b2p[c] = (b2 ? b2[c] : 0.f) * s3[c] + t3[c];
+      // fc2 bias row: K index 72 (first padding channel of the chunk) of the FIRST chunk's W2
+      // tile; the kernels keep a constant 1 in that column of the hidden activations
+      tile2[umma::tile_off(c, 72, NOUT) / 2] = f32_to_bf16(b2p[c]);
+    }
+    // depthwise-conv tiles (see FfnLayout::o_tc_dg)
+    uint16_t* dg = reinterpret_cast<uint16_t*>(blob + L.o_tc_dg);
+    for (int ch = 0; ch < L.tc_nchunk; ++ch) {
+      const float* fb = f + (size_t)ch * 880;
+      for (int s = 0; s < 5; ++s)
+        for (int n = 0; n < 16; ++n) {
+          const int jj = 16 * s + n;
+          if (jj >= 72) continue;
+          uint16_t* base = dg + ((size_t)ch * 50 + s * 10) * 256;
+          for (int t = 0; t < 9; ++t)
+            base[t * 256 + umma::tile_off(n, n, 16) / 2] = f32_to_bf16(fb[80 + t * 80 + jj]);
+          base[9 * 256 + umma::tile_off(n, 8, 16) / 2] = f32_to_bf16(fb[800 + jj]);
+        }
+    }
   }
   return HRF_OK;
 }
@@ -355,7 +375,7 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
   FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
   cudaStream_t st = (cudaStream_t)stream;
   switch (ffn_path(d)) {
-    case PATH_TC: return launch_mixffn_tc(p, st);
+    case PATH_TC: return ffn_tcd_supported(p) ? launch_mixffn_tcd(p, st) : launch_mixffn_tc(p, st);
     case PATH_FUSED_SIMT:
       return d->dtype == HRF_F32 ? launch_mixffn<float>(p, st) : launch_mixffn<__nv_bfloat16>(p, st);
   }
@@ -495,3 +515,16 @@ int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, co
 }
 
 }  // extern "C"
+
+#ifdef HRF_FFN_PROFILE
+// debug build only: phase cycle counters of mixffn_tcd_kernel (see mixffn_tcd.cuh)
+extern "C" int hrf_debug_ffn_prof(unsigned long long* out, int n, int reset) {
+  using namespace hrf;
+  if (out) HRF_CUDA(cudaMemcpyFromSymbol(out, g_ffn_prof, sizeof(unsigned long long) * n));
+  if (reset) {
+    static unsigned long long zeros[1024 * 16];
+    HRF_CUDA(cudaMemcpyToSymbol(g_ffn_prof, zeros, sizeof(zeros)));
+  }
+  return HRF_OK;
+}
+#endif

@@ -41,11 +41,15 @@ struct FfnLayout {
     o = round_up(o, 4);
     o_tc_w1 = o; o += tc_nchunk * 80 * tc_KC / 2;
     o_tc_w2 = o; o += tc_nchunk * tc_NOUT * 80 / 2;
+    // depthwise 3x3 as tensor-core work: per chunk, per 16-channel column group s (5), ten
+    // [16 x 16] bf16 B tiles: taps 0..8 = diag(wd[tap][16s..16s+15]), tile 9 = the bias tile
+    // (row k = 8 holds bd[16s..], it multiplies the constant-1 column 72 of the activations)
+    o_tc_dg = o; o += tc_nchunk * 50 * 256 / 2;
     total = o;
     ldx = stride4odd(Cp);
     ldh = stride4odd(HC);
   }
-  int tc_KC, tc_NOUT, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2;
+  int tc_KC, tc_NOUT, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2, o_tc_dg;
 };
 
 constexpr int kFfnThreads = 256;

@@ -58,6 +58,9 @@ struct FfnTc {
   // H2 = fc2 A operand: NTOK live rows; the M=128 MMA also reads (and ignores) the rows up to
   // 127, which alias the next chunk / the tables behind the tile
   static constexpr int H2R = (NTOK + 7) / 8 * 8;                         // 88 | 128
+  // depthwise conv units: SH vertically adjacent outputs x 4 channels per thread
+  static constexpr int SH = SMALL ? 3 : 4, NSTRIP = TH / SH;
+  static_assert(TH % SH == 0, "tile height must split into strips");
   static constexpr int H2_B = 9 * H2R * 16 + 128 * 16;
   // shared-memory map (bytes)
   static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
@@ -78,20 +81,38 @@ struct FfnTc {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-// GELU for the bf16 mode: 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with the coefficients fitted
-// to the exact erf form (max abs error 2.5e-5, tools/fit_gelu.py) on the hardware tanh unit
-// (MUFU.TANH, relative error 2^-11): 8 instructions and one SFU op per evaluation instead of
-// ~17 / two for an erf evaluation; the total error (<= 2.5e-4 |x|) stays an order of magnitude
-// below the bf16 rounding of the value it produces.  x^2 is clamped at 64, beyond which the
-// result has saturated to x or 0 and the quartic would change sign.
+// GELU for the bf16 mode: 0.5 x (1 + tanh(x (a + b x^2))), a / b the minimax fit to the exact
+// erf form (max abs error 2.7e-4, tools/fit_gelu.py; the bf16 rounding of the value it
+// produces is 4e-3 at the |x| ~ 3 where that maximum sits) on the hardware tanh unit
+// (MUFU.TANH).  b > 0 keeps the argument monotone, so no clamp is needed, and the four
+// multiply-adds are issued as packed fp32x2 instructions (FMUL2 / FFMA2, sm_100): 7
+// instructions per PAIR of values instead of ~17 per value for an erf evaluation.
+constexpr float kGeluA = 0.80015708f, kGeluB = 0.03470089f;
+__device__ __forceinline__ float2 gelu_as2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 w = __ffma2_rn(x2, make_float2(kGeluB, kGeluB), make_float2(kGeluA, kGeluA));
+  const float2 a = __fmul2_rn(w, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
 __device__ __forceinline__ float gelu_as(float x) {
-  const float x2 = fminf(x * x, 64.0f);
-  float w = fmaf(x2, -3.51516792e-4f, 0.0370056460f);
-  w = fmaf(w, x2, 0.797507884f);
+  const float w = fmaf(x * x, kGeluB, kGeluA);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(w * x));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+// in place on 8 values
+__device__ __forceinline__ void gelu8(float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float2 g = gelu_as2(make_float2(v[j], v[j + 1]));
+    v[j] = g.x;
+    v[j + 1] = g.y;
+  }
 }
 
 // Warp w reads TMEM lanes 32*(w%4).. (its quadrant q) and belongs to group gq = w/4.
@@ -108,7 +129,7 @@ mixffn_tc_kernel(FfnParams p) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int gq = warp >> 2, q = warp & 3;          // work group, TMEM quadrant
   const int row = q * 32 + lane;                   // TMEM lane == row of the M=128 tiles
   const int cg = blockIdx.x % NG;                  // chunk group of this CTA
@@ -137,8 +158,11 @@ mixffn_tc_kernel(FfnParams p) {
     // (its 10th chunk, channels 72..79, stays zero)
     uint4* z = reinterpret_cast<uint4*>(sm + K::o_xn);
     for (int e = tid; e < NMT * K::XT / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
+    // H2: zero; its 10th chunk (the K padding, channels 72..79) holds the constant 1 in
+    // channel 72 that multiplies the b2 row of the W2 tile
     z = reinterpret_cast<uint4*>(sm + K::o_h2);
-    for (int e = tid; e < K::H2_B / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < K::H2_B / 16; e += NT)
+      z[e] = (e >= 9 * K::H2R && e < 10 * K::H2R) ? make_uint4(0x00003F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   if (tid == 0) {
@@ -216,11 +240,17 @@ mixffn_tc_kernel(FfnParams p) {
     const int oh = ty0 + row / K::TW, ow = tx0 + row % K::TW;
     const bool o_in = row < K::NTOK && oh < p.H && ow < p.W;
     const size_t o_tok = o_in ? (size_t)(b * p.H + oh) * p.W + ow : 0;
-    uint32_t rres[4] = {0u, 0u, 0u, 0u};           // residual of epilogue-2 unit cc = gq
-    if (!K::SPLIT && o_in && gq * 8 < C) {
+    // residual slices of this thread's epilogue-2 units cc = gq + u * NGQ
+    constexpr int NU2 = K::SPLIT ? 1 : ((C + 7) / 8 + NGQ - 1) / NGQ;
+    uint32_t rres[NU2][4];
+    if constexpr (!K::SPLIT) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (gq * 8 + 2 * j < C) rres[j] = __ldg(reinterpret_cast<const uint32_t*>(x + o_tok * C + gq * 8) + j);
+      for (int u = 0; u < NU2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = (gq + u * NGQ) * 8 + 2 * j;
+          rres[u][j] = (o_in && c0 < C) ? __ldg(reinterpret_cast<const uint32_t*>(x + o_tok * C + c0)) : 0u;
+        }
     }
 
 #pragma unroll 1
@@ -229,7 +259,7 @@ mixffn_tc_kernel(FfnParams p) {
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t id1 = idesc_bf16(128, N1, false, false);
         const uint32_t w1c = a_w1 + c * (N1 * KC * 2);
@@ -256,15 +286,17 @@ mixffn_tc_kernel(FfnParams p) {
         const int t = mt * 128 + row;                 // halo token
         if (t < K::NHALO) {
           if constexpr (K::BIAS_MMA) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_as(v[j]);
+            gelu8(v);
           } else {
             const bool in = sIn[t] != 0;
             const float4 ba = *reinterpret_cast<const float4*>(fb + ch * 8);
             const float4 bb = *reinterpret_cast<const float4*>(fb + ch * 8 + 4);
             const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = in ? gelu_as(v[j] + bv[j]) : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] += bv[j];
+            gelu8(v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = in ? v[j] : 0.f;
           }
           if constexpr (K::H1F32) {
             float4* h1 = reinterpret_cast<float4*>(sm + K::o_h1);
@@ -278,8 +310,9 @@ mixffn_tc_kernel(FfnParams p) {
       tc_fence_before();
       __syncthreads();
 
-      // ---- depthwise 3x3 + GELU: unit = (output token, 8-channel chunk), dealt linearly ---
-      {
+      // ---- depthwise 3x3 + GELU -> H2 --------------------------------------------------
+      if constexpr (K::H1F32) {
+        // fp32 H1: unit = (output token, 8-channel chunk), dealt linearly
         const float* wd = fb + 80;
         const float* bd = fb + 800;
 #pragma unroll 1
@@ -297,28 +330,70 @@ mixffn_tc_kernel(FfnParams p) {
               const float* wt = wd + (dy * 3 + dx) * 80 + ch * 8;
               const float4 wa = *reinterpret_cast<const float4*>(wt);
               const float4 wb = *reinterpret_cast<const float4*>(wt + 4);
-              if constexpr (K::H1F32) {
-                const float4* h1 = reinterpret_cast<const float4*>(sm + K::o_h1);
-                const float4 fa = h1[(2 * ch) * K::H1R + tt], fb4 = h1[(2 * ch + 1) * K::H1R + tt];
-                acc[0] = fmaf(fa.x, wa.x, acc[0]); acc[1] = fmaf(fa.y, wa.y, acc[1]);
-                acc[2] = fmaf(fa.z, wa.z, acc[2]); acc[3] = fmaf(fa.w, wa.w, acc[3]);
-                acc[4] = fmaf(fb4.x, wb.x, acc[4]); acc[5] = fmaf(fb4.y, wb.y, acc[5]);
-                acc[6] = fmaf(fb4.z, wb.z, acc[6]); acc[7] = fmaf(fb4.w, wb.w, acc[7]);
-              } else {
-                const uint4 u = *reinterpret_cast<const uint4*>(sm + K::o_h1 + (size_t)ch * (K::H1R * 16) + tt * 16);
-                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+              const float4* h1 = reinterpret_cast<const float4*>(sm + K::o_h1);
+              const float4 fa = h1[(2 * ch) * K::H1R + tt], fb4 = h1[(2 * ch + 1) * K::H1R + tt];
+              acc[0] = fmaf(fa.x, wa.x, acc[0]); acc[1] = fmaf(fa.y, wa.y, acc[1]);
+              acc[2] = fmaf(fa.z, wa.z, acc[2]); acc[3] = fmaf(fa.w, wa.w, acc[3]);
+              acc[4] = fmaf(fb4.x, wb.x, acc[4]); acc[5] = fmaf(fb4.y, wb.y, acc[5]);
+              acc[6] = fmaf(fb4.z, wb.z, acc[6]); acc[7] = fmaf(fb4.w, wb.w, acc[7]);
+            }
+          gelu8(acc);
+          st_chunk(sm + K::o_h2, o, ch, K::H2R, acc);
+        }
+      } else {
+        // bf16 H1: unit = (strip of SH vertically adjacent outputs, 4 channels).  Every halo
+        // value is loaded and unpacked once per column offset and feeds up to three outputs;
+        // the multiply-adds are packed fp32x2 (FFMA2).  Lane pairs cover the two halves of one
+        // token's 16-byte chunk, so a warp's 8-byte accesses are contiguous.
+        constexpr int SH = K::SH;
+        constexpr int NUNIT = 9 * K::NSTRIP * K::TW * 2;
+        const float* wd = fb + 80;
+        const float* bd = fb + 800;
+#pragma unroll 1
+        for (int id = tid; id < NUNIT; id += NT) {
+          const int hf = id & 1;
+          int r = id >> 1;
+          const int ox = r % K::TW;
+          r /= K::TW;
+          const int st = r % K::NSTRIP, ch = r / K::NSTRIP;
+          const int oy0 = st * SH, c4 = ch * 8 + hf * 4;
+          const float4 bq = *reinterpret_cast<const float4*>(bd + c4);
+          float2 acc[SH][2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
-                  acc[2 * j] = fmaf(f.x, wv[2 * j], acc[2 * j]);
-                  acc[2 * j + 1] = fmaf(f.y, wv[2 * j + 1], acc[2 * j + 1]);
-                }
-              }
+          for (int o = 0; o < SH; ++o) {
+            acc[o][0] = make_float2(bq.x, bq.y);
+            acc[o][1] = make_float2(bq.z, bq.w);
+          }
+          const unsigned char* hp = sm + K::o_h1 + ((size_t)ch * K::H1R + oy0 * K::HW + ox) * 16 + hf * 8;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            float2 f[SH + 2][2];
+#pragma unroll
+            for (int rr = 0; rr < SH + 2; ++rr) {
+              const uint2 u = *reinterpret_cast<const uint2*>(hp + (rr * K::HW + dx) * 16);
+              f[rr][0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+              f[rr][1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
             }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = gelu_as(acc[j]);
-          st_chunk(sm + K::o_h2, o, ch, K::H2R, acc);
+            for (int dy = 0; dy < 3; ++dy) {
+              const float4 w = *reinterpret_cast<const float4*>(wd + (dy * 3 + dx) * 80 + c4);
+              const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+#pragma unroll
+              for (int o = 0; o < SH; ++o) {
+                acc[o][0] = __ffma2_rn(f[o + dy][0], w0, acc[o][0]);
+                acc[o][1] = __ffma2_rn(f[o + dy][1], w1, acc[o][1]);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < SH; ++o) {
+            const float2 g0 = gelu_as2(acc[o][0]), g1 = gelu_as2(acc[o][1]);
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x, g0.y), p1 = __floats2bfloat162_rn(g1.x, g1.y);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&p0);
+            u.y = *reinterpret_cast<const uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(sm + K::o_h2 + ((size_t)ch * K::H2R + (oy0 + o) * K::TW + ox) * 16 + hf * 8) = u;
+          }
         }
       }
 
@@ -326,7 +401,7 @@ mixffn_tc_kernel(FfnParams p) {
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t id2 = idesc_bf16(128, NOUT, false, false);
         const uint32_t w2c = a_w2 + c * (NOUT * N1 * 2);
@@ -342,33 +417,34 @@ mixffn_tc_kernel(FfnParams p) {
     }
 
     // ---- epilogue 2: unit = (output token, 8-channel chunk of the C outputs) ----------
+    // (b2 came through the MMA: row 72 of the first chunk's W2 tile x the constant-1 column)
     {
-      const bool in = o_in;
-      const size_t tok = o_tok;
-      const float* b2 = sF + CPG * 880;
-#pragma unroll 1
-      for (int cc = gq; cc * 8 < C; cc += NGQ) {      // warp-uniform trip count
-        float y[8];
-        tmem_ld8(trow + K::Y_COL + cc * 8, y);
-        tmem_ld_wait();
-        if (!in) continue;
-        if constexpr (K::SPLIT) {      // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
-          const size_t n_tok = (size_t)p.B * p.H * p.W;
-          float* wrow = static_cast<float*>(p.ws) + ((size_t)cg * n_tok + tok) * C + cc * 8;
-          *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
-        } else {                       // + b2, GELU, + residual; rows are only 4-byte aligned
-          const uint32_t* xr4 = reinterpret_cast<const uint32_t*>(x + tok * C + cc * 8);
-          uint32_t* orow = reinterpret_cast<uint32_t*>(out + tok * C + cc * 8);
+      constexpr int NCC = (C + 7) / 8;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (cc * 8 + 2 * j < C) {
-              const uint32_t u = (cc == gq) ? rres[j] : __ldg(xr4 + j);
-              const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-              const float a0 = r.x + gelu_as(y[2 * j] + b2[cc * 8 + 2 * j]);
-              const float a1 = r.y + gelu_as(y[2 * j + 1] + b2[cc * 8 + 2 * j + 1]);
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
-              orow[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      for (int u = 0; u < (NCC + NGQ - 1) / NGQ; ++u) {
+        const int cc = gq + u * NGQ;
+        if (cc < NCC) {                               // warp-uniform
+          float y[8];
+          tmem_ld8(trow + K::Y_COL + cc * 8, y);
+          tmem_ld_wait();
+          if (o_in) {
+            if constexpr (K::SPLIT) {  // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
+              const size_t n_tok = (size_t)p.B * p.H * p.W;
+              float* wrow = static_cast<float*>(p.ws) + ((size_t)cg * n_tok + o_tok) * C + cc * 8;
+              *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            } else {                   // GELU, + residual; rows are only 4-byte aligned
+              gelu8(y);
+              uint32_t* orow = reinterpret_cast<uint32_t*>(out + o_tok * C + cc * 8);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (cc * 8 + 2 * j < C) {
+                  const uint32_t rw = rres[K::SPLIT ? 0 : u][j];
+                  const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw));
+                  const __nv_bfloat162 hh = __floats2bfloat162_rn(r.x + y[2 * j], r.y + y[2 * j + 1]);
+                  orow[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+              }
             }
           }
         }
@@ -402,7 +478,7 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
     const int c0 = (int)(e0 % C);
     float acc[8], r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = __ldg(b2 + c0 + j);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;     // b2 is part of the first partial (MMA bias row)
     for (int gi = 0; gi < ng; ++gi) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0));
       const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0 + 4));
@@ -411,7 +487,9 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
     }
     load_row_bf16<8>(x + e0, r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = r[j] + gelu_as(acc[j]);
+    gelu8(acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += r[j];
     store_row_bf16<8>(out + e0, acc);
   }
 }

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
   __shared__ float sBias[COUT];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = warp_idx_uniform();
   const StemLayout L(p.Cin, COUT);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.blob + L.o_w);
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t id = idesc_bf16(128, COUT, false, false);
       mma_bf16(tmem, desc_kmajor(a_a, 128, 0), desc_kmajor(a_w, COUT, 0), id, false);

@@ -72,6 +72,24 @@ __device__ __forceinline__ void cta_wait(uint64_t* bar, uint32_t parity) {
   __syncthreads();
 }
 
+// ---- single-thread issue -----------------------------------------------------------
+// tcgen05.mma / commit are issued by one thread.  Guarding them with `threadIdx.x == 0` makes
+// the branch thread-divergent for the compiler, which then wraps every UTCHMMA in an
+// ELECT/BRA loop over the active lanes (~65 cycles per MMA).  A warp-uniform warp index plus
+// elect.sync keeps the region uniform: one UTCHMMA, no loop.
+__device__ __forceinline__ int warp_idx_uniform() {
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+__device__ __forceinline__ bool elect_one() {     // all 32 lanes of the warp must be converged
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- fences --------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() {

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t valid_bits[4];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int g = tid >> 6, i = tid & 63;            // window of the pair, slot in the window
   const int hg = blockIdx.x % NG;                  // head group of this CTA
   const int h0 = hg * HG;                          // first (absolute) head
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     __syncthreads();
 
     // ---- q / k / v projections of this head group --------------------------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idq = idesc_bf16(128, NQG, false, false);
       const uint32_t a_kv = CROSS ? a_zn : a_xn;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t ids = idesc_bf16(128, 128, false, false);
 #pragma unroll
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t ido = idesc_bf16(128, HDP, false, true);
 #pragma unroll
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idy = idesc_bf16(128, NOUT, false, false);
 #pragma unroll

@@ -127,6 +127,7 @@ class FfnLayout:
         o = _ru(o + nch * 880 + (KC if nch else 0), 4)
         self.tc_w1 = o; o += nch * 80 * KC // 2
         self.tc_w2 = o; o += nch * KC * 80 // 2
+        self.tc_dg = o; o += nch * 50 * 256 // 2
         self.tc = dict(KC=KC, NOUT=KC, nchunk=nch)
         self.total = o
 

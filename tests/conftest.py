@@ -19,3 +19,17 @@ def built_lib():
     from hrfuser_b200 import _lib, build
     build.build()
     return _lib.load()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """HRF_PARITY_LOG=<file>: append the measured parity errors of this run (worst first)."""
+    path = os.environ.get('HRF_PARITY_LOG')
+    if not path:
+        return
+    import json
+    from helpers import PARITY_LOG
+    if PARITY_LOG:
+        rows = sorted(PARITY_LOG, key=lambda r: -r[2])
+        with open(path, 'a') as f:
+            for what, mode, e, out in rows:
+                f.write(json.dumps(dict(what=what, mode=mode, err=e, frac_out=out)) + '\n')

@@ -22,6 +22,9 @@ def rms(t):
     return float(t.double().pow(2).mean().sqrt())
 
 
+PARITY_LOG = []      # (what, mode, norm-wise error, fraction of elements out of tolerance)
+
+
 def assert_parity(got, ref, mode, what=''):
     """fp32: rtol 1e-3 (north_star) -- checked as norm-wise <= 2e-5 *and*
     elementwise allclose(rtol=1e-3, atol=1e-3*rms(ref)).
@@ -34,11 +37,13 @@ def assert_parity(got, ref, mode, what=''):
     r = max(rms(ref), 1e-12)
     if mode == 'fp32':
         ok = torch.isclose(got, ref, rtol=1e-3, atol=1e-3 * r)
+        PARITY_LOG.append((str(what), mode, e, float((~ok).float().mean())))
         assert e <= 2e-5 and bool(ok.all()), \
             f'{what}: fp32 parity failed: norm-wise {e:.3e}, {float((~ok).float().mean()):.2%} elements out'
     else:
         ok = torch.isclose(got, ref, rtol=2e-2, atol=2e-2 * r)
         frac = float(ok.float().mean())
+        PARITY_LOG.append((str(what), mode, e, 1 - frac))
         assert e <= 2e-2 and frac >= 0.99, \
             f'{what}: bf16 parity failed: norm-wise {e:.3e}, {1 - frac:.2%} elements out'
     return e

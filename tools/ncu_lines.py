@@ -1,7 +1,10 @@
 """Join an ncu SASS source page (per-instruction execution counts, program order) with
 nvdisasm line info of the same cubin -> executed warp instructions per CUDA source line.
 
-    python tools/ncu_lines.py report.ncu-rep <mangled kernel name> [top N]
+    python tools/ncu_lines.py report.ncu-rep <mangled kernel name> [top N] [column]
+
+`column` defaults to "Instructions Executed"; "# Samples" gives the warp-sampling (time)
+attribution per source line instead.
 """
 import collections
 import csv
@@ -13,6 +16,7 @@ import tempfile
 
 rep, mangled = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+column = sys.argv[4] if len(sys.argv) > 4 else 'Instructions Executed'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, 'hrfuser_b200', 'libhrfuser_b200.so')
 tmp = tempfile.mkdtemp()
@@ -43,7 +47,7 @@ for r in rows[hi + 1:]:
     if len(r) < len(h) or r[0] == 'Address':
         break
     try:
-        counts.append(int(r[col['Instructions Executed']]))
+        counts.append(int(r[col[column]]))
     except ValueError:
         break
 print(len(lines), 'SASS instructions with line info;', len(counts), 'in the profile')
