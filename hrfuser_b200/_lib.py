@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 HRF_F32, HRF_BF16 = 0, 1
 MAX_FUSE_TERMS = 4
@@ -61,6 +61,7 @@ SIGNATURES = {
     'hrf_last_error': (C.c_char_p, []),
     'hrf_device_check': (C.c_int, []),
     'hrf_launch_count': (C.c_ulonglong, []),
+    'hrf_set_pdl': (C.c_int, [C.c_int32]),
     'hrf_attn_blob_floats': (C.c_size_t, [C.POINTER(AttnDesc)]),
     'hrf_attn_pack': (C.c_int, [C.POINTER(AttnDesc)] + [_F] * 13 + [_F]),
     'hrf_attn_workspace_bytes': (C.c_size_t, [C.POINTER(AttnDesc)]),

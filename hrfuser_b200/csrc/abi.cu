@@ -53,6 +53,20 @@ bool tc_disabled() {
   }();
   return off;
 }
+// Programmatic dependent launch: off unless HRF_PDL=1 or hrf_set_pdl(1).  Measured on B200: a
+// single lsa -> mixffn chain in a graph gains 5 %, but the engine's multi-stream graph loses
+// ~2 % (early-launched dependents hold SM slots and TMEM columns that kernels of the other
+// streams could use), so the engine leaves it off.
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("HRF_PDL");
+    v = (e && std::atoi(e) != 0) ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // round-to-nearest-even fp32 -> bf16 bits (finite inputs)
@@ -95,6 +109,12 @@ extern "C" {
 
 int hrf_abi_version(void) { return HRF_ABI_VERSION; }
 const char* hrf_last_error(void) { return g_err; }
+int hrf_set_pdl(int32_t enable) {
+  const int prev = hrf::pdl_enabled() ? 1 : 0;
+  hrf::g_pdl.store(enable ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
 unsigned long long hrf_launch_count(void) { return g_launches.load(); }
 
 int hrf_device_check(void) {
@@ -516,14 +536,14 @@ int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, co
 
 }  // extern "C"
 
-#ifdef HRF_FFN_PROFILE
-// debug build only: phase cycle counters of mixffn_tcd_kernel (see mixffn_tcd.cuh)
-extern "C" int hrf_debug_ffn_prof(unsigned long long* out, int n, int reset) {
+#ifdef HRF_KERNEL_PROFILE
+// instrumented build only: phase cycle counters (see common.cuh)
+extern "C" int hrf_debug_prof(unsigned long long* out, int n, int reset) {
   using namespace hrf;
-  if (out) HRF_CUDA(cudaMemcpyFromSymbol(out, g_ffn_prof, sizeof(unsigned long long) * n));
+  if (out) HRF_CUDA(cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * n));
   if (reset) {
-    static unsigned long long zeros[1024 * 16];
-    HRF_CUDA(cudaMemcpyToSymbol(g_ffn_prof, zeros, sizeof(zeros)));
+    static unsigned long long zeros[2048 * 16];
+    HRF_CUDA(cudaMemcpyToSymbol(g_prof, zeros, sizeof(zeros)));
   }
   return HRF_OK;
 }

@@ -8,6 +8,27 @@
 
 namespace hrf {
 
+// -DHRF_KERNEL_PROFILE (tools/gpu_phases.sh): thread 0 of every CTA accumulates clock64 deltas
+// per phase of a kernel's tile loop into g_prof[cta][16] (slot 15 = tiles processed), read back
+// by hrf_debug_prof().  Compiled out of the product library.
+#ifdef HRF_KERNEL_PROFILE
+__device__ unsigned long long g_prof[2048 * 16];
+#define HRF_PROF_DECL long long pt_ = clock64();
+#define HRF_PROF(k)                                                       \
+  if (threadIdx.x == 0) {                                                 \
+    const long long now_ = clock64();                                     \
+    g_prof[(blockIdx.x & 2047) * 16 + (k)] += (unsigned long long)(now_ - pt_); \
+    pt_ = now_;                                                           \
+  }
+#define HRF_PROF_TILE \
+  if (threadIdx.x == 0) g_prof[(blockIdx.x & 2047) * 16 + 15] += 1;
+#else
+#define HRF_PROF_DECL
+#define HRF_PROF(k)
+#define HRF_PROF_TILE
+#endif
+
+
 constexpr int kWarp = 32;
 
 // ---- error plumbing (thread-local message, never throws) --------------------
@@ -15,9 +36,40 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 bool tc_disabled();
+bool pdl_enabled();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (kept out of
 // CUDA-graph capture after the first, warm-up, call)
 cudaError_t ensure_smem(const void* kern, size_t bytes);
+
+// ---- programmatic dependent launch ---------------------------------------------------
+// Every hot kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it
+// may start while its predecessor in the stream is still draining, runs its prologue (weights
+// -> shared memory, TMEM allocation, barrier init: nothing that depends on the predecessor),
+// and only then executes griddepcontrol.wait, which returns once the predecessor has completed
+// and flushed its memory.  launch_dependents is issued first thing, so the successor's CTAs
+// fill SM slots as soon as this grid's CTAs retire.  Inside a CUDA graph the edges become
+// programmatic dependencies.  A kernel launched this way MUST call pdl_wait() before it touches
+// anything an earlier kernel wrote.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define HRF_REQUIRE(cond, code, ...)          \
   do {                                        \

@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
   T* out = static_cast<T*>(p.out);
   const int t0 = blockIdx.x * TOK;
   const int m = min(TOK, p.ntok - t0);
+  pdl_launch_dependents();
+  const float* Wt = stage_weights(p.blob + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
+  pdl_wait();
   // stage the token tile (contiguous in memory) as fp32, zero-padded to lda
   const int hp = L.lda / 2;
   for (int e = threadIdx.x; e < TOK * hp; e += blockDim.x) {
@@ -70,7 +73,6 @@ __global__ void __launch_bounds__(kPwThreads) pw_kernel(PwParams p) {
     if (r < m && c < p.Cin) v = Pair<T>::ld(x + (size_t)(t0 + r) * p.Cin + c);
     *reinterpret_cast<float2*>(smem + r * L.lda + c) = v;
   }
-  const float* Wt = stage_weights(p.blob + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
   __syncthreads();
   const float* bias = p.blob + L.o_b;
   const int relu = p.relu, Cout = p.Cout;
@@ -90,7 +92,7 @@ static int launch_pw_tok(PwParams p, cudaStream_t stream) {
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "pw: Cin=%d too wide", p.Cin);
   auto kern = (p.Cout % 4 == 0) ? pw_kernel<T, 4, TOK> : pw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
-  kern<<<ceil_div(p.ntok, TOK), kPwThreads, smem, stream>>>(p);
+  HRF_CUDA(launch_pdl(kern, dim3(ceil_div(p.ntok, TOK)), dim3(kPwThreads), smem, stream, p));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
@@ -133,6 +135,10 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
   const int m = min(TOK, ntok - t0);
   const float* wd = p.blob + D.o_wd;
   const float* bd = p.blob + D.o_bd;
+  const float* pw = p.blob + D.o_pw;
+  pdl_launch_dependents();
+  const float* Wt = stage_weights(pw + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
+  pdl_wait();
   const int hp = L.lda / 2;
   for (int e = threadIdx.x; e < TOK * hp; e += blockDim.x) {
     const int r = e / hp, c = (e - r * hp) * 2;
@@ -160,8 +166,6 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
     }
     *reinterpret_cast<float2*>(smem + r * L.lda + c) = s;
   }
-  const float* pw = p.blob + D.o_pw;
-  const float* Wt = stage_weights(pw + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
   __syncthreads();
   const float* bias = pw + L.o_b;
   const int relu = p.relu, Cout = p.Cout;
@@ -181,7 +185,7 @@ static int launch_dwpw_tok(DwPwParams p, cudaStream_t stream) {
   HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "dwpw: Cin=%d too wide", p.Cin);
   auto kern = (p.Cout % 4 == 0) ? dwpw_kernel<T, 4, TOK> : dwpw_kernel<T, 2, TOK>;
   HRF_CUDA(ensure_smem((const void*)kern, smem));
-  kern<<<ceil_div(p.B * p.Ho * p.Wo, TOK), kPwThreads, smem, stream>>>(p);
+  HRF_CUDA(launch_pdl(kern, dim3(ceil_div(p.B * p.Ho * p.Wo, TOK)), dim3(kPwThreads), smem, stream, p));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
@@ -214,6 +218,8 @@ struct FuseParams {
 // thread = (token, channel pair); 32-bit index math (tensors are < 2^31 elements)
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int hc = p.C / 2;
   const int total = p.B * p.H * p.W * hc;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -261,7 +267,7 @@ static int launch_fuse(const FuseParams& p, cudaStream_t stream) {
   HRF_REQUIRE(p.C % 2 == 0 && total * 2 < ((size_t)1 << 31), HRF_EUNSUPPORTED,
               "fuse_sum: C=%d must be even and the tensor below 2^31 elements", p.C);
   const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  fuse_sum_kernel<T><<<grid, 256, 0, stream>>>(p);
+  HRF_CUDA(launch_pdl(fuse_sum_kernel<T>, dim3(grid), dim3(256), 0, stream, p));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;

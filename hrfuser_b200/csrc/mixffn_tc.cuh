@@ -2,17 +2,19 @@
 //
 //   out = x + GELU(BN3(W2 * GELU(BN2(dw3x3(GELU(BN1(W1*LN(x)+b1)))+bd)) + b2))
 //
-// One CTA (256 threads) owns an 8 x 16 tile of output tokens per iteration:
-//   LN prologue   the 10 x 18 halo (180 tokens) is LayerNormed one token per thread
-//                 and written as two bf16 M=128 operand tiles
+// One CTA (256 threads) owns a 6 x 14 tile of output tokens per iteration:
+//   LN prologue   the 8 x 16 halo (128 tokens) is LayerNormed (a lane pair per token for
+//                 C <= 36) and written as one bf16 M=128 operand tile with a constant-1
+//                 column that carries b1 through the MMA (all-zero rows outside the image)
 //   per chunk of 72 hidden channels (hidden = 4C = 72 * nchunk):
-//     fc1 (UMMA)  2 x [128 x KC] x W1c^T -> TMEM (N = 80)
-//     epilogue    + b1, GELU, zero outside the image (that is what the reference's
-//                 zero-padded depthwise conv sees), bf16 -> H1 [9 chunks][180 tok][8]
-//     dw 3x3      SIMT on H1 (16-byte shared loads, fp32 accumulate), + bd, GELU,
-//                 bf16 -> H2 operand tile [128 x 80]
-//     fc2 (UMMA)  H2 x W2c^T accumulated over the chunks in TMEM (N = NOUT)
-//   epilogue      + b2, GELU, + residual, bf16 -> global
+//     fc1 (UMMA)  [128 x KC] x W1c^T -> TMEM (N = 80)
+//     epilogue    GELU (zero outside the image: that is what the reference's zero-padded
+//                 depthwise conv sees), bf16 -> H1 [9 chunks][128 tok][8]
+//     dw 3x3      CUDA cores on H1: strips of 3 outputs x 4 channels per thread, packed
+//                 fp32x2 FMAs, + bd, GELU, bf16 -> H2 operand tile [88 x 80]
+//     fc2 (UMMA)  H2 x W2c^T accumulated over the chunks in TMEM (N = NOUT); b2 rides on
+//                 the constant-1 column 72 of H2
+//   epilogue      GELU, + residual, bf16 -> global
 // The 4C-wide hidden activation never leaves the SM.  BN is folded (eval mode).
 #pragma once
 #include <cstdlib>
@@ -27,48 +29,51 @@ namespace hrf {
 // CPG = hidden chunks handled by one CTA.  CPG == NCH: the CTA finishes the block.
 // CPG < NCH (C = 72, 144: few tokens, many chunks): NCH/CPG CTAs share a token tile,
 // each writes its fp32 partial fc2 product to a workspace and `ffn_reduce_kernel`
-// applies b2 / GELU / residual to the fixed-order sum.
+// applies GELU / residual to the fixed-order sum.
 //
-// Two tile geometries:
-//   C = 18 (the 96x160 branch, 77 % of all FFN tokens): 6 x 14 outputs, 8 x 16 = 128 halo
-//       tokens = exactly one M=128 fc1 tile, 256 threads, 128 TMEM columns, ~55 KB smem
-//       -> four CTAs (four independent barrier domains) per SM;
-//   otherwise: 8 x 16 outputs, 10 x 18 = 180 halo tokens in two M tiles, 512 threads.
+// Tile geometry: 6 x 14 outputs inside an 8 x 16 = 128 token halo = exactly one M=128 fc1
+// tile, 256 threads.  Small tiles keep the per-tile dependency chain short and give the
+// low-resolution branches (1 920 .. 30 720 tokens) enough CTAs to cover the 148 SMs; C = 18
+// needs 128 TMEM columns and 47 KB of shared memory -> four CTAs (four independent barrier
+// domains) per SM, the wider variants two.
 template <int C, int CPG>
 struct FfnTc {
   static constexpr int HID = 4 * C, NCH = HID / 72, NG = NCH / CPG;
   static constexpr bool SPLIT = CPG < NCH, BIGC = C > 40;
   static_assert(HID % 72 == 0 && NCH % CPG == 0, "hidden must split into 72-channel chunks");
   static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
-  static constexpr bool SMALL = (C == 18);
-  static constexpr int TH = SMALL ? 6 : 8, TW = SMALL ? 14 : 16;
-  static constexpr int HH = TH + 2, HW = TW + 2, NHALO = HH * HW;      // 128 | 180
-  static constexpr int NTOK = TH * TW;                                  // 84 | 128 outputs
-  static constexpr int NMT = (NHALO + 127) / 128;                       // fc1 M tiles: 1 | 2
-  static constexpr int NT = SMALL ? 256 : 512, NGQ = NT / 128;          // threads, groups per quadrant
-  static constexpr int XT = 128 * KC * 2;            // one XN operand tile
-  static constexpr int H1R = (NHALO + 7) / 8 * 8;    // rows per 16-byte column group of H1
+  static constexpr int TH = 6, TW = 14;
+  static constexpr int HH = TH + 2, HW = TW + 2, NHALO = HH * HW;      // 128
+  static constexpr int NTOK = TH * TW;                                  // 84 outputs
+  static constexpr int NMT = 1;                                         // fc1 M tiles
+  static_assert(NHALO == 128, "the halo is one M=128 operand tile");
+  static constexpr int NT = 256, NGQ = NT / 128;     // threads, groups per TMEM quadrant
+  static constexpr int XT = 128 * KC * 2;            // the LN(x) operand tile
+  static constexpr int H1R = NHALO;                  // rows per 16-byte column group of H1
   // fc1 bias through the MMA: XN column C holds 1 for in-image tokens and W1 row C holds b1, so
   // the epilogue needs neither a bias add nor the outside-the-image select (zero rows give
   // GELU(0) = 0).  Needs a spare K column (not C = 144).
   static constexpr bool BIAS_MMA = KC > C;
-  // H1 (GELU(fc1) on the halo) in fp32 where smem allows (C = 144), bf16 otherwise
-  static constexpr bool H1F32 = (C == 144);
-  static constexpr int H1_B = (H1F32 ? 18 : 9) * H1R * 16;
+  static constexpr int H1_B = 9 * H1R * 16;          // GELU(fc1) on the halo, bf16
   // H2 = fc2 A operand: NTOK live rows; the M=128 MMA also reads (and ignores) the rows up to
-  // 127, which alias the next chunk / the tables behind the tile
-  static constexpr int H2R = (NTOK + 7) / 8 * 8;                         // 88 | 128
+  // 127, which alias the next chunk / the bytes behind the tile
+  static constexpr int H2R = (NTOK + 7) / 8 * 8;     // 88
   // depthwise conv units: SH vertically adjacent outputs x 4 channels per thread
-  static constexpr int SH = SMALL ? 3 : 4, NSTRIP = TH / SH;
+  static constexpr int SH = 3, NSTRIP = TH / SH;
   static_assert(TH % SH == 0, "tile height must split into strips");
   static constexpr int H2_B = 9 * H2R * 16 + 128 * 16;
+  // With one chunk per CTA LN(x) is dead once fc1 has run: H1 | H2 reuse its bytes.
+  static constexpr bool XN_ALIAS = (CPG == 1);
+  static constexpr int ACT_B = XN_ALIAS ? (XT > H1_B + H2_B ? XT : H1_B + H2_B) : XT + H1_B + H2_B;
+  // ... in which case a wide LN(x) tile also overwrites the constant-1 column of H2
+  static constexpr bool REWRITE_ONE = XN_ALIAS && XT > H1_B + 9 * H2R * 16;
   // shared-memory map (bytes)
   static constexpr int o_w1 = 0;                               // CPG tiles [80 x KC]
   static constexpr int o_w2 = o_w1 + CPG * N1 * KC * 2;        // CPG tiles [NOUT x 80]
-  static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;      // NMT tiles
-  static constexpr int o_h1 = o_xn + NMT * XT;
+  static constexpr int o_xn = o_w2 + CPG * NOUT * N1 * 2;
+  static constexpr int o_h1 = XN_ALIAS ? o_xn : o_xn + XT;
   static constexpr int o_h2 = o_h1 + H1_B;
-  static constexpr int o_f32 = o_h2 + H2_B;                    // per chunk 880 floats, then b2[NOUT]
+  static constexpr int o_f32 = o_xn + ACT_B;                   // per chunk 880 floats, then b2[NOUT]
   static constexpr int o_ln = o_f32 + (CPG * 880 + NOUT) * 4;  // gamma[C4] beta[C4]
   static constexpr int C4 = (C + 3) / 4 * 4;
   static constexpr int o_in = o_ln + 2 * C4 * 4;               // inside flags [256] bytes
@@ -77,6 +82,7 @@ struct FfnTc {
   static constexpr int Y_COL = D_COLS;                         // fc2 accumulator
   static constexpr int TMEM_COLS = (D_COLS + NOUT <= 128) ? 128 : (D_COLS + NOUT <= 256) ? 256 : 512;
   static constexpr int CTAS_PER_SM = (SMEM + 1024) * 4 <= 227 * 1024 && TMEM_COLS <= 128 ? 4
+                                   : (SMEM + 1024) * 3 <= 227 * 1024 && TMEM_COLS <= 128 ? 3
                                    : (SMEM + 1024) * 2 <= 227 * 1024 && TMEM_COLS <= 256 ? 2 : 1;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -126,9 +132,11 @@ mixffn_tc_kernel(FfnParams p) {
   constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH, NG = K::NG;
   constexpr int NT = K::NT, NGQ = K::NGQ, NMT = K::NMT;
   extern __shared__ __align__(128) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
 
+  HRF_PROF_DECL
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int gq = warp >> 2, q = warp & 3;          // work group, TMEM quadrant
   const int row = q * 32 + lane;                   // TMEM lane == row of the M=128 tiles
@@ -140,35 +148,33 @@ mixffn_tc_kernel(FfnParams p) {
   unsigned char* sIn = sm + K::o_in;
 
   // ---- one-time setup ---------------------------------------------------------------
+  // The weight tiles and per-chunk tables (this group's chunks are contiguous in each blob
+  // section) arrive by bulk async copies that run behind the first tile's LN prologue.
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+    constexpr uint32_t b1 = CPG * N1 * KC * 2, b2 = CPG * NOUT * N1 * 2, b3 = CPG * 880 * 4, b4 = NOUT * 4;
+    mbar_expect_tx(&wbar, b1 + b2 + b3 + b4);
+    bulk_g2s(sm + K::o_w1, reinterpret_cast<const unsigned char*>(blob + L.o_tc_w1) + (size_t)cg * b1, b1, &wbar);
+    bulk_g2s(sm + K::o_w2, reinterpret_cast<const unsigned char*>(blob + L.o_tc_w2) + (size_t)cg * b2, b2, &wbar);
+    bulk_g2s(sF, blob + L.o_tc_f32 + (size_t)cg * CPG * 880, b3, &wbar);
+    bulk_g2s(sF + CPG * 880, blob + L.o_tc_f32 + NCH * 880, b4, &wbar);
+  }
   {
-    // this group's chunks are contiguous in each blob section
-    const uint4* s1 = reinterpret_cast<const uint4*>(blob + L.o_tc_w1) + (size_t)cg * CPG * (N1 * KC * 2 / 16);
-    const uint4* s2 = reinterpret_cast<const uint4*>(blob + L.o_tc_w2) + (size_t)cg * CPG * (NOUT * N1 * 2 / 16);
-    uint4* d1 = reinterpret_cast<uint4*>(sm + K::o_w1);
-    uint4* d2 = reinterpret_cast<uint4*>(sm + K::o_w2);
-    for (int e = tid; e < CPG * N1 * KC * 2 / 16; e += NT) d1[e] = __ldg(s1 + e);
-    for (int e = tid; e < CPG * NOUT * N1 * 2 / 16; e += NT) d2[e] = __ldg(s2 + e);
-    for (int e = tid; e < CPG * 880; e += NT) sF[e] = __ldg(blob + L.o_tc_f32 + cg * CPG * 880 + e);
-    for (int e = tid; e < NOUT; e += NT) sF[CPG * 880 + e] = __ldg(blob + L.o_tc_f32 + NCH * 880 + e);
     for (int e = tid; e < K::C4; e += NT) {
       sLn[e] = __ldg(blob + L.o_ln_w + e);
       sLn[K::C4 + e] = __ldg(blob + L.o_ln_b + e);
     }
-    // zero the XN tiles (dead rows of the last M tile are never written again) and H2
-    // (its 10th chunk, channels 72..79, stays zero)
-    uint4* z = reinterpret_cast<uint4*>(sm + K::o_xn);
-    for (int e = tid; e < NMT * K::XT / 16; e += NT) z[e] = make_uint4(0, 0, 0, 0);
+    // (every row and chunk of the LN(x) tile is rewritten per tile: no initialisation)
     // H2: zero; its 10th chunk (the K padding, channels 72..79) holds the constant 1 in
     // channel 72 that multiplies the b2 row of the W2 tile
-    z = reinterpret_cast<uint4*>(sm + K::o_h2);
+    uint4* z = reinterpret_cast<uint4*>(sm + K::o_h2);
     for (int e = tid; e < K::H2_B / 16; e += NT)
       z[e] = (e >= 9 * K::H2R && e < 10 * K::H2R) ? make_uint4(0x00003F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
+  bool w_ready = false;                            // bulk copies observed complete
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -187,56 +193,69 @@ mixffn_tc_kernel(FfnParams p) {
   // halo rows in this quadrant
   const int n_units = 9 * ((K::NHALO - q * 32 + 127) / 128);
 
-  // Software pipeline (C <= 40): halo token `tid` of the NEXT tile is requested while the
-  // current tile computes; the residual slice of the first epilogue-2 unit is requested
-  // at the top of the tile.  No thread waits on global memory with the CTA behind it.
+  // Software pipeline (C <= 40): the halo token of the NEXT tile is requested while the
+  // current tile computes; no thread waits on global memory with the CTA behind it.  There a
+  // PAIR of adjacent lanes normalises one halo token (ln_pair_to_tile); for wide C one thread
+  // streams the row.
   constexpr bool PIPE = !K::BIGC;
-  constexpr int NW = PIPE ? C / 2 : 1;
+  constexpr int NW = PIPE ? LnPair<PIPE ? C : 16>::NW : 1;
   const int tile_step = gridDim.x / NG;
-  // halo token of this thread in a given tile: global token index or -1 (outside / none)
+  const int ht = PIPE ? tid >> 1 : tid, half = tid & 1;     // halo token of this thread
+  // global token index of halo token `ht` in a given tile, or -1 (outside / none)
   auto halo_token = [&](int tile) -> int {
-    if (tile >= n_tiles || tid >= K::NHALO) return -1;
+    if (tile >= n_tiles || ht >= K::NHALO) return -1;
     int b, rem, ty, tx;
     p.d_tiles_xy.divmod(tile, b, rem);
     p.d_tiles_x.divmod(rem, ty, tx);
-    const int h = ty * K::TH - 1 + tid / K::HW;
-    const int w = tx * K::TW - 1 + tid % K::HW;
+    const int h = ty * K::TH - 1 + ht / K::HW;
+    const int w = tx * K::TW - 1 + ht % K::HW;
     return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
   };
+  pdl_wait();                                      // everything above only read the weight blob
   uint32_t xr[NW];
   int htok = halo_token(blockIdx.x / NG);
-  if (PIPE && htok >= 0) load_row_raw<C>(x + (size_t)htok * C, xr);
+  if constexpr (PIPE) {
+    if (htok >= 0) ln_pair_load<C>(x + (size_t)htok * C, half, xr);
+  }
 
+  HRF_PROF(14)                                     // setup
   for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
+    HRF_PROF_TILE
     int b, rem, ty0, tx0;
     p.d_tiles_xy.divmod(tile, b, rem);
     p.d_tiles_x.divmod(rem, ty0, tx0);
     ty0 *= K::TH;
     tx0 *= K::TW;
 
-    // ---- LN prologue: halo token `tid` ---------------------------------------------
-    if (tid < K::NHALO) {
+    // ---- LN prologue ---------------------------------------------------------------------
+    if constexpr (PIPE) {
+      // whole warps (the pair LayerNorm shuffles): skip only warps with no halo token at all
+      if (((tid & ~31) >> 1) < K::NHALO) {
+        const bool row_ok = ht < K::NHALO, in = htok >= 0;
+        unsigned char* xt = sm + K::o_xn + ((row_ok ? ht : 0) >> 7) * K::XT;
+        ln_pair_to_tile<C, KC, K::BIAS_MMA>(xr, half, in, row_ok, sLn, sLn + K::C4, p.eps, xt, ht & 127);
+        if (!K::BIAS_MMA && half == 0 && row_ok) sIn[ht] = in ? 1 : 0;
+      }
+    } else if (ht < K::NHALO) {
       const bool in = htok >= 0;
-      sIn[tid] = in ? 1 : 0;
-      unsigned char* xt = sm + K::o_xn + (tid >> 7) * K::XT;
-      if (in) {
-        if constexpr (PIPE) {
-          float v[C];
-          unpack_row<C>(xr, v);
-          ln_row_to_tile<C, KC, K::BIAS_MMA>(v, sLn, sLn + K::C4, p.eps, xt, tid & 127);
+      unsigned char* xt = sm + K::o_xn + (ht >> 7) * K::XT;
+      {
+        sIn[ht] = in ? 1 : 0;
+        if (in) {
+          ln_token<C, KC, true, K::BIAS_MMA>(x + (size_t)htok * C, sLn, sLn + K::C4, p.eps, xt, ht & 127);
         } else {
-          ln_token<C, KC, true, K::BIAS_MMA>(x + (size_t)htok * C, sLn, sLn + K::C4, p.eps, xt, tid & 127);
-        }
-      } else {
-        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ch = 0; ch < KC / 8; ++ch) st_chunk(xt, tid & 127, ch, 128, zero);
+          for (int ch = 0; ch < KC / 8; ++ch) st_chunk(xt, ht & 127, ch, 128, zero);
+        }
       }
     }
     // requests that complete behind this tile's work
     const int htok_next = halo_token(tile + tile_step);
     uint32_t xnext[NW];
-    if (PIPE && htok_next >= 0) load_row_raw<C>(x + (size_t)htok_next * C, xnext);
+    if constexpr (PIPE) {
+      if (htok_next >= 0) ln_pair_load<C>(x + (size_t)htok_next * C, half, xnext);
+    }
     const int oh = ty0 + row / K::TW, ow = tx0 + row % K::TW;
     const bool o_in = row < K::NTOK && oh < p.H && ow < p.W;
     const size_t o_tok = o_in ? (size_t)(b * p.H + oh) * p.W + ow : 0;
@@ -256,9 +275,15 @@ mixffn_tc_kernel(FfnParams p) {
 #pragma unroll 1
     for (int c = 0; c < CPG; ++c) {
       // ---- fc1 on the halo M tile(s) ---------------------------------------------------
+      HRF_PROF(0)                                  // LN prologue (first chunk)
+      if (!w_ready) {                              // first tile: weights have landed?
+        mbar_wait(&wbar, 0);
+        w_ready = true;
+      }
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      HRF_PROF(1)
       if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t id1 = idesc_bf16(128, N1, false, false);
@@ -271,9 +296,11 @@ mixffn_tc_kernel(FfnParams p) {
                      id1, s > 0);
         mma_commit(&bar);
       }
+      HRF_PROF(2)                                  // fc1 issue
       cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
+      HRF_PROF(3)                                  // fc1 wait
 
       // ---- epilogue 1: (+ b1,) GELU, zero outside the image -> H1 -----------------------
       const float* fb = sF + c * 880;
@@ -298,55 +325,24 @@ mixffn_tc_kernel(FfnParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = in ? v[j] : 0.f;
           }
-          if constexpr (K::H1F32) {
-            float4* h1 = reinterpret_cast<float4*>(sm + K::o_h1);
-            h1[(2 * ch) * K::H1R + t] = make_float4(v[0], v[1], v[2], v[3]);
-            h1[(2 * ch + 1) * K::H1R + t] = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
-          }
+          st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
         }
       }
+      HRF_PROF(4)                                  // epilogue 1
       tc_fence_before();
       __syncthreads();
+      HRF_PROF(5)
 
       // ---- depthwise 3x3 + GELU -> H2 --------------------------------------------------
-      if constexpr (K::H1F32) {
-        // fp32 H1: unit = (output token, 8-channel chunk), dealt linearly
-        const float* wd = fb + 80;
-        const float* bd = fb + 800;
-#pragma unroll 1
-        for (int id = tid; id < K::NTOK * 9; id += NT) {
-          const int ch = id / K::NTOK, o = id - ch * K::NTOK;
-          const int oy = o / K::TW, ox = o - oy * K::TW;
-          const float4 da = *reinterpret_cast<const float4*>(bd + ch * 8);
-          const float4 db = *reinterpret_cast<const float4*>(bd + ch * 8 + 4);
-          float acc[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const int tt = (oy + dy) * K::HW + ox + dx;
-              const float* wt = wd + (dy * 3 + dx) * 80 + ch * 8;
-              const float4 wa = *reinterpret_cast<const float4*>(wt);
-              const float4 wb = *reinterpret_cast<const float4*>(wt + 4);
-              const float4* h1 = reinterpret_cast<const float4*>(sm + K::o_h1);
-              const float4 fa = h1[(2 * ch) * K::H1R + tt], fb4 = h1[(2 * ch + 1) * K::H1R + tt];
-              acc[0] = fmaf(fa.x, wa.x, acc[0]); acc[1] = fmaf(fa.y, wa.y, acc[1]);
-              acc[2] = fmaf(fa.z, wa.z, acc[2]); acc[3] = fmaf(fa.w, wa.w, acc[3]);
-              acc[4] = fmaf(fb4.x, wb.x, acc[4]); acc[5] = fmaf(fb4.y, wb.y, acc[5]);
-              acc[6] = fmaf(fb4.z, wb.z, acc[6]); acc[7] = fmaf(fb4.w, wb.w, acc[7]);
-            }
-          gelu8(acc);
-          st_chunk(sm + K::o_h2, o, ch, K::H2R, acc);
-        }
-      } else {
+      {
         // bf16 H1: unit = (strip of SH vertically adjacent outputs, 4 channels).  Every halo
         // value is loaded and unpacked once per column offset and feeds up to three outputs;
         // the multiply-adds are packed fp32x2 (FFMA2).  Lane pairs cover the two halves of one
         // token's 16-byte chunk, so a warp's 8-byte accesses are contiguous.
         constexpr int SH = K::SH;
         constexpr int NUNIT = 9 * K::NSTRIP * K::TW * 2;
+        if (K::REWRITE_ONE && tid < K::H2R)          // LN(x) overwrote the constant-1 column
+          *reinterpret_cast<uint4*>(sm + K::o_h2 + (9 * K::H2R + tid) * 16) = make_uint4(0x00003F80u, 0, 0, 0);
         const float* wd = fb + 80;
         const float* bd = fb + 800;
 #pragma unroll 1
@@ -398,9 +394,11 @@ mixffn_tc_kernel(FfnParams p) {
       }
 
       // ---- fc2 partial product over this chunk's 72 (padded 80) channels --------------
+      HRF_PROF(6)                                  // depthwise conv
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      HRF_PROF(7)
       if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t id2 = idesc_bf16(128, NOUT, false, false);
@@ -411,9 +409,11 @@ mixffn_tc_kernel(FfnParams p) {
                    (c > 0) || (s > 0));
         mma_commit(&bar);
       }
+      HRF_PROF(8)                                  // fc2 issue
       cta_wait(&bar, phase);        // H2 / XN free again, Y complete after the last chunk
       phase ^= 1;
       tc_fence_after();
+      HRF_PROF(9)                                  // fc2 wait
     }
 
     // ---- epilogue 2: unit = (output token, 8-channel chunk of the C outputs) ----------
@@ -450,6 +450,7 @@ mixffn_tc_kernel(FfnParams p) {
         }
       }
     }
+    HRF_PROF(10)                                   // epilogue 2
     // rotate the software pipeline
     htok = htok_next;
     if constexpr (PIPE) {
@@ -471,11 +472,12 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
                                                          const __nv_bfloat16* x,
                                                          const float* __restrict__ b2,
                                                          __nv_bfloat16* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n_vec = n_tok * (C / 8);
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (size_t)gridDim.x * blockDim.x) {
     const size_t e0 = v * 8;
-    const int c0 = (int)(e0 % C);
     float acc[8], r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;     // b2 is part of the first partial (MMA bias row)
@@ -486,7 +488,6 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
       acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
     }
     load_row_bf16<8>(x + e0, r);
-#pragma unroll
     gelu8(acc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += r[j];
@@ -514,8 +515,9 @@ static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
   const int cap = 148 * per_sm / K::NG > 0 ? 148 * per_sm / K::NG : 1;
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tc: workspace required for C=%d", C);
+  HRF_REQUIRE((reinterpret_cast<uintptr_t>(p.blob) & 15) == 0, HRF_EINVAL, "mixffn_tc: blob must be 16-byte aligned");
   HRF_CUDA(ensure_smem((const void*)mixffn_tc_kernel<C, CPG>, K::SMEM));
-  mixffn_tc_kernel<C, CPG><<<grid, K::NT, K::SMEM, stream>>>(p);
+  HRF_CUDA(launch_pdl(mixffn_tc_kernel<C, CPG>, dim3(grid), dim3(K::NT), K::SMEM, stream, p));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   if constexpr (K::SPLIT) {
@@ -523,9 +525,9 @@ static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
     const size_t n_tok = (size_t)p.B * p.H * p.W;
     const size_t n_vec = n_tok * (C / 8);
     const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
-    ffn_reduce_kernel<C><<<rgrid, 256, 0, stream>>>(
-        static_cast<const float*>(p.ws), K::NG, n_tok, static_cast<const __nv_bfloat16*>(p.x),
-        p.blob + L.o_tc_f32 + K::NCH * 880, static_cast<__nv_bfloat16*>(p.out));
+    HRF_CUDA(launch_pdl(ffn_reduce_kernel<C>, dim3(rgrid), dim3(256), 0, stream,
+                        static_cast<const float*>(p.ws), K::NG, n_tok, static_cast<const __nv_bfloat16*>(p.x),
+                        p.blob + L.o_tc_f32 + K::NCH * 880, static_cast<__nv_bfloat16*>(p.out)));
     count_launch();
     HRF_CUDA(cudaGetLastError());
   }

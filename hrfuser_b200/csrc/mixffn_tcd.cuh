@@ -26,22 +26,6 @@
 
 namespace hrf {
 
-// -DHRF_FFN_PROFILE: thread 0 of every CTA accumulates clock64 deltas per phase of the tile
-// loop into g_ffn_prof[cta][16] (slot 15 = tiles), read back by hrf_debug_ffn_prof().
-#ifdef HRF_FFN_PROFILE
-__device__ unsigned long long g_ffn_prof[1024 * 16];
-#define FFN_PROF_DECL long long pt_ = clock64();
-#define FFN_PROF(k)                                                          \
-  if (tid == 0) {                                                            \
-    const long long now_ = clock64();                                        \
-    g_ffn_prof[blockIdx.x * 16 + (k)] += (unsigned long long)(now_ - pt_);   \
-    pt_ = now_;                                                              \
-  }
-#else
-#define FFN_PROF_DECL
-#define FFN_PROF(k)
-#endif
-
 template <int C, int CPG>
 struct FfnTcd {
   static constexpr int HID = 4 * C, NCH = HID / 72, NG = NCH / CPG;
@@ -87,6 +71,8 @@ mixffn_tcd_kernel(FfnParams p) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
 
+  HRF_PROF_DECL
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int gq = warp >> 2, q = warp & 3;          // work group, TMEM quadrant
   const int row = q * 32 + lane;                   // TMEM lane == halo token == tile row
@@ -165,6 +151,7 @@ mixffn_tcd_kernel(FfnParams p) {
     const int w = tx * K::TW - 1 + (tid & 15);
     return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? (b * p.H + h) * p.W + w : -1;
   };
+  pdl_wait();
   uint32_t xr[NW];
   int htok = halo_token(blockIdx.x / NG);
   if (PIPE && htok >= 0) load_row_raw<C>(x + (size_t)htok * C, xr);
@@ -173,17 +160,14 @@ mixffn_tcd_kernel(FfnParams p) {
   const int oy = row >> 4, ox = row & 15;
   const bool o_row = (oy < K::TH) && (ox < K::TW);
 
-  FFN_PROF_DECL
-  FFN_PROF(14)                                     // setup
+  HRF_PROF(14)                                     // setup
   for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
     int b, rem, ty0, tx0;
     p.d_tiles_xy.divmod(tile, b, rem);
     p.d_tiles_x.divmod(rem, ty0, tx0);
     ty0 *= K::TH;
     tx0 *= K::TW;
-#ifdef HRF_FFN_PROFILE
-    if (tid == 0) g_ffn_prof[blockIdx.x * 16 + 15] += 1;
-#endif
+    HRF_PROF_TILE
 
     // ---- LN prologue: halo token `tid` -> row `tid` of the LN(x) tile -----------------
     if (tid < K::NHALO) {
@@ -215,21 +199,21 @@ mixffn_tcd_kernel(FfnParams p) {
         if (gq * 8 + 2 * j < C) rres[j] = __ldg(reinterpret_cast<const uint32_t*>(x + o_tok * C + gq * 8) + j);
     }
 
-    FFN_PROF(0)                                    // LN prologue
+    HRF_PROF(0)                                    // LN prologue
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    FFN_PROF(1)                                    // barrier skew
+    HRF_PROF(1)                                    // barrier skew
     if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_fc1(0);
       mma_commit(&bar);
     }
-    FFN_PROF(2)                                    // fc1 issue
+    HRF_PROF(2)                                    // fc1 issue
     cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
-    FFN_PROF(3)                                    // fc1 wait
+    HRF_PROF(3)                                    // fc1 wait
 
 #pragma unroll 1
     for (int c = 0; c < CPG; ++c) {
@@ -243,12 +227,12 @@ mixffn_tcd_kernel(FfnParams p) {
         st_chunk(sm + K::o_h, row, ch, 128, v);
       }
 
-      FFN_PROF(4)                                  // epilogue 1
+      HRF_PROF(4)                                  // epilogue 1
       // ---- depthwise 3x3 (+ bd) on the tensor cores: D = sum_tap shift_tap(H1) . diag(wd_tap)
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      FFN_PROF(5)
+      HRF_PROF(5)
       if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t idd = idesc_bf16(128, 16, false, false);
@@ -269,11 +253,11 @@ mixffn_tcd_kernel(FfnParams p) {
         }
         mma_commit(&bar);
       }
-      FFN_PROF(6)                                  // conv issue
+      HRF_PROF(6)                                  // conv issue
       cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
-      FFN_PROF(7)                                  // conv wait
+      HRF_PROF(7)                                  // conv wait
 
       // ---- epilogue dw: H2 = GELU(conv), in place over H1 (rows of real output tokens) ---
       if (q < 3) {                                   // rows 96..127 hold no output token
@@ -289,12 +273,12 @@ mixffn_tcd_kernel(FfnParams p) {
         }
       }
 
-      FFN_PROF(8)                                  // epilogue dw
+      HRF_PROF(8)                                  // epilogue dw
       // ---- fc2 partial product over this chunk (and fc1 of the next chunk behind it) -----
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      FFN_PROF(9)
+      HRF_PROF(9)
       if (warp == 0 && elect_one()) {
         tc_fence_after();
         constexpr uint32_t id2 = idesc_bf16(128, NOUT, false, false);
@@ -306,11 +290,11 @@ mixffn_tcd_kernel(FfnParams p) {
         if (c + 1 < CPG) issue_fc1(c + 1);
         mma_commit(&bar);
       }
-      FFN_PROF(10)                                 // fc2 issue
+      HRF_PROF(10)                                 // fc2 issue
       cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
-      FFN_PROF(11)                                 // fc2 wait
+      HRF_PROF(11)                                 // fc2 wait
     }
 
     // ---- epilogue 2: unit = (output token, 8-channel chunk of the C outputs) ----------
@@ -344,7 +328,7 @@ mixffn_tcd_kernel(FfnParams p) {
         }
       }
     }
-    FFN_PROF(12)                                   // epilogue 2
+    HRF_PROF(12)                                   // epilogue 2
     htok = htok_next;
     if constexpr (PIPE) {
 #pragma unroll
@@ -377,7 +361,7 @@ static int launch_ffn_tcd_c(FfnParams p, cudaStream_t stream) {
   const int grid = (n_tiles < cap ? n_tiles : cap) * K::NG;
   if (K::SPLIT) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "mixffn_tcd: workspace required for C=%d", C);
   HRF_CUDA(ensure_smem((const void*)mixffn_tcd_kernel<C, CPG>, K::SMEM));
-  mixffn_tcd_kernel<C, CPG><<<grid, K::NT, K::SMEM, stream>>>(p);
+  HRF_CUDA(launch_pdl(mixffn_tcd_kernel<C, CPG>, dim3(grid), dim3(K::NT), K::SMEM, stream, p));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;

@@ -72,6 +72,23 @@ __device__ __forceinline__ void cta_wait(uint64_t* bar, uint32_t parity) {
   __syncthreads();
 }
 
+// ---- bulk async copy global -> shared (TMA, 1-D), completion on an mbarrier ---------------
+// `bytes` multiple of 16, both addresses 16-byte aligned.  One thread: expect_tx(total) once,
+// then any number of copies; waiters use mbar_wait(bar, phase).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- single-thread issue -----------------------------------------------------------
 // tcgen05.mma / commit are issued by one thread.  Guarding them with `threadIdx.x == 0` makes
 // the branch thread-divergent for the compiler, which then wraps every UTCHMMA in an

@@ -180,6 +180,83 @@ __device__ __forceinline__ void ln_row_to_tile(const float* x, const float* gamm
   }
 }
 
+// ---- LayerNorm of one token by a PAIR of adjacent lanes ------------------------------------
+// half = lane & 1.  Half 0 owns channels [0, CA) (whole 8-channel chunks), half 1 owns [CA, C)
+// plus the constant-1 column; the statistics are combined with two shuffles.  Halves the
+// serial chain of the row-per-thread version and keeps every thread of a 2 x rows CTA busy.
+template <int C>
+struct LnPair {
+  static constexpr int CA = (C / 2) / 8 * 8;                 // 8 (C=18) | 16 (C=36)
+  static constexpr int NA = CA, NB = C - CA;                 // channels of half 0 / half 1
+  static constexpr int NM = NB > NA ? NB : NA;
+  static constexpr int NW = NM / 2;                          // packed words per thread
+  static_assert(C % 2 == 0 && CA >= 8, "pair LayerNorm: even C >= 16");
+};
+// raw packed words of this thread's part of the row (absent words read as 0)
+template <int C>
+__device__ __forceinline__ void ln_pair_load(const __nv_bfloat16* row, int half, uint32_t* w) {
+  using P = LnPair<C>;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(row) + (half ? P::CA / 2 : 0);
+  const int n = half ? P::NB / 2 : P::NA / 2;
+#pragma unroll
+  for (int j = 0; j < P::NW; ++j) w[j] = (j < n) ? __ldg(src + j) : 0u;
+}
+// `valid` is uniform over the pair; an invalid (outside / pad) token becomes an all-zero row.
+// Contains warp shuffles: every lane of the warp must call it (`store` = false for lanes whose
+// row does not exist).
+template <int C, int KC, bool ONE>
+__device__ __forceinline__ void ln_pair_to_tile(const uint32_t* w, int half, bool valid, bool store,
+                                                const float* gamma, const float* beta, float eps,
+                                                unsigned char* tile, int row) {
+  using P = LnPair<C>;
+  constexpr int NM = P::NM, NA = P::NA, NB = P::NB;
+  float v[NM];
+#pragma unroll
+  for (int j = 0; j < P::NW; ++j) {
+    const uint32_t wj = valid ? w[j] : 0u;                    // invalid rows hold no data
+    v[2 * j] = __uint_as_float(wj << 16);
+    v[2 * j + 1] = __uint_as_float(wj & 0xffff0000u);
+  }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NM; i += 2) { s0 += v[i]; s1 += v[i + 1]; }
+  float s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const float mean = s * (1.0f / C);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NM; i += 2) {
+    float d0 = v[i] - mean, d1 = v[i + 1] - mean;
+    if (i >= NA) { d0 = half ? d0 : 0.f; d1 = half ? d1 : 0.f; }    // half 0 has no such channel
+    q0 = fmaf(d0, d0, q0);
+    q1 = fmaf(d1, d1, q1);
+    v[i] = d0; v[i + 1] = d1;
+  }
+  float q = q0 + q1;
+  q += __shfl_xor_sync(0xffffffffu, q, 1);
+  const float rstd = valid ? rsqrtf(q * (1.0f / C) + eps) : 0.f;
+  const float one = valid ? 1.f : 0.f;
+  const float* ga = gamma + (half ? P::CA : 0);
+  const float* be = beta + (half ? P::CA : 0);
+  constexpr int ZC0 = (C + (ONE ? 1 : 0) + 7) / 8;            // first all-zero chunk
+  constexpr int KA = P::CA / 8 + (KC / 8 - ZC0), KB = ZC0 - P::CA / 8;
+  constexpr int KMAX = KA > KB ? KA : KB;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = 8 * k + j;
+      const float n = (i < NM) ? fmaf(v[i < NM ? i : 0] * rstd, ga[i < NM ? i : 0], valid ? be[i < NM ? i : 0] : 0.f) : 0.f;
+      const float a = (i < NA) ? n : 0.f;
+      const float b = (i < NB) ? n : (ONE && i == NB) ? one : 0.f;
+      o[j] = (i < NA && i < NB) ? n : (half ? b : a);
+    }
+    const int chunk = half ? P::CA / 8 + k : (k < P::CA / 8 ? k : ZC0 + k - P::CA / 8);
+    if (store && chunk < (half ? ZC0 : KC / 8)) umma::st_chunk(tile, row, chunk, 128, o);
+  }
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -245,10 +322,12 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   constexpr int HDP = K::HDP, KC = K::KC, NQ = K::NQ, NQG = K::NQG, NOUT = K::NOUT;
   constexpr int WIN = K::WIN, S = K::S, NG = K::NG;
   extern __shared__ __align__(128) unsigned char sm[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t valid_bits[4];
 
+  HRF_PROF_DECL
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int g = tid >> 6, i = tid & 63;            // window of the pair, slot in the window
   const int hg = blockIdx.x % NG;                  // head group of this CTA
@@ -260,23 +339,30 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   float* sLn = reinterpret_cast<float*>(sm + K::o_ln);
 
   // ---- one-time setup: this group's weight slices + small tables -> smem -----------
-  {
-    // q/k/v tiles in the blob are [KC/8][NQ rows][16 B]; take rows h0*32 .. +NQG
+  // The bf16 weight tiles arrive by bulk async copies (one thread issues them, completion on
+  // `wbar`) that run behind the table loads and the first tile's LN prologue.
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+    constexpr uint32_t piece = NQG * 16;           // one 8-column chunk of this group's rows
+    constexpr uint32_t wo_b = (NQG / 8) * NOUT * 16;
+    mbar_expect_tx(&wbar, 3 * (KC / 8) * piece + wo_b);
+    // q/k/v tiles in the blob are [KC/8][NQ rows][16 B]; take rows h0*32 .. +NQG of each chunk
+#pragma unroll 1
     for (int part = 0; part < 3; ++part) {
-      const uint4* src = reinterpret_cast<const uint4*>(
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(
           blob + (part == 0 ? L.o_tc_wq : part == 1 ? L.o_tc_wk : L.o_tc_wv));
-      uint4* dst = reinterpret_cast<uint4*>(sm + (part == 0 ? K::o_wq : part == 1 ? K::o_wk : K::o_wv));
-      for (int e = tid; e < (KC / 8) * NQG; e += 128) {
-        const int ch = e / NQG, r = e - ch * NQG;
-        dst[e] = __ldg(src + (size_t)ch * NQ + h0 * HDP + r);
-      }
+      unsigned char* dst = sm + (part == 0 ? K::o_wq : part == 1 ? K::o_wk : K::o_wv);
+#pragma unroll 1
+      for (int ch = 0; ch < KC / 8; ++ch)
+        bulk_g2s(dst + ch * piece, src + ((size_t)ch * NQ + h0 * HDP) * 16, piece, &wbar);
     }
     // out-proj tile [NQ/8][NOUT rows][16 B]: this group's K chunks are contiguous
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(blob + L.o_tc_wo) + (size_t)(h0 * HDP / 8) * NOUT;
-      uint4* dst = reinterpret_cast<uint4*>(sm + K::o_wo);
-      for (int e = tid; e < (NQG / 8) * NOUT; e += 128) dst[e] = __ldg(src + e);
-    }
+    bulk_g2s(sm + K::o_wo, reinterpret_cast<const unsigned char*>(blob + L.o_tc_wo) + (size_t)(h0 * HDP / 8) * NOUT * 16,
+             wo_b, &wbar);
+  }
+  {
     for (int e = tid; e < 3 * NQG; e += 128)
       sBias[e] = __ldg(blob + L.o_tc_bias + (e / NQG) * NQ + h0 * HDP + (e % NQG));
     for (int e = tid; e < NOUT; e += 128) sBias[3 * NQG + e] = __ldg(blob + L.o_tc_bias + 3 * NQ + e);
@@ -289,10 +375,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     }
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
+  bool w_ready = false;                            // bulk copies observed complete
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -340,13 +423,16 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
   constexpr int NW = PIPE ? C / 2 : 1;
   uint32_t xr[NW], zr[NW];
   const int tile_step = gridDim.x / NG;
+  pdl_wait();                                      // everything above only read the weight blob
   int tok = row_token(blockIdx.x / NG);
   if (PIPE && tok >= 0) {
     load_row_raw<C>(xq + (size_t)tok * C, xr);
     if (CROSS) load_row_raw<C>(zz + (size_t)tok * C, zr);
   }
 
+  HRF_PROF(14)                                     // setup
   for (int tile = blockIdx.x / NG; tile < n_tiles; tile += tile_step) {
+    HRF_PROF_TILE
     const int wdx = tile * 2 + g;
     {
       const unsigned bal = __ballot_sync(0xffffffffu, tok >= 0);
@@ -387,9 +473,15 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         if (CROSS) load_row_raw<C>(zz + (size_t)tok_next * C, znext);
       }
     }
+    HRF_PROF(0)                                    // LN prologue
+    if (!w_ready) {                                // first tile: weights have landed?
+      mbar_wait(&wbar, 0);
+      w_ready = true;
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    HRF_PROF(1)
 
     // ---- q / k / v projections of this head group --------------------------------------
     if (warp == 0 && elect_one()) {
@@ -407,9 +499,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         mma_bf16(tmem + 2 * NQG, desc_kmajor(a_kv, 128, s), desc_kmajor(a_wv, NQG, s), idq, s > 0);
       mma_commit(&bar);
     }
+    HRF_PROF(2)                                    // q/k/v issue
     cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
+    HRF_PROF(3)                                    // q/k/v wait
 #pragma unroll
     for (int part = 0; part < 3; ++part) {
 #pragma unroll
@@ -436,6 +530,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
 #pragma unroll
     for (int h = 0; h < HG; ++h) {
       // ---- S = Q_h [K_A;K_B]^T -------------------------------------------------------
+      HRF_PROF(4)                                  // q/k/v epilogue (h = 0) | PV epilogue
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -448,9 +543,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
                    desc_kmajor(a_qk + h * 2 * K::HT + K::HT, 128, s), ids, s > 0);
         mma_commit(&bar);
       }
+      HRF_PROF(5)                                  // sync + S issue
       cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
+      HRF_PROF(6)                                  // S wait
 
       // ---- softmax over the 49 keys of this row's window ---------------------------
       float sc[56];
@@ -494,6 +591,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       }
 
       // ---- O = P V (both windows' V; each row keeps its own) -------------------------
+      HRF_PROF(7)                                  // softmax
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -508,9 +606,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
                      desc_mnmajor(a_v + h * K::HT + g2 * 64 * 16, 128, s), ido, s > 0);
         mma_commit(&bar);
       }
+      HRF_PROF(8)                                  // sync + PV issue
       cta_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
+      HRF_PROF(9)                                  // PV wait
       {
         float o[32];
         tmem_ld32(trow + g * HDP, o);
@@ -525,6 +625,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     }
 
     // ---- output projection (this group's K slice) --------------------------------------
+    HRF_PROF(10)                                   // PV epilogue (last head)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -536,9 +637,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         mma_bf16(tmem, desc_kmajor(a_xn, 128, s), desc_kmajor(a_wo, NOUT, s), idy, s > 0);
       mma_commit(&bar);
     }
+    HRF_PROF(11)                                   // sync + out-proj issue
     cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
+    HRF_PROF(12)                                   // out-proj wait
     if constexpr (!K::SPLIT) {
       float y[NOUT];
 #pragma unroll
@@ -574,6 +677,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         }
       }
     }
+    HRF_PROF(13)                                   // output epilogue
     // rotate the software pipeline
     tok = tok_next;
     if constexpr (PIPE) {
@@ -595,6 +699,8 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int n
                                                           const __nv_bfloat16* zz,
                                                           const float* __restrict__ bo,
                                                           __nv_bfloat16* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n_vec = n_tok * (C / 8);
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (size_t)gridDim.x * blockDim.x) {
@@ -627,18 +733,19 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
   // debug knob: HRF_ATTN_CTAS_PER_SM limits the persistent grid (occupancy experiments)
-  static const int per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e ? atoi(e) : 4; }();
+  static const int per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
   const int per_group = n_tiles < 148 * per_sm / NG ? n_tiles : 148 * per_sm / NG;   // <= 4 CTAs / SM (TMEM)
   const int grid = per_group * NG;
   if (NG > 1) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn_tc: workspace required for C=%d", C);
+  HRF_REQUIRE((reinterpret_cast<uintptr_t>(p.blob) & 15) == 0, HRF_EINVAL, "attn_tc: blob must be 16-byte aligned");
   if (p.cross) {
     using K = AttnTc<C, HEADS, HG, true>;
     HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, HG, true>, K::SMEM));
-    window_attn_tc_kernel<C, HEADS, HG, true><<<grid, 128, K::SMEM, stream>>>(p);
+    HRF_CUDA(launch_pdl(window_attn_tc_kernel<C, HEADS, HG, true>, dim3(grid), dim3(128), K::SMEM, stream, p));
   } else {
     using K = AttnTc<C, HEADS, HG, false>;
     HRF_CUDA(ensure_smem((const void*)window_attn_tc_kernel<C, HEADS, HG, false>, K::SMEM));
-    window_attn_tc_kernel<C, HEADS, HG, false><<<grid, 128, K::SMEM, stream>>>(p);
+    HRF_CUDA(launch_pdl(window_attn_tc_kernel<C, HEADS, HG, false>, dim3(grid), dim3(128), K::SMEM, stream, p));
   }
   count_launch();
   HRF_CUDA(cudaGetLastError());
@@ -647,10 +754,10 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
     const size_t n_tok = (size_t)p.B * p.H * p.W;
     const size_t n_vec = n_tok * (C / 8);
     const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
-    attn_reduce_kernel<C><<<rgrid, 256, 0, stream>>>(
-        static_cast<const float*>(p.ws), NG, n_tok, static_cast<const __nv_bfloat16*>(p.resid),
-        p.cross ? static_cast<const __nv_bfloat16*>(p.z) : nullptr, p.blob + L.o_tc_bias + 3 * L.tc_NQ,
-        static_cast<__nv_bfloat16*>(p.out));
+    HRF_CUDA(launch_pdl(attn_reduce_kernel<C>, dim3(rgrid), dim3(256), 0, stream,
+                        static_cast<const float*>(p.ws), NG, n_tok, static_cast<const __nv_bfloat16*>(p.resid),
+                        p.cross ? static_cast<const __nv_bfloat16*>(p.z) : nullptr,
+                        p.blob + L.o_tc_bias + 3 * L.tc_NQ, static_cast<__nv_bfloat16*>(p.out)));
     count_launch();
     HRF_CUDA(cudaGetLastError());
   }

@@ -330,3 +330,8 @@ def nhwc_to_nchw(x, dtype=None):
 
 def launch_count():
     return int(_lib.load().hrf_launch_count())
+
+
+def set_pdl(enable):
+    """Programmatic dependent launch on/off (hrf_set_pdl); returns the previous setting."""
+    return bool(_lib.load().hrf_set_pdl(1 if enable else 0))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 3
+#define HRF_ABI_VERSION 4
 
 enum { HRF_F32 = 0, HRF_BF16 = 1 };
 enum {
@@ -46,6 +46,11 @@ const char* hrf_last_error(void);
 int hrf_device_check(void);
 /* Number of kernels this library has launched since load (all threads). */
 unsigned long long hrf_launch_count(void);
+/* Programmatic dependent launch (a kernel's prologue overlaps its predecessor's tail).  Off by
+ * default (HRF_PDL=1 in the environment enables it): it helps a single-stream chain of kernels
+ * and costs ~2 % in the engine's multi-stream graph.  Returns the previous setting.  Affects
+ * launches (and graph captures) made after the call. */
+int hrf_set_pdl(int32_t enable);
 
 /* ------------------------------------------------------------------------
  * Window attention: LocalWindowSelfAttention + WindowMSA
