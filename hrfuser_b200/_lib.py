@@ -39,6 +39,11 @@ class DwPwDesc(PwDesc):
     pass
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32),
+                ('Cout', C.c_int32), ('stride', C.c_int32), ('dtype', C.c_int32), ('relu', C.c_int32)]
+
+
 class StemDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('Cin', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('Cout', C.c_int32), ('relu', C.c_int32)]
@@ -76,6 +81,9 @@ SIGNATURES = {
     'hrf_pw_blob_floats': (C.c_size_t, [C.POINTER(PwDesc)]),
     'hrf_pw_pack': (C.c_int, [C.POINTER(PwDesc), _F, _F, _FP4, C.c_float, _F]),
     'hrf_pw_fwd': (C.c_int, [C.POINTER(PwDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hrf_conv3x3_blob_floats': (C.c_size_t, [C.POINTER(ConvDesc)]),
+    'hrf_conv3x3_pack': (C.c_int, [C.POINTER(ConvDesc), _F, _F, _FP4, C.c_float, _F]),
+    'hrf_conv3x3_fwd': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrf_dwpw_blob_floats': (C.c_size_t, [C.POINTER(DwPwDesc)]),
     'hrf_dwpw_pack': (C.c_int, [C.POINTER(DwPwDesc), _F, _FP4, _F, _FP4, C.c_float, _F]),
     'hrf_dwpw_fwd': (C.c_int, [C.POINTER(DwPwDesc), C.c_void_p, C.c_void_p, C.c_void_p,

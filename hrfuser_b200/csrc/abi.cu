@@ -423,6 +423,34 @@ int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, 
   HRF_REQUIRE(false, HRF_EINVAL, "pw_fwd: dtype");
 }
 
+size_t hrf_conv3x3_blob_floats(const HrfConvDesc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
+  return (size_t)PwLayout(9 * d->Cin, d->Cout).total;
+}
+int hrf_conv3x3_pack(const HrfConvDesc* d, const float* w, const float* bias, const float* const bn[4],
+                     float bn_eps, float* blob) {
+  HRF_REQUIRE(d && w && blob, HRF_EINVAL, "conv3x3_pack: null pointer");
+  // (Cout, Cin, 3, 3) -> (Cout, tap, Cin): the K index of the implicit GEMM is tap*Cin + c
+  const int Cin = d->Cin, Cout = d->Cout;
+  std::vector<float> wp((size_t)Cout * 9 * Cin);
+  for (int n = 0; n < Cout; ++n)
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < 9; ++t) wp[((size_t)n * 9 + t) * Cin + c] = w[((size_t)n * Cin + c) * 9 + t];
+  pack_pw(PwLayout(9 * Cin, Cout), wp.data(), bias, bn, bn_eps, blob);
+  return HRF_OK;
+}
+int hrf_conv3x3_fwd(const HrfConvDesc* d, const void* x, const float* blob, void* out, void* stream) {
+  HRF_REQUIRE(d && x && blob && out, HRF_EINVAL, "conv3x3_fwd: null pointer");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, HRF_EINVAL, "conv3x3_fwd: dims");
+  Conv3Params p{};
+  p.x = x; p.blob = blob; p.out = out;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.stride = d->stride; p.relu = d->relu;
+  if (d->dtype == HRF_F32) return launch_conv3x3<float>(p, (cudaStream_t)stream);
+  if (d->dtype == HRF_BF16) return launch_conv3x3<__nv_bfloat16>(p, (cudaStream_t)stream);
+  HRF_REQUIRE(false, HRF_EINVAL, "conv3x3_fwd: dtype");
+}
+
 size_t hrf_dwpw_blob_floats(const HrfDwPwDesc* d) {
   if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
   return (size_t)DwPwLayout(d->Cin, d->Cout).total;

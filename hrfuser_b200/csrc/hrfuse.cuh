@@ -106,6 +106,175 @@ static int launch_pw(const PwParams& p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------
+// dense 3x3 conv (pad 1, stride 1 or 2) + folded BN (+ReLU) on channels-last tokens: the
+// transition layers between the HRNet stages and towards the fusion blocks
+// (reference hrformer.py `_make_transition_layer` :562-607 and hrfuser_hrformer_based.py
+// `_make_transition_layer_modality`).  Implicit GEMM: the CTA gathers the 9 taps of TOK output
+// tokens into an fp32 [TOK][9*Cin] tile (zero outside the image) and runs the block GEMM of the
+// 1x1 kernel on it.  blob = PwLayout(9*Cin, Cout), K index = tap*Cin + c.
+// ---------------------------------------------------------------------------
+struct Conv3Params {
+  const void* x; const float* blob; void* out;
+  int B, H, W, Ho, Wo, Cin, Cout, stride, relu;
+  int w_smem;
+  FastDiv d_cin, d_wo, d_howo;
+};
+
+template <typename T, int CT, int TOK>
+__global__ void __launch_bounds__(kPwThreads) conv3x3_kernel(Conv3Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = 9 * p.Cin;
+  const PwLayout L(K, p.Cout);
+  const T* x = static_cast<const T*>(p.x);
+  T* out = static_cast<T*>(p.out);
+  const int ntok = p.B * p.Ho * p.Wo;
+  const int t0 = blockIdx.x * TOK;
+  const int m = min(TOK, ntok - t0);
+  pdl_launch_dependents();
+  const float* Wt = stage_weights(p.blob + L.o_w, smem + TOK * L.lda, L.Kp * p.Cout, p.w_smem);
+  pdl_wait();
+  // gather: element (r, k = tap*Cin + c) of the patch matrix, two channels at a time
+  const int hk = K / 2, hp = L.lda / 2;
+  for (int e = threadIdx.x; e < TOK * hp; e += blockDim.x) {
+    const int r = e / hp, k2 = e - r * hp;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < m && k2 < hk) {
+      int tap, c;
+      p.d_cin.divmod(2 * k2, tap, c);
+      int b, rem, oy, ox;
+      p.d_howo.divmod(t0 + r, b, rem);
+      p.d_wo.divmod(rem, oy, ox);
+      const int iy = oy * p.stride - 1 + tap / 3, ix = ox * p.stride - 1 + tap % 3;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v = Pair<T>::ld(x + ((size_t)(b * p.H + iy) * p.W + ix) * p.Cin + c);
+    }
+    *reinterpret_cast<float2*>(smem + r * L.lda + 2 * k2) = v;
+  }
+  __syncthreads();
+  const float* bias = p.blob + L.o_b;
+  const int relu = p.relu, Cout = p.Cout;
+  block_gemm<4, CT>(smem, L.lda, m, Wt, L.Kp, Cout, [&](int r, int n, float v) {
+    v += __ldg(bias + n);
+    if (relu) v = fmaxf(v, 0.f);
+    Elem<T>::st(out + (size_t)(t0 + r) * Cout + n, v);
+  });
+}
+
+template <typename T, int TOK>
+static int launch_conv3x3_tok(Conv3Params p, cudaStream_t stream) {
+  const PwLayout L(9 * p.Cin, p.Cout);
+  size_t smem = (size_t)TOK * L.lda * sizeof(float);
+  p.w_smem = smem + (size_t)L.Kp * p.Cout * sizeof(float) <= 160 * 1024;
+  if (p.w_smem) smem += (size_t)L.Kp * p.Cout * sizeof(float);
+  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "conv3x3: Cin=%d too wide", p.Cin);
+  auto kern = (p.Cout % 4 == 0) ? conv3x3_kernel<T, 4, TOK> : conv3x3_kernel<T, 2, TOK>;
+  HRF_CUDA(ensure_smem((const void*)kern, smem));
+  const int ntok = p.B * p.Ho * p.Wo;
+  HRF_CUDA(launch_pdl(kern, dim3(ceil_div(ntok, TOK)), dim3(kPwThreads), smem, stream, p));
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+// Direct form for the narrow transition convs (K = 9*Cin is small; the op is launch / latency
+// bound, so it wants many short threads): a thread owns one output token x NCO output channels,
+// a warp covers 32 consecutive tokens of one output-channel group, so the weights (fp32
+// [K][NCO] slice of this group in shared memory) are warp-broadcast 8-byte loads and every
+// multiply-add is a packed fp32x2 FMA on a channel pair.  Per input-channel pair the nine
+// taps are requested together.  grid = (token blocks, Cout / NCO).
+template <typename T, int NCO>
+__global__ void __launch_bounds__(128) conv3x3_direct_kernel(Conv3Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = 9 * p.Cin, co0 = blockIdx.y * NCO;
+  const PwLayout L(K, p.Cout);
+  const T* x = static_cast<const T*>(p.x);
+  T* out = static_cast<T*>(p.out);
+  pdl_launch_dependents();
+  for (int e = threadIdx.x; e < K * NCO; e += blockDim.x) {
+    const int k = e / NCO, j = e - k * NCO;
+    smem[e] = __ldg(p.blob + L.o_w + (size_t)k * p.Cout + co0 + j);
+  }
+  pdl_wait();
+  __syncthreads();
+  const int ntok = p.B * p.Ho * p.Wo;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntok) return;
+  int bb, rem, oy, ox;
+  p.d_howo.divmod(t, bb, rem);
+  p.d_wo.divmod(rem, oy, ox);
+  // the nine taps: clamped row pointer + inside flag
+  const T* px[9];
+  bool in[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = oy * p.stride - 1 + tap / 3, ix = ox * p.stride - 1 + tap % 3;
+    in[tap] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    px[tap] = x + ((size_t)(bb * p.H + (in[tap] ? iy : 0)) * p.W + (in[tap] ? ix : 0)) * p.Cin;
+  }
+  float2 acc[NCO / 2];
+#pragma unroll
+  for (int j = 0; j < NCO / 2; ++j)
+    acc[j] = __ldg(reinterpret_cast<const float2*>(p.blob + L.o_b + co0) + j);
+  const int hc = p.Cin / 2;
+#pragma unroll 1
+  for (int c2 = 0; c2 < hc; ++c2) {
+    float2 xv[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      xv[tap] = Pair<T>::ld(px[tap] + 2 * c2);
+      if (!in[tap]) xv[tap] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float2* w0 = reinterpret_cast<const float2*>(smem + (size_t)(tap * p.Cin + 2 * c2) * NCO);
+      const float2* w1 = w0 + NCO / 2;
+#pragma unroll
+      for (int j = 0; j < NCO / 2; ++j) {
+        acc[j] = __ffma2_rn(make_float2(xv[tap].x, xv[tap].x), w0[j], acc[j]);
+        acc[j] = __ffma2_rn(make_float2(xv[tap].y, xv[tap].y), w1[j], acc[j]);
+      }
+    }
+  }
+  T* o = out + (size_t)t * p.Cout + co0;
+#pragma unroll
+  for (int j = 0; j < NCO / 2; ++j) {
+    float2 v = acc[j];
+    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+    Pair<T>::st(o + 2 * j, v.x, v.y);
+  }
+}
+
+template <typename T, int NCO>
+static int launch_conv3x3_direct(const Conv3Params& p, cudaStream_t stream) {
+  const size_t smem = (size_t)9 * p.Cin * NCO * sizeof(float);
+  auto kern = conv3x3_direct_kernel<T, NCO>;
+  HRF_CUDA(ensure_smem((const void*)kern, smem));
+  const int ntok = p.B * p.Ho * p.Wo;
+  HRF_CUDA(launch_pdl(kern, dim3(ceil_div(ntok, 128), p.Cout / NCO), dim3(128), smem, stream, p));
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+template <typename T>
+static int launch_conv3x3(Conv3Params p, cudaStream_t stream) {
+  HRF_REQUIRE(p.Cout % 2 == 0 && p.Cin % 2 == 0, HRF_EUNSUPPORTED,
+              "conv3x3: Cin=%d / Cout=%d must be even", p.Cin, p.Cout);
+  HRF_REQUIRE(p.stride == 1 || p.stride == 2, HRF_EUNSUPPORTED, "conv3x3: stride %d", p.stride);
+  p.Ho = (p.H - 1) / p.stride + 1;
+  p.Wo = (p.W - 1) / p.stride + 1;
+  p.d_cin = FastDiv(p.Cin);
+  p.d_wo = FastDiv(p.Wo);
+  p.d_howo = FastDiv(p.Ho * p.Wo);
+  const int ntok = p.B * p.Ho * p.Wo;
+  if (p.Cin <= 160 && p.Cout / 6 <= 65535) {   // narrow: the direct kernel
+    if (p.Cout % 6 == 0) return launch_conv3x3_direct<T, 6>(p, stream);
+    if (p.Cout % 8 == 0) return launch_conv3x3_direct<T, 8>(p, stream);
+  }
+  return ntok >= 148 * 2 * 64 ? launch_conv3x3_tok<T, 64>(p, stream) : launch_conv3x3_tok<T, 16>(p, stream);
+}
+
+// ---------------------------------------------------------------------------
 // depthwise 3x3 stride-2 (pad 1) + BN, then 1x1 + BN (+ReLU).
 // blob = Wdw [9][Cin] (BN folded), bdw [c4(Cin)], then a PwLayout blob.
 // ---------------------------------------------------------------------------

@@ -182,15 +182,32 @@ class BackboneEngine:
             slot.t = self.arena[o:o + b.numel()]
         self._host_blobs = None
 
+    def _tconv(self, mods):
+        """[conv3x3, bn, relu] of a transition layer.  Narrow ones (the modality transitions
+        18 -> 36 -> 72 -> 144 and the camera's new-branch convs) run in the library's implicit
+        GEMM kernel on tokens: cuDNN has no good kernel for these channel counts and wraps
+        each call in ~10 padding / layout launches."""
+        mods = list(mods)
+        conv, bn = mods[0], mods[1]
+        relu = len(mods) > 2 and isinstance(mods[2], nn.ReLU)
+        own = (isinstance(bn, nn.BatchNorm2d) and conv.kernel_size == (3, 3) and conv.groups == 1 and
+               conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1) and
+               conv.in_channels <= 72 and conv.in_channels % 2 == 0 and conv.out_channels % 2 == 0)
+        if not own:
+            return _Conv(conv, bn, relu, self.dtype)
+        blob = self._blob(ops.pack_conv3x3(conv, bn, bn.eps))
+        cout, stride = conv.out_channels, conv.stride[0]
+        return lambda x_img: self._image(self.ops.conv3x3(self._tokens(x_img), blob.t, cout, stride, relu))
+
     def _transitions(self, tl):
         out = []
         for t in tl:
             if t is None:
                 out.append(None)
             elif isinstance(t[0], nn.Conv2d):
-                out.append([_seq(t, self.dtype)])
+                out.append([self._tconv(t)])
             else:
-                out.append([_seq(s, self.dtype) for s in t])
+                out.append([self._tconv(s) for s in t])
         return out
 
     def _ffn(self, ln, ffn):

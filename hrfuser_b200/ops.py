@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, StemDesc,
+from ._lib import (AttnDesc, ConvDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, StemDesc,
                    check)
 
 _DT = {torch.float32: HRF_F32, torch.bfloat16: HRF_BF16}
@@ -147,6 +147,20 @@ def pack_pw(conv, bn, bn_eps=1e-5):
     return blob
 
 
+def pack_conv3x3(conv, bn, bn_eps=1e-5):
+    """Dense 3x3 conv (pad 1) + BN folded -> blob of hrf_conv3x3_fwd."""
+    lib = _lib.load()
+    cout, cin = conv.weight.shape[:2]
+    assert conv.weight.shape[2:] == (3, 3) and conv.groups == 1 and conv.padding == (1, 1)
+    d = ConvDesc(1, 1, 1, cin, cout, conv.stride[0], HRF_F32, 0)
+    blob = torch.empty(lib.hrf_conv3x3_blob_floats(C.byref(d)), dtype=torch.float32)
+    keep = []
+    w = _host(conv.weight)
+    b = _host(conv.bias) if conv.bias is not None else None
+    check(lib.hrf_conv3x3_pack(C.byref(d), _fp(w), _fp(b), _bn4(bn, keep), C.c_float(bn_eps), _fp(blob)))
+    return blob
+
+
 def pack_dwpw(conv_dw, bn_dw, conv_pw, bn_pw, bn_eps=1e-5):
     lib = _lib.load()
     cout, cin = conv_pw.weight.shape[:2]
@@ -243,6 +257,22 @@ def pointwise(x, blob, cout, relu=False):
     with _timed('pw', C=Cin, launches=1, bytes=float(n * (Cin + cout) * x.element_size()),
                 flops=float(2 * n * Cin * cout)):
         check(lib.hrf_pw_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def conv3x3(x, blob, cout, stride=1, relu=False):
+    """tokens [B,H,W,Cin] -> tokens [B,ceil(H/s),ceil(W/s),cout] (3x3, pad 1, BN folded)."""
+    lib = _lib.load()
+    _check_act(x)
+    B, H, W, Cin = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = x.new_empty(B, Ho, Wo, cout)
+    d = ConvDesc(B, H, W, Cin, cout, stride, _dtype_code(x), int(relu))
+    no = B * Ho * Wo
+    with _timed('conv3x3', C=Cin, launches=1,
+                bytes=float((B * H * W * Cin + no * cout) * x.element_size()),
+                flops=float(2 * no * 9 * Cin * cout)):
+        check(lib.hrf_conv3x3_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(), _stream()))
     return out
 
 

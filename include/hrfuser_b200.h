@@ -140,6 +140,21 @@ int hrf_pw_pack(const HrfPwDesc* d, const float* w, const float* bias,
                 const float* const bn[4], float bn_eps, float* blob_out);
 int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, void* stream);
 
+typedef struct HrfConvDesc {    /* dense 3x3 conv, pad 1, stride 1|2, + folded BN (+ReLU): the
+                                   transition layers (hrformer.py:562-607 and the modality
+                                   transitions of hrfuser_hrformer_based.py) */
+  int32_t B, H, W, Cin, Cout;   /* H, W: INPUT size; output is ceil(H/stride) x ceil(W/stride) */
+  int32_t stride;
+  int32_t dtype;
+  int32_t relu;
+} HrfConvDesc;
+size_t hrf_conv3x3_blob_floats(const HrfConvDesc* d);
+/* w: (Cout, Cin, 3, 3); bn = {weight,bias,mean,var} or NULL; bias may be NULL */
+int hrf_conv3x3_pack(const HrfConvDesc* d, const float* w, const float* bias,
+                     const float* const bn[4], float bn_eps, float* blob_out);
+/* x: [B][H][W][Cin] tokens -> out: [B][Ho][Wo][Cout] tokens */
+int hrf_conv3x3_fwd(const HrfConvDesc* d, const void* x, const float* blob, void* out, void* stream);
+
 typedef struct HrfDwPwDesc {    /* dw3x3 stride 2 pad 1 + BN + 1x1 + BN (+ReLU): one
                                    down-sampling step, hrformer.py:531-557 */
   int32_t B, H, W, Cin, Cout;   /* H, W: INPUT size; output is ceil(H/2) x ceil(W/2) */

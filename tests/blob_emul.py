@@ -168,6 +168,20 @@ def pointwise(x, blob, cout, relu=False):
     return _pw(x.float(), blob, cout, relu).to(x.dtype)
 
 
+def conv3x3(x, blob, cout, stride=1, relu=False):
+    """blob = PwLayout(9*Cin, cout): Wt [Kp][cout], k = tap*Cin + c; then the bias."""
+    blob = blob.float().cpu()
+    Cin = x.shape[-1]
+    K = 9 * Cin
+    Kp = _ru(K, 4)
+    assert blob.numel() == _ru(Kp * cout, 4) + _ru(cout, 4)
+    w = blob[:Kp * cout].view(Kp, cout)[:K].view(3, 3, Cin, cout).permute(3, 2, 0, 1)
+    ob = _ru(Kp * cout, 4)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, blob[ob:ob + cout], stride, 1)
+    y = y.relu() if relu else y
+    return y.permute(0, 2, 3, 1).contiguous().to(x.dtype)
+
+
 def dw_down(x, blob, cout, relu=False):
     blob = blob.float().cpu()
     Cin = x.shape[-1]

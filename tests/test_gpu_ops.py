@@ -210,3 +210,29 @@ def test_stem_conv_tc(built_lib, cin, H, W):
     torch.cuda.synchronize()
     assert got.dtype == torch.bfloat16 and tuple(got.shape) == tuple(ref.shape)
     assert_parity(got, ref, 'bf16', f'stem conv cin={cin}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('cin,cout,stride,H,W,relu', [
+    (18, 36, 2, 96, 160, True), (36, 72, 2, 48, 80, True), (72, 144, 2, 24, 40, True),
+    (18, 36, 2, 33, 47, True), (36, 72, 2, 7, 5, False), (18, 18, 1, 14, 21, True), (72, 144, 2, 1, 1, True),
+    (18, 20, 2, 9, 11, True), (78, 156, 2, 12, 20, True), (14, 32, 1, 6, 5, False)])
+def test_conv3x3(built_lib, cin, cout, stride, H, W, relu, mode):
+    """transition conv (3x3, pad 1, stride 1|2) + eval BN (+ReLU) on tokens vs conv2d"""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from hrfuser_b200 import ops
+    from hrfuser_b200.utils import randomize_parameters
+    conv, bn = nn.Conv2d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout)
+    randomize_parameters(nn.Sequential(conv, bn), cin + cout)
+    bn.eval()
+    B = 2
+    x = tokens(B, H, W, cin, seed=H + W).to(DT[mode])
+    with torch.no_grad():
+        ref = bn(conv(x.float().permute(0, 3, 1, 2)))
+        ref = (F.relu(ref) if relu else ref).permute(0, 2, 3, 1)
+    blob = ops.pack_conv3x3(conv, bn, bn.eps).cuda()
+    got = ops.conv3x3(x.cuda(), blob, cout, stride, relu)
+    torch.cuda.synchronize()
+    assert got.dtype == DT[mode] and tuple(got.shape) == tuple(ref.shape)
+    assert_parity(got, ref, mode, f'conv3x3 {cin}->{cout} s{stride} {H}x{W}')
