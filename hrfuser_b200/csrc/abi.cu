@@ -16,6 +16,7 @@
 #include "window_attn_tc.cuh"
 #include "mixffn_tc.cuh"
 #include "mixffn_tcd.cuh"
+#include "conv3x3_tc.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
 #include "window_attn.cuh"
@@ -425,7 +426,7 @@ int hrf_pw_fwd(const HrfPwDesc* d, const void* x, const float* blob, void* out, 
 
 size_t hrf_conv3x3_blob_floats(const HrfConvDesc* d) {
   if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
-  return (size_t)PwLayout(9 * d->Cin, d->Cout).total;
+  return (size_t)ConvTcLayout(d->Cin, d->Cout).total;
 }
 int hrf_conv3x3_pack(const HrfConvDesc* d, const float* w, const float* bias, const float* const bn[4],
                      float bn_eps, float* blob) {
@@ -436,7 +437,22 @@ int hrf_conv3x3_pack(const HrfConvDesc* d, const float* w, const float* bias, co
   for (int n = 0; n < Cout; ++n)
     for (int c = 0; c < Cin; ++c)
       for (int t = 0; t < 9; ++t) wp[((size_t)n * 9 + t) * Cin + c] = w[((size_t)n * Cin + c) * 9 + t];
-  pack_pw(PwLayout(9 * Cin, Cout), wp.data(), bias, bn, bn_eps, blob);
+  const PwLayout P(9 * Cin, Cout);
+  const ConvTcLayout T(Cin, Cout);
+  std::memset(blob, 0, sizeof(float) * T.total);
+  pack_pw(P, wp.data(), bias, bn, bn_eps, blob);
+  if (T.total > P.total) {
+    // tensor-core section: per tap a bf16 B tile [KC/8][NOUT][8]; row k = Cin of the centre tap
+    // holds the folded bias (it multiplies the constant-1 column of the activation tile)
+    uint16_t* wt = reinterpret_cast<uint16_t*>(blob + T.o_w);
+    for (int t = 0; t < 9; ++t)
+      for (int n = 0; n < Cout; ++n) {
+        uint16_t* tile = wt + (size_t)t * T.NOUT * kConvTcKC;
+        for (int c = 0; c < Cin; ++c)    // folded weight from the fp32 section: Wt[k][n]
+          tile[umma::tile_off(n, c, T.NOUT) / 2] = f32_to_bf16(blob[P.o_w + (size_t)(t * Cin + c) * Cout + n]);
+        if (t == 4) tile[umma::tile_off(n, Cin, T.NOUT) / 2] = f32_to_bf16(blob[P.o_b + n]);
+      }
+  }
   return HRF_OK;
 }
 int hrf_conv3x3_fwd(const HrfConvDesc* d, const void* x, const float* blob, void* out, void* stream) {
@@ -446,8 +462,12 @@ int hrf_conv3x3_fwd(const HrfConvDesc* d, const void* x, const float* blob, void
   p.x = x; p.blob = blob; p.out = out;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.stride = d->stride; p.relu = d->relu;
+  const int rc = conv3x3_prepare(p);
+  if (rc) return rc;
   if (d->dtype == HRF_F32) return launch_conv3x3<float>(p, (cudaStream_t)stream);
-  if (d->dtype == HRF_BF16) return launch_conv3x3<__nv_bfloat16>(p, (cudaStream_t)stream);
+  if (d->dtype == HRF_BF16)
+    return conv3x3_tc_supported(p) ? launch_conv3x3_tc(p, (cudaStream_t)stream)
+                                   : launch_conv3x3<__nv_bfloat16>(p, (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "conv3x3_fwd: dtype");
 }
 

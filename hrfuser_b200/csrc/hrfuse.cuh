@@ -256,8 +256,8 @@ static int launch_conv3x3_direct(const Conv3Params& p, cudaStream_t stream) {
   return HRF_OK;
 }
 
-template <typename T>
-static int launch_conv3x3(Conv3Params p, cudaStream_t stream) {
+// output size + index helpers; call before any conv3x3 launcher
+static int conv3x3_prepare(Conv3Params& p) {
   HRF_REQUIRE(p.Cout % 2 == 0 && p.Cin % 2 == 0, HRF_EUNSUPPORTED,
               "conv3x3: Cin=%d / Cout=%d must be even", p.Cin, p.Cout);
   HRF_REQUIRE(p.stride == 1 || p.stride == 2, HRF_EUNSUPPORTED, "conv3x3: stride %d", p.stride);
@@ -266,6 +266,11 @@ static int launch_conv3x3(Conv3Params p, cudaStream_t stream) {
   p.d_cin = FastDiv(p.Cin);
   p.d_wo = FastDiv(p.Wo);
   p.d_howo = FastDiv(p.Ho * p.Wo);
+  return HRF_OK;
+}
+
+template <typename T>
+static int launch_conv3x3(const Conv3Params& p, cudaStream_t stream) {
   const int ntok = p.B * p.Ho * p.Wo;
   if (p.Cin <= 160 && p.Cout / 6 <= 65535) {   // narrow: the direct kernel
     if (p.Cout % 6 == 0) return launch_conv3x3_direct<T, 6>(p, stream);

@@ -174,7 +174,9 @@ def conv3x3(x, blob, cout, stride=1, relu=False):
     Cin = x.shape[-1]
     K = 9 * Cin
     Kp = _ru(K, 4)
-    assert blob.numel() == _ru(Kp * cout, 4) + _ru(cout, 4)
+    base = _ru(Kp * cout, 4) + _ru(cout, 4)
+    tc = 9 * _ru(cout, 16) * 32 // 2 if Cin == 18 else 0      # bf16 tiles of the tensor-core kernel
+    assert blob.numel() == (_ru(base, 4) + tc if tc else base)
     w = blob[:Kp * cout].view(Kp, cout)[:K].view(3, 3, Cin, cout).permute(3, 2, 0, 1)
     ob = _ru(Kp * cout, 4)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, blob[ob:ob + cout], stride, 1)
