@@ -442,16 +442,19 @@ int hrf_conv3x3_pack(const HrfConvDesc* d, const float* w, const float* bias, co
   std::memset(blob, 0, sizeof(float) * T.total);
   pack_pw(P, wp.data(), bias, bn, bn_eps, blob);
   if (T.total > P.total) {
-    // tensor-core section: per tap a bf16 B tile [KC/8][NOUT][8]; row k = Cin of the centre tap
-    // holds the folded bias (it multiplies the constant-1 column of the activation tile)
+    // tensor-core section: per N split and tap a bf16 B tile [KC/8][NOUT][8]; row k = Cin of the
+    // centre tap holds the folded bias (it multiplies the constant-1 column of the activations)
     uint16_t* wt = reinterpret_cast<uint16_t*>(blob + T.o_w);
-    for (int t = 0; t < 9; ++t)
-      for (int n = 0; n < Cout; ++n) {
-        uint16_t* tile = wt + (size_t)t * T.NOUT * kConvTcKC;
-        for (int c = 0; c < Cin; ++c)    // folded weight from the fp32 section: Wt[k][n]
-          tile[umma::tile_off(n, c, T.NOUT) / 2] = f32_to_bf16(blob[P.o_w + (size_t)(t * Cin + c) * Cout + n]);
-        if (t == 4) tile[umma::tile_off(n, Cin, T.NOUT) / 2] = f32_to_bf16(blob[P.o_b + n]);
-      }
+    const int cper = Cout / T.NSPLIT;
+    for (int sp = 0; sp < T.NSPLIT; ++sp)
+      for (int t = 0; t < 9; ++t)
+        for (int nn = 0; nn < cper; ++nn) {
+          const int n = sp * cper + nn;
+          uint16_t* tile = wt + ((size_t)sp * 9 + t) * T.NOUT * T.KC;
+          for (int c = 0; c < Cin; ++c)    // folded weight from the fp32 section: Wt[k][n]
+            tile[umma::tile_off(nn, c, T.NOUT) / 2] = f32_to_bf16(blob[P.o_w + (size_t)(t * Cin + c) * Cout + n]);
+          if (t == 4) tile[umma::tile_off(nn, Cin, T.NOUT) / 2] = f32_to_bf16(blob[P.o_b + n]);
+        }
   }
   return HRF_OK;
 }

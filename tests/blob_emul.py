@@ -175,7 +175,11 @@ def conv3x3(x, blob, cout, stride=1, relu=False):
     K = 9 * Cin
     Kp = _ru(K, 4)
     base = _ru(Kp * cout, 4) + _ru(cout, 4)
-    tc = 9 * _ru(cout, 16) * 32 // 2 if Cin == 18 else 0      # bf16 tiles of the tensor-core kernel
+    # bf16 tiles of the tensor-core kernel (ConvTcCfg in csrc/conv3x3_tc.cuh)
+    nsplit = 2 if (Cin, cout) == (72, 144) else 1
+    nout, kc = _ru(cout // nsplit, 16), _ru(Cin + 1, 16)
+    ok = (Cin == 18 and nout in (32, 48, 80, 144)) or (Cin, cout) in ((36, 72), (72, 144))
+    tc = nsplit * 9 * nout * kc // 2 if ok else 0
     assert blob.numel() == (_ru(base, 4) + tc if tc else base)
     w = blob[:Kp * cout].view(Kp, cout)[:K].view(3, 3, Cin, cout).permute(3, 2, 0, 1)
     ob = _ru(Kp * cout, 4)
