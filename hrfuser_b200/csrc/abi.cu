@@ -507,8 +507,7 @@ int hrf_fuse_sum_fwd(const HrfFuseDesc* d, const void* x, const void* const* up,
   HRF_REQUIRE(d->n_up >= 0 && d->n_up <= HRF_MAX_FUSE_TERMS && d->n_same >= 0 &&
                   d->n_same <= HRF_MAX_FUSE_TERMS, HRF_EINVAL, "fuse_fwd: term count");
   HRF_REQUIRE((d->n_up == 0 || up) && (d->n_same == 0 || same), HRF_EINVAL, "fuse_fwd: term list");
-  FuseParams p;
-  std::memset(&p, 0, sizeof(p));
+  FuseParams p{};
   p.x = x; p.out = out; p.out_nchw = out_nchw_f32;
   p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.n_up = d->n_up; p.n_same = d->n_same;
   p.relu = d->relu;

@@ -80,10 +80,13 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(Conv3Params p) {
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
   // chunks past the data + bias column are zero padding (written once)
-  for (int e = tid; e < TPP * (KC / 8 - NCH0 - NCH1) * 128; e += 256) {
-    const int tp = e / ((KC / 8 - NCH0 - NCH1) * 128), rest = e - tp * ((KC / 8 - NCH0 - NCH1) * 128);
-    *reinterpret_cast<uint4*>(sA + tp * A_B + (NCH0 + NCH1 + (rest >> 7)) * 2048 + (rest & 127) * 16) =
-        make_uint4(0, 0, 0, 0);
+  constexpr int NZ = KC / 8 - NCH0 - NCH1;           // all-zero chunks per tap
+  if constexpr (NZ > 0) {
+    for (int e = tid; e < TPP * NZ * 128; e += 256) {
+      const int tp = e / (NZ * 128), rest = e - tp * (NZ * 128);
+      *reinterpret_cast<uint4*>(sA + tp * A_B + (NCH0 + NCH1 + (rest >> 7)) * 2048 + (rest & 127) * 16) =
+          make_uint4(0, 0, 0, 0);
+    }
   }
   __syncthreads();                                  // barriers initialised, TMEM address published
   pdl_wait();

@@ -26,6 +26,7 @@ template <typename T> struct Pair;
 template <> struct Pair<float> {
   __device__ static float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
   __device__ static void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+  __device__ static float2 rt(float2 v) { return v; }      // value as stored
 };
 template <> struct Pair<__nv_bfloat16> {
   __device__ static float2 ld(const __nv_bfloat16* p) {
@@ -36,6 +37,7 @@ template <> struct Pair<__nv_bfloat16> {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&h);
   }
+  __device__ static float2 rt(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
 };
 
 struct PwParams {
@@ -387,7 +389,39 @@ struct FuseParams {
   void* out;
   float* out_nchw;
   int B, H, W, C, n_up, n_same, relu;
+  float up_sh[HRF_MAX_FUSE_TERMS], up_sw[HRF_MAX_FUSE_TERMS];   // filled by launch_fuse
+  FastDiv d_hc, d_w, d_h, d_hw;
 };
+
+// value of one (token, channel pair) element: x + same-resolution terms + bilinear gathers
+template <typename T>
+__device__ __forceinline__ float2 fuse_value(const FuseParams& p, int b, int h, int w, size_t off, int c) {
+  float2 v = Pair<T>::ld(static_cast<const T*>(p.x) + off);
+  for (int j = 0; j < p.n_same; ++j) {
+    const float2 a = Pair<T>::ld(static_cast<const T*>(p.same[j]) + off);
+    v.x += a.x; v.y += a.y;
+  }
+  for (int j = 0; j < p.n_up; ++j) {
+    const int ih = p.up_H[j], iw = p.up_W[j];
+    const T* u = static_cast<const T*>(p.up[j]);
+    // align_corners=False, scale = in / out (computed on the host exactly as float(in)/float(out))
+    const float fy = fmaxf(p.up_sh[j] * ((float)h + 0.5f) - 0.5f, 0.f);
+    const float fx = fmaxf(p.up_sw[j] * ((float)w + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)fy, ih - 1), x0 = min((int)fx, iw - 1);
+    const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
+    const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const T* ub = u + (size_t)b * ih * iw * p.C + c;
+    const float2 v00 = Pair<T>::ld(ub + (size_t)(y0 * iw + x0) * p.C);
+    const float2 v01 = Pair<T>::ld(ub + (size_t)(y0 * iw + x1) * p.C);
+    const float2 v10 = Pair<T>::ld(ub + (size_t)(y1 * iw + x0) * p.C);
+    const float2 v11 = Pair<T>::ld(ub + (size_t)(y1 * iw + x1) * p.C);
+    v.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    v.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+  }
+  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+  return v;
+}
 
 // thread = (token, channel pair); 32-bit index math (tensors are < 2^31 elements)
 template <typename T>
@@ -397,51 +431,75 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
   const int hc = p.C / 2;
   const int total = p.B * p.H * p.W * hc;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int t = e / hc, c = (e - t * hc) * 2;
-    const int w = t % p.W, hb = t / p.W, h = hb % p.H, b = hb / p.H;
-    const size_t off = (size_t)t * p.C + c;
-    float2 v = Pair<T>::ld(static_cast<const T*>(p.x) + off);
-    for (int j = 0; j < p.n_same; ++j) {
-      const float2 a = Pair<T>::ld(static_cast<const T*>(p.same[j]) + off);
-      v.x += a.x; v.y += a.y;
-    }
-    for (int j = 0; j < p.n_up; ++j) {
-      const int ih = p.up_H[j], iw = p.up_W[j];
-      const T* u = static_cast<const T*>(p.up[j]);
-      const float sh = (float)ih / (float)p.H, sw = (float)iw / (float)p.W;
-      const float fy = fmaxf(sh * ((float)h + 0.5f) - 0.5f, 0.f);
-      const float fx = fmaxf(sw * ((float)w + 0.5f) - 0.5f, 0.f);
-      const int y0 = min((int)fy, ih - 1), x0 = min((int)fx, iw - 1);
-      const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
-      const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      const size_t base = (size_t)b * ih * iw;
-      const float2 v00 = Pair<T>::ld(u + ((base + (size_t)y0 * iw + x0) * p.C + c));
-      const float2 v01 = Pair<T>::ld(u + ((base + (size_t)y0 * iw + x1) * p.C + c));
-      const float2 v10 = Pair<T>::ld(u + ((base + (size_t)y1 * iw + x0) * p.C + c));
-      const float2 v11 = Pair<T>::ld(u + ((base + (size_t)y1 * iw + x1) * p.C + c));
-      v.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-      v.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    }
-    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+    int t, c2, hb, w, b, h;
+    p.d_hc.divmod(e, t, c2);
+    p.d_w.divmod(t, hb, w);
+    p.d_h.divmod(hb, b, h);
+    const size_t off = (size_t)t * p.C + 2 * c2;
+    const float2 v = fuse_value<T>(p, b, h, w, off, 2 * c2);
     Pair<T>::st(static_cast<T*>(p.out) + off, v.x, v.y);
-    if (p.out_nchw) {
-      // round through the storage type so both copies hold the same values
-      const float2 vs = Pair<T>::ld(static_cast<const T*>(p.out) + off);
-      const size_t o = (((size_t)b * p.C + c) * p.H + h) * p.W + w;
-      p.out_nchw[o] = vs.x;
-      p.out_nchw[o + (size_t)p.H * p.W] = vs.y;
+  }
+}
+
+// Variant that also writes the fp32 NCHW copy (the backbone's four outputs): a CTA owns
+// kFuseTok consecutive tokens, keeps the values (rounded through the storage type, so both
+// copies agree) in shared memory [C][tokens] and writes every channel's run of tokens as one
+// contiguous segment -- the direct form scatters 4-byte writes H*W*4 bytes apart.
+constexpr int kFuseTok = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_sum_nchw_kernel(FuseParams p) {
+  extern __shared__ float sv[];                      // [C][kFuseTok + 1]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int hc = p.C / 2, ntok = p.B * p.H * p.W, hw = p.H * p.W;
+  const int t0 = blockIdx.x * kFuseTok;
+  const int m = min(kFuseTok, ntok - t0);
+  for (int e = threadIdx.x; e < m * hc; e += blockDim.x) {
+    int r, c2, hb, w, b, h;
+    p.d_hc.divmod(e, r, c2);
+    const int t = t0 + r;
+    p.d_w.divmod(t, hb, w);
+    p.d_h.divmod(hb, b, h);
+    const size_t off = (size_t)t * p.C + 2 * c2;
+    const float2 v = fuse_value<T>(p, b, h, w, off, 2 * c2);
+    Pair<T>::st(static_cast<T*>(p.out) + off, v.x, v.y);
+    const float2 vs = Pair<T>::rt(v);                // as stored
+    sv[(2 * c2) * (kFuseTok + 1) + r] = vs.x;
+    sv[(2 * c2 + 1) * (kFuseTok + 1) + r] = vs.y;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < p.C * kFuseTok; e += blockDim.x) {
+    const int c = e / kFuseTok, r = e - c * kFuseTok;
+    if (r < m) {
+      const int t = t0 + r;
+      const int b = p.d_hw.div(t), thw = t - b * hw;
+      p.out_nchw[((size_t)b * p.C + c) * hw + thw] = sv[c * (kFuseTok + 1) + r];
     }
   }
 }
 
 template <typename T>
-static int launch_fuse(const FuseParams& p, cudaStream_t stream) {
+static int launch_fuse(FuseParams p, cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.H * p.W * (p.C / 2);
   HRF_REQUIRE(p.C % 2 == 0 && total * 2 < ((size_t)1 << 31), HRF_EUNSUPPORTED,
               "fuse_sum: C=%d must be even and the tensor below 2^31 elements", p.C);
-  const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  HRF_CUDA(launch_pdl(fuse_sum_kernel<T>, dim3(grid), dim3(256), 0, stream, p));
+  p.d_hc = FastDiv(p.C / 2);
+  p.d_w = FastDiv(p.W);
+  p.d_h = FastDiv(p.H);
+  p.d_hw = FastDiv(p.H * p.W);
+  for (int j = 0; j < p.n_up; ++j) {
+    p.up_sh[j] = (float)p.up_H[j] / (float)p.H;
+    p.up_sw[j] = (float)p.up_W[j] / (float)p.W;
+  }
+  if (p.out_nchw) {
+    const size_t smem = (size_t)p.C * (kFuseTok + 1) * sizeof(float);
+    HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T>, smem));
+    const int ntok = p.B * p.H * p.W;
+    HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T>, dim3(ceil_div(ntok, kFuseTok)), dim3(256), smem, stream, p));
+  } else {
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    HRF_CUDA(launch_pdl(fuse_sum_kernel<T>, dim3(grid), dim3(256), 0, stream, p));
+  }
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
