@@ -26,10 +26,11 @@ struct StemParams {
   const float* blob;
   __nv_bfloat16* out;  // (B, Ho, Wo, Cout) bf16
   int B, Cin, H, W, Ho, Wo, Cout, relu;
+  FastDiv d_wo, d_ho;  // filled by launch_stem_conv
 };
 
 template <int COUT>
-__global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
+__global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
   using namespace umma;
   static_assert(COUT % 16 == 0 && COUT <= 256, "Cout");
   constexpr int TCOLS = COUT <= 32 ? 32 : COUT <= 64 ? 64 : COUT <= 128 ? 128 : 256;
@@ -63,14 +64,14 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
   const int n_tiles = ceil_div(n_pix, 128);
   const size_t plane = (size_t)p.H * p.W;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int pix = tile * 128 + tid;
-    // ---- gather this pixel's 3x3xCin patch (k = (ci*3 + ky)*3 + kx) -----------------
-    float v[32];
+  // this pixel's 3x3xCin patch (k = (ci*3 + ky)*3 + kx), zero outside the image / the tensor
+  auto gather = [&](int pix, float* v) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    for (int k = 0; k < 27; ++k) v[k] = 0.f;
     if (pix < n_pix) {
-      const int ox = pix % p.Wo, t = pix / p.Wo, oy = t % p.Ho, b = t / p.Ho;
+      int ox, t, oy, b;
+      p.d_wo.divmod(pix, t, ox);
+      p.d_ho.divmod(t, b, oy);
       const float* xb = p.x + (size_t)b * p.Cin * plane;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
@@ -88,6 +89,16 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
         }
       }
     }
+  };
+  // software pipeline: the next tile's patch is requested before this tile's MMA / epilogue
+  float vn[27];
+  gather(blockIdx.x * 128 + tid, vn);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int pix = tile * 128 + tid;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < 27 ? vn[k] : 0.f;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) st_chunk(sA, tid, ch, 128, v + 8 * ch);
     fence_proxy_async();
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(128) stem_conv_tc_kernel(StemParams p) {
       mma_bf16(tmem, desc_kmajor(a_a, 128, 1), desc_kmajor(a_w, COUT, 1), id, true);
       mma_commit(&bar);
     }
+    gather((tile + gridDim.x) * 128 + tid, vn);     // lands behind the MMA and the epilogue
     cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -142,8 +154,13 @@ static int launch_stem_conv(const StemParams& p, cudaStream_t stream) {
   HRF_REQUIRE(p.Cin >= 1 && p.Cin <= 3, HRF_EUNSUPPORTED, "stem_conv: Cin=%d (1..3)", p.Cin);
   HRF_REQUIRE(p.Cout == 64, HRF_EUNSUPPORTED, "stem_conv: Cout=%d (64)", p.Cout);
   const int n_tiles = ceil_div(p.B * p.Ho * p.Wo, 128);
-  const int grid = n_tiles < 148 * 8 ? n_tiles : 148 * 8;
-  stem_conv_tc_kernel<64><<<grid, 128, 0, stream>>>(p);
+  // persistent: exactly the CTAs that are resident at once (6 per SM by registers); a larger
+  // grid runs as a full wave plus a mostly idle second one
+  const int grid = n_tiles < 148 * 6 ? n_tiles : 148 * 6;
+  StemParams q = p;
+  q.d_wo = FastDiv(p.Wo);
+  q.d_ho = FastDiv(p.Ho);
+  stem_conv_tc_kernel<64><<<grid, 128, 0, stream>>>(q);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;

@@ -45,11 +45,28 @@ class _Conv:
         if extra_bias is not None:
             b = b + extra_bias
         self.has_bias = use_bias and (conv.bias is not None or bn is not None or extra_bias is not None)
+        self.stride, self.padding, self.groups, self.relu = conv.stride, conv.padding, conv.groups, relu
+        # cuDNN has no good kernel for output widths like 18 / 36 (it falls back to slower
+        # engines plus nhwcAddPadding passes: 65.6 -> 43.5 us and 33.7 -> 17.7 us for the
+        # 256 -> 18 / 36 transitions, tools/probe_trans1.py): compute zero-padded output
+        # channels and slice them off afterwards
+        self.cout = self.w.shape[0]
+        if self.w.is_cuda and self.cout % 8 != 0 and self.groups == 1:
+            padded = (self.cout + 15) // 16 * 16
+            w = self.w.new_zeros((padded,) + tuple(self.w.shape[1:]))
+            w[:self.cout] = self.w
+            self.w = w.contiguous(memory_format=torch.channels_last)
+            b = torch.cat([b, b.new_zeros(padded - self.cout)])
         self.b = b if self.has_bias else None
         self.b32 = b.float() if self.has_bias else None
-        self.stride, self.padding, self.groups, self.relu = conv.stride, conv.padding, conv.groups, relu
 
     def __call__(self, x, residual=None):
+        y = self._run(x, residual)
+        if y.shape[1] != self.cout:
+            y = y[:, :self.cout].contiguous(memory_format=torch.channels_last)
+        return y
+
+    def _run(self, x, residual=None):
         if x.is_cuda and self.relu and self.has_bias:
             if residual is None:
                 return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding,
