@@ -43,7 +43,24 @@ cudaError_t ensure_smem(const void* kern, size_t bytes) {
   auto it = done.find(kern);
   if (it != done.end() && it->second >= bytes) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // ask for the largest shared-memory carve-out: the driver's default split sizes it for ONE
+  // CTA of the kernel, which can leave room for fewer co-resident CTAs than the kernel was
+  // designed for (HRF_CARVEOUT=0 keeps the driver default, for A/B runs)
+  static const bool carve = [] { const char* v = std::getenv("HRF_CARVEOUT"); return !(v && v[0] == '0'); }();
+  if (e == cudaSuccess && carve)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) done[kern] = bytes;
+  // HRF_DEBUG_OCC=<threads>: print the resident CTAs per SM the runtime predicts for this kernel
+  static const int occ_threads = [] { const char* v = std::getenv("HRF_DEBUG_OCC"); return v ? std::atoi(v) : 0; }();
+  if (e == cudaSuccess && occ_threads > 0) {
+    int nb = -1;
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, kern);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, fa.maxThreadsPerBlock < occ_threads ? fa.maxThreadsPerBlock : occ_threads, bytes);
+    std::fprintf(stderr, "[hrf occ] kernel %p regs %d static smem %zu dyn smem %zu maxThreads %d -> %d CTAs/SM (at %d threads)\n",
+                 kern, fa.numRegs, fa.sharedSizeBytes, bytes, fa.maxThreadsPerBlock, nb,
+                 fa.maxThreadsPerBlock < occ_threads ? fa.maxThreadsPerBlock : occ_threads);
+  }
   return e;
 }
 // HRF_DISABLE_TC=1 routes bf16 problems to the SIMT kernels (A/B comparisons)
@@ -588,6 +605,11 @@ int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, co
 
 #ifdef HRF_KERNEL_PROFILE
 // instrumented build only: phase cycle counters (see common.cuh)
+extern "C" int hrf_debug_prof_cta(unsigned long long* out, int n) {
+  using namespace hrf;
+  HRF_CUDA(cudaMemcpyFromSymbol(out, g_prof_cta, sizeof(unsigned long long) * n));
+  return HRF_OK;
+}
 extern "C" int hrf_debug_prof(unsigned long long* out, int n, int reset) {
   using namespace hrf;
   if (out) HRF_CUDA(cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * n));

@@ -13,7 +13,25 @@ namespace hrf {
 // by hrf_debug_prof().  Compiled out of the product library.
 #ifdef HRF_KERNEL_PROFILE
 __device__ unsigned long long g_prof[2048 * 16];
-#define HRF_PROF_DECL long long pt_ = clock64();
+__device__ unsigned long long g_prof_cta[2048 * 4];      // per CTA: SM id, globaltimer start / end
+__device__ __forceinline__ unsigned long long prof_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void prof_cta_begin() {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_prof_cta[(blockIdx.x & 2047) * 4 + 0] = smid;
+    g_prof_cta[(blockIdx.x & 2047) * 4 + 1] = prof_gtime();
+  }
+}
+__device__ __forceinline__ void prof_cta_end() {
+  if (threadIdx.x == 0) g_prof_cta[(blockIdx.x & 2047) * 4 + 2] = prof_gtime();
+}
+#define HRF_PROF_DECL long long pt_ = clock64(); prof_cta_begin();
+#define HRF_PROF_END prof_cta_end();
 #define HRF_PROF(k)                                                       \
   if (threadIdx.x == 0) {                                                 \
     const long long now_ = clock64();                                     \
@@ -24,6 +42,7 @@ __device__ unsigned long long g_prof[2048 * 16];
   if (threadIdx.x == 0) g_prof[(blockIdx.x & 2047) * 16 + 15] += 1;
 #else
 #define HRF_PROF_DECL
+#define HRF_PROF_END
 #define HRF_PROF(k)
 #define HRF_PROF_TILE
 #endif

@@ -461,6 +461,7 @@ mixffn_tc_kernel(FfnParams p) {
     // before the next fc1 / fc2 MMAs; the XN tiles were released by the fc2 wait above.
   }
 
+  HRF_PROF_END
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);

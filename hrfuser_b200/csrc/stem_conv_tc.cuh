@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
   __shared__ float sBias[COUT];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
+  HRF_PROF_DECL
   const int tid = threadIdx.x, warp = warp_idx_uniform();
   const StemLayout L(p.Cin, COUT);
   {
@@ -94,16 +95,20 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
   float vn[27];
   gather(blockIdx.x * 128 + tid, vn);
 
+  HRF_PROF(14)                                     // setup + first gather
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    HRF_PROF_TILE
     const int pix = tile * 128 + tid;
     float v[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = k < 27 ? vn[k] : 0.f;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) st_chunk(sA, tid, ch, 128, v + 8 * ch);
+    HRF_PROF(0)                                    // patch -> operand tile (waits for the loads)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    HRF_PROF(1)
     if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t id = idesc_bf16(128, COUT, false, false);
@@ -111,10 +116,13 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
       mma_bf16(tmem, desc_kmajor(a_a, 128, 1), desc_kmajor(a_w, COUT, 1), id, true);
       mma_commit(&bar);
     }
+    HRF_PROF(2)                                    // MMA issue
     gather((tile + gridDim.x) * 128 + tid, vn);     // lands behind the MMA and the epilogue
+    HRF_PROF(3)                                    // next tile's loads issued
     cta_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
+    HRF_PROF(4)                                    // MMA wait
     // ---- epilogue: + bias, ReLU, bf16, 16-byte stores (one 2*COUT-byte row per thread) --
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 32) {
@@ -141,10 +149,13 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
         }
       }
     }
+    HRF_PROF(5)                                    // epilogue
     // the barrier before the next MMA orders these TMEM reads and the sA rewrite
     tc_fence_before();
     __syncthreads();
+    HRF_PROF(6)
   }
+  HRF_PROF_END
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
@@ -157,6 +168,7 @@ static int launch_stem_conv(const StemParams& p, cudaStream_t stream) {
   // persistent: exactly the CTAs that are resident at once (6 per SM by registers); a larger
   // grid runs as a full wave plus a mostly idle second one
   const int grid = n_tiles < 148 * 6 ? n_tiles : 148 * 6;
+  HRF_CUDA(ensure_smem((const void*)stem_conv_tc_kernel<64>, 0));
   StemParams q = p;
   q.d_wo = FastDiv(p.Wo);
   q.d_ho = FastDiv(p.Ho);

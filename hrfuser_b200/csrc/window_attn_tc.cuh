@@ -687,6 +687,7 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
     // the next iteration's first barrier orders these TMEM reads before its MMAs
   }
 
+  HRF_PROF_END
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, K::TMEM_COLS);

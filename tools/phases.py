@@ -32,17 +32,28 @@ NAMES = {
              'out epilogue'],
 }
 ap = argparse.ArgumentParser()
-ap.add_argument('--kind', default='ffn', choices=['ffn', 'lsa', 'mwca'])
+ap.add_argument('--kind', default='ffn', choices=['ffn', 'lsa', 'mwca', 'stem'])
 ap.add_argument('--C', type=int, default=18)
 ap.add_argument('--batch', type=int, default=8)
 a = ap.parse_args()
 lib = _lib.load()
 lib.hrf_debug_prof.argtypes = [C.c_void_p, C.c_int, C.c_int]
+if a.kind == 'stem':
+    a.C = 18
 k = [w for w, _ in WIDTHS].index(a.C)
 (H, W), (Cc, heads) = GRIDS['nus'][k], WIDTHS[k]
 e = stub()
 x = torch.randn(a.batch, H, W, Cc, device='cuda').to(torch.bfloat16)
-if a.kind == 'ffn':
+if a.kind == 'stem':
+    import torch.nn as nn
+    from hrfuser_b200.utils import randomize_parameters
+    conv, bn = nn.Conv2d(3, 64, 3, 2, 1, bias=False), nn.BatchNorm2d(64)
+    randomize_parameters(nn.Sequential(conv, bn), 3)
+    sblob = ops.pack_stem(conv, bn, bn.eps).cuda()
+    img = torch.randn(a.batch, 3, 384, 640, device='cuda')
+    fn = lambda: ops.stem_conv(img, sblob, 64)
+    names = ['patch -> tile', 'sync', 'MMA issue', 'next loads', 'MMA wait', 'epilogue', 'sync'] + ['-'] * 7
+elif a.kind == 'ffn':
     blk, _ = make_block('lsa', Cc, heads)
     f = e._ffn(blk.norm2, blk.ffn)
     e._upload()
@@ -85,3 +96,27 @@ for j in range(14):
     if v > 0:
         print(f'  {names[j]:16s} {v:9.0f} cycles / tile')
 print(f'  {"total":16s} {tot:9.0f} cycles / tile;  setup {t[:, 14].mean() / n_it:.0f} cycles / CTA')
+
+# residency: SM id and globaltimer lifetime of every CTA of the LAST launch
+lib.hrf_debug_prof_cta.argtypes = [C.c_void_p, C.c_int]
+cb = np.zeros(2048 * 4, dtype=np.uint64)
+lib.hrf_debug_prof_cta(cb.ctypes.data, cb.size)
+cta = cb.reshape(2048, 4)[:len(t)].astype(np.int64)
+t_begin = cta[:, 1].min()
+span = (cta[:, 2].max() - t_begin) / 1e3
+per_sm = {}
+for smid, a0, a1, _ in cta:
+    per_sm.setdefault(int(smid), []).append((int(a0 - t_begin), int(a1 - t_begin)))
+peak = []
+for smid, iv in per_sm.items():
+    ev = sorted([(a0, 1) for a0, _ in iv] + [(a1, -1) for _, a1 in iv])
+    cur = mx = 0
+    for _, d in ev:
+        cur += d
+        mx = max(mx, cur)
+    peak.append(mx)
+life = (cta[:, 2] - cta[:, 1]) / 1e3
+starts = np.sort(cta[:, 1] - t_begin) / 1e3
+print(f'  last launch: first CTA start -> last CTA end {span:.1f} us; {len(per_sm)} SMs used; co-resident CTAs per SM '
+      f'max {max(peak)} / min {min(peak)}; CTA lifetime mean {life.mean():.1f} us max {life.max():.1f} us; '
+      f'CTA start times: median {np.median(starts):.1f} us, 90 % {np.percentile(starts, 90):.1f} us, last {starts[-1]:.1f} us')
