@@ -69,6 +69,10 @@ struct AttnTc {
   static constexpr int PROJ_COLS = 3 * NQG > NOUT ? 3 * NQG : NOUT;
   static constexpr int TMEM_COLS = (PROJ_COLS <= 128) ? 128 : (PROJ_COLS <= 256 ? 256 : 512);
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  // CTAs that are resident per SM (shared memory incl. ~1 KB static + 1 KB reserved, TMEM
+  // columns): the persistent grid is sized to exactly one wave of them
+  static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 2048), BY_TMEM = 512 / TMEM_COLS;
+  static constexpr int CTAS_PER_SM = BY_SMEM < 1 ? 1 : (BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM);
 };
 
 // one token row: C bf16 -> fp32 registers, widest aligned vector loads
@@ -734,8 +738,11 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
   const int n_tiles = (n_windows + 1) / 2;
   // debug knob: HRF_ATTN_CTAS_PER_SM limits the persistent grid (occupancy experiments)
-  static const int per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
-  const int per_group = n_tiles < 148 * per_sm / NG ? n_tiles : 148 * per_sm / NG;   // <= 4 CTAs / SM (TMEM)
+  static const int env_per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 0; }();
+  const int fit = p.cross ? AttnTc<C, HEADS, HG, true>::CTAS_PER_SM : AttnTc<C, HEADS, HG, false>::CTAS_PER_SM;
+  const int per_sm = env_per_sm > 0 ? env_per_sm : fit;
+  const int cap = 148 * per_sm / NG > 0 ? 148 * per_sm / NG : 1;
+  const int per_group = n_tiles < cap ? n_tiles : cap;      // one resident wave
   const int grid = per_group * NG;
   if (NG > 1) HRF_REQUIRE(p.ws != nullptr, HRF_EINVAL, "attn_tc: workspace required for C=%d", C);
   HRF_REQUIRE((reinterpret_cast<uintptr_t>(p.blob) & 15) == 0, HRF_EINVAL, "attn_tc: blob must be 16-byte aligned");
