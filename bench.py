@@ -199,26 +199,43 @@ def run_ours(args):
         host_sets.append([t.pin_memory() for t in (x, *mods)])
     dev_sets = [[t.to(dev) for t in hs] for hs in host_sets]
 
-    # ---- one CUDA graph per input set, shared memory pool --------------------
+    # ---- one CUDA graph per input set -------------------------------------------
+    # HRF_STEPS_IN_FLIGHT=n > 1 (experiment): n independent steps replay concurrently on n
+    # streams (private memory pools); the default 1 runs the steps back to back.
+    n_fly = max(1, int(os.environ.get('HRF_STEPS_IN_FLIGHT', '1')))
     graphs, pool = [], None
     for ds in dev_sets:
-        g = GraphedForward(engine, ds[0], ds[1:], pool=pool)
+        g = GraphedForward(engine, ds[0], ds[1:], pool=None if n_fly > 1 else pool)
         pool = pool or g.pool()
         graphs.append(g)
     launches_per_step = graphs[0].launches
+    fly_streams = [torch.cuda.Stream() for _ in range(n_fly)] if n_fly > 1 else None
     torch.cuda.synchronize()
 
+    def run_steps(n):
+        if fly_streams is None:
+            for i in range(n):
+                graphs[i % R]()
+            return
+        cur = torch.cuda.current_stream()
+        for st in fly_streams:
+            st.wait_stream(cur)
+        for i in range(n):
+            gi = i % R
+            with torch.cuda.stream(fly_streams[gi % n_fly]):
+                graphs[gi]()
+        for st in fly_streams:
+            cur.wait_stream(st)
+
     # ---- (a) device-resident throughput -----------------------------------------
-    for i in range(Wm):
-        graphs[i % R]()
+    run_steps(Wm)
     torch.cuda.synchronize()
     hdist.barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     t_wall = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        graphs[i % R]()
+    run_steps(K)
     e1.record()
     torch.cuda.synchronize()
     hdist.barrier()
