@@ -174,6 +174,38 @@ def test_error_paths(built_lib):
         ops.window_attention(x, None, [blob], heads=4)
     with pytest.raises(_lib.HrfError, match='alias'):
         ops.mixffn(x, blob, 72, out=x)
+    with pytest.raises(_lib.HrfError, match='stride'):
+        ops.conv3x3(x, blob, 18, stride=3)
+    with pytest.raises(_lib.HrfError, match='even'):
+        ops.conv3x3(torch.zeros(1, 7, 7, 17, device='cuda'), blob, 18)
+
+
+def test_programmatic_dependent_launch(built_lib):
+    """hrf_set_pdl(1): a chain lsa -> mixffn -> lsa launched with programmatic stream
+    serialization (each kernel's prologue overlaps its predecessor's tail) gives the same bits"""
+    from hrfuser_b200 import ops
+    blk, sd = make_block('lsa', 18, 1)
+    e = _engine_stub()
+    pk = e._hrformer_block(blk)
+    e._upload()
+    blobs, f = [s.t for s in pk['attn']], pk['ffn']
+    x = tokens(2, 33, 47, 18, seed=5).to(torch.bfloat16).cuda()
+
+    def chain():
+        y = x
+        for _ in range(3):
+            y = ops.window_attention(y, None, blobs, 1)
+            y = ops.mixffn(y, f['blob'].t, f['hidden'], f['eps'])
+        torch.cuda.synchronize()
+        return y
+    was = ops.set_pdl(False)
+    try:
+        ref = chain()
+        assert ops.set_pdl(True) is False
+        got = chain()
+    finally:
+        ops.set_pdl(was)
+    assert torch.equal(ref, got)
 
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
