@@ -352,8 +352,8 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
       float* fb = f + (size_t)ch * 880;                       // b1[80] | wd[9][80] | bd[80]
       uint16_t* w1t = tile1 + (size_t)ch * 80 * KC;           // B of fc1: rows = hidden ch, K = C
       uint16_t* w2t = tile2 + (size_t)ch * NOUT * 80;         // B of fc2: rows = out ch, K = hidden ch
-      for (int jj = 0; jj < 72; ++jj) {
-        const int j = ch * 72 + jj;
+      for (int jj = 0; jj < L.tc_CH; ++jj) {
+        const int j = ch * L.tc_CH + jj;
         fb[jj] = (b1 ? b1[j] : 0.f) * s1[j] + t1[j];
         for (int t = 0; t < 9; ++t) fb[80 + t * 80 + jj] = wd[(size_t)j * 9 + t] * s2[j];
         fb[800 + jj] = (bd ? bd[j] : 0.f) * s2[j] + t2[j];
@@ -369,13 +369,13 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
     float* b2p = f + (size_t)L.tc_nchunk * 880;
     for (int c = 0; c < C; ++c) {
       b2p[c] = (b2 ? b2[c] : 0.f) * s3[c] + t3[c];
-      // fc2 bias row: K index 72 (first padding channel of the chunk) of the FIRST chunk's W2
+      // fc2 bias row: K index CH (first padding channel of the chunk) of the FIRST chunk's W2
       // tile; the kernels keep a constant 1 in that column of the hidden activations
-      tile2[umma::tile_off(c, 72, NOUT) / 2] = f32_to_bf16(b2p[c]);
+      tile2[umma::tile_off(c, L.tc_CH, NOUT) / 2] = f32_to_bf16(b2p[c]);
     }
     // depthwise-conv tiles (see FfnLayout::o_tc_dg)
     uint16_t* dg = reinterpret_cast<uint16_t*>(blob + L.o_tc_dg);
-    for (int ch = 0; ch < L.tc_nchunk; ++ch) {
+    for (int ch = 0; ch < (L.tc_CH == 72 ? L.tc_nchunk : 0); ++ch) {   // experimental kernel: 72 only
       const float* fb = f + (size_t)ch * 880;
       for (int s = 0; s < 5; ++s)
         for (int n = 0; n < 16; ++n) {

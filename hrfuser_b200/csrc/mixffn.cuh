@@ -32,11 +32,13 @@ struct FfnLayout {
     o_w2 = o; o += hidden * C; o = round_up(o, 4);         // W2t [hidden][C]
     o_b2 = o; o += c4;
     // tensor-core (bf16) sections, present when hidden splits into chunks of 72
-    // channels (every HRFuser-T width): per chunk, fp32 b1[80] | wd[9][80] | bd[80]
-    // (zero padded 72 -> 80), then b2[NOUT]; then bf16 operand tiles in the
+    // (HRFuser-T) or 78 (HRFuser-B) channels: per chunk, fp32 b1[80] | wd[9][80] | bd[80]
+    // (zero padded to 80), then b2[NOUT]; then bf16 operand tiles in the
     // chunk-major layout of umma.cuh: W1 [KC/8][80][8] and W2 [80/8][NOUT][8] per chunk.
     tc_KC = round_up(C, 16); tc_NOUT = tc_KC;
-    tc_nchunk = (hidden % 72 == 0) ? hidden / 72 : 0;
+    // chunk width: 72 hidden channels (HRFuser-T widths, hidden = 4 * 18k) or 78 (HRFuser-B)
+    tc_CH = (hidden % 72 == 0) ? 72 : (hidden % 78 == 0) ? 78 : 0;
+    tc_nchunk = tc_CH ? hidden / tc_CH : 0;
     o_tc_f32 = o; o += tc_nchunk * (11 * 80) + (tc_nchunk ? tc_NOUT : 0);
     o = round_up(o, 4);
     o_tc_w1 = o; o += tc_nchunk * 80 * tc_KC / 2;
@@ -49,7 +51,7 @@ struct FfnLayout {
     ldx = stride4odd(Cp);
     ldh = stride4odd(HC);
   }
-  int tc_KC, tc_NOUT, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2, o_tc_dg;
+  int tc_KC, tc_NOUT, tc_CH, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2, o_tc_dg;
 };
 
 constexpr int kFfnThreads = 256;

@@ -38,9 +38,14 @@ namespace hrf {
 // domains) per SM, the wider variants two.
 template <int C, int CPG>
 struct FfnTc {
-  static constexpr int HID = 4 * C, NCH = HID / 72, NG = NCH / CPG;
+  // hidden channels per chunk: 72 (HRFuser-T widths 18k) or 78 (HRFuser-B widths 78k); both
+  // are padded to N1 = 80 MMA columns, the first padding column (72 | 78) carries the constant 1
+  static constexpr int CH = (C % 18 == 0) ? 72 : 78;
+  static constexpr int HID = 4 * C, NCH = HID / CH, NG = NCH / CPG;
   static constexpr bool SPLIT = CPG < NCH, BIGC = C > 40;
-  static_assert(HID % 72 == 0 && NCH % CPG == 0, "hidden must split into 72-channel chunks");
+  static_assert(HID % CH == 0 && NCH % CPG == 0, "hidden must split into 72- or 78-channel chunks");
+  static constexpr int NDC = (CH + 7) / 8;           // 8-channel data chunks per hidden chunk: 9 | 10
+  static constexpr int ONE_CHUNK = CH / 8, ONE_ELEM = CH % 8;    // where the constant 1 lives in H2
   static constexpr int KC = (C + 15) / 16 * 16, NOUT = KC, N1 = 80;
   static constexpr int TH = 6, TW = 14;
   static constexpr int HH = TH + 2, HW = TW + 2, NHALO = HH * HW;      // 128
@@ -54,7 +59,7 @@ struct FfnTc {
   // the epilogue needs neither a bias add nor the outside-the-image select (zero rows give
   // GELU(0) = 0).  Needs a spare K column (not C = 144).
   static constexpr bool BIAS_MMA = KC > C;
-  static constexpr int H1_B = 9 * H1R * 16;          // GELU(fc1) on the halo, bf16
+  static constexpr int H1_B = NDC * H1R * 16;        // GELU(fc1) on the halo, bf16
   // H2 = fc2 A operand: NTOK live rows; the M=128 MMA also reads (and ignores) the rows up to
   // 127, which alias the next chunk / the bytes behind the tile
   static constexpr int H2R = (NTOK + 7) / 8 * 8;     // 88
@@ -121,6 +126,13 @@ __device__ __forceinline__ void gelu8(float* v) {
   }
 }
 
+// 16-byte H2 chunk that holds only the constant 1 (bf16) at element `elem`
+__device__ __forceinline__ uint4 one_chunk(int elem) {
+  const uint32_t w = (elem & 1) ? 0x3F800000u : 0x00003F80u;
+  const int i = elem >> 1;
+  return make_uint4(i == 0 ? w : 0u, i == 1 ? w : 0u, i == 2 ? w : 0u, i == 3 ? w : 0u);
+}
+
 // Warp w reads TMEM lanes 32*(w%4).. (its quadrant q) and belongs to group gq = w/4.
 // Epilogue and depthwise work is dealt out in units of (row, 8-channel chunk) so all groups of
 // a quadrant stay busy and no thread holds more than 8 accumulators (<= 64 registers).
@@ -171,7 +183,7 @@ mixffn_tc_kernel(FfnParams p) {
     // channel 72 that multiplies the b2 row of the W2 tile
     uint4* z = reinterpret_cast<uint4*>(sm + K::o_h2);
     for (int e = tid; e < K::H2_B / 16; e += NT)
-      z[e] = (e >= 9 * K::H2R && e < 10 * K::H2R) ? make_uint4(0x00003F80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+      z[e] = (e >= 9 * K::H2R && e < 10 * K::H2R) ? one_chunk(K::ONE_ELEM) : make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   bool w_ready = false;                            // bulk copies observed complete
@@ -191,7 +203,7 @@ mixffn_tc_kernel(FfnParams p) {
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
   // epilogue-1 units of this quadrant: (M tile mt, chunk 0..8) for every M tile that has live
   // halo rows in this quadrant
-  const int n_units = 9 * ((K::NHALO - q * 32 + 127) / 128);
+  const int n_units = K::NDC * ((K::NHALO - q * 32 + 127) / 128);
 
   // Software pipeline (C <= 40): the halo token of the NEXT tile is requested while the
   // current tile computes; no thread waits on global memory with the CTA behind it.  There a
@@ -306,7 +318,7 @@ mixffn_tc_kernel(FfnParams p) {
       const float* fb = sF + c * 880;
 #pragma unroll 1
       for (int u = gq; u < n_units; u += NGQ) {       // warp-uniform trip count
-        const int mt = u >= 9 ? 1 : 0, ch = u - mt * 9;
+        const int mt = u >= K::NDC ? 1 : 0, ch = u - mt * K::NDC;
         float v[8];
         tmem_ld8(trow + mt * N1 + ch * 8, v);
         tmem_ld_wait();
@@ -340,9 +352,9 @@ mixffn_tc_kernel(FfnParams p) {
         // the multiply-adds are packed fp32x2 (FFMA2).  Lane pairs cover the two halves of one
         // token's 16-byte chunk, so a warp's 8-byte accesses are contiguous.
         constexpr int SH = K::SH;
-        constexpr int NUNIT = 9 * K::NSTRIP * K::TW * 2;
+        constexpr int NUNIT = K::NDC * K::NSTRIP * K::TW * 2;
         if (K::REWRITE_ONE && tid < K::H2R)          // LN(x) overwrote the constant-1 column
-          *reinterpret_cast<uint4*>(sm + K::o_h2 + (9 * K::H2R + tid) * 16) = make_uint4(0x00003F80u, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sm + K::o_h2 + (9 * K::H2R + tid) * 16) = one_chunk(K::ONE_ELEM);
         const float* wd = fb + 80;
         const float* bd = fb + 800;
 #pragma unroll 1
@@ -383,7 +395,15 @@ mixffn_tc_kernel(FfnParams p) {
           }
 #pragma unroll
           for (int o = 0; o < SH; ++o) {
-            const float2 g0 = gelu_as2(acc[o][0]), g1 = gelu_as2(acc[o][1]);
+            float2 g0 = gelu_as2(acc[o][0]), g1 = gelu_as2(acc[o][1]);
+            if constexpr (K::ONE_ELEM != 0) {      // CH = 78: this half-chunk holds the constant 1
+              if (ch == K::ONE_CHUNK && hf == K::ONE_ELEM / 4) {
+                if (K::ONE_ELEM % 4 == 0) g0.x = 1.f;
+                if (K::ONE_ELEM % 4 == 1) g0.y = 1.f;
+                if (K::ONE_ELEM % 4 == 2) g1.x = 1.f;
+                if (K::ONE_ELEM % 4 == 3) g1.y = 1.f;
+              }
+            }
             const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x, g0.y), p1 = __floats2bfloat162_rn(g1.x, g1.y);
             uint2 u;
             u.x = *reinterpret_cast<const uint32_t*>(&p0);
@@ -431,8 +451,14 @@ mixffn_tc_kernel(FfnParams p) {
             if constexpr (K::SPLIT) {  // fp32 partial of this chunk group -> workspace [NG][n_tok][C]
               const size_t n_tok = (size_t)p.B * p.H * p.W;
               float* wrow = static_cast<float*>(p.ws) + ((size_t)cg * n_tok + o_tok) * C + cc * 8;
-              *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
+              if constexpr (C % 8 == 0) {
+                *reinterpret_cast<float4*>(wrow) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(wrow + 4) = make_float4(y[4], y[5], y[6], y[7]);
+              } else {                 // C = 78 / 156: rows are 8-byte aligned, the last chunk is partial
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (cc * 8 + 2 * j < C) *reinterpret_cast<float2*>(wrow + 2 * j) = make_float2(y[2 * j], y[2 * j + 1]);
+              }
             } else {                   // GELU, + residual; rows are only 4-byte aligned
               gelu8(y);
               uint32_t* orow = reinterpret_cast<uint32_t*>(out + o_tok * C + cc * 8);
@@ -475,13 +501,21 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
                                                          __nv_bfloat16* out) {
   pdl_launch_dependents();
   pdl_wait();
-  const size_t n_vec = n_tok * (C / 8);
+  // flat over [n_tok][C] (no per-channel term: b2 is part of the first partial, MMA bias row)
+  const size_t n_el = n_tok * C, n_vec = n_el / 8;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {         // tail when n_tok * C is not a multiple of 8
+    for (size_t e = n_vec * 8; e < n_el; ++e) {
+      float a = 0.f;
+      for (int gi = 0; gi < ng; ++gi) a += ws[(size_t)gi * n_el + e];
+      out[e] = __float2bfloat16(__bfloat162float(x[e]) + gelu_as(a));
+    }
+  }
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (size_t)gridDim.x * blockDim.x) {
     const size_t e0 = v * 8;
     float acc[8], r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;     // b2 is part of the first partial (MMA bias row)
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int gi = 0; gi < ng; ++gi) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0));
       const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0 + 4));
@@ -497,11 +531,14 @@ __global__ void __launch_bounds__(256) ffn_reduce_kernel(const float* ws, int ng
 }
 
 static bool ffn_tc_supported(const FfnParams& p) {
-  return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144);
+  return p.hidden == 4 * p.C && (p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144 ||   // HRFuser-T
+                                 p.C == 78 || p.C == 156);                               // HRFuser-B
 }
+// chunk groups (CTAs per tile) of the split variants; 0: the CTA finishes the block
+static int ffn_tc_groups(int C) { return C == 72 || C == 78 ? 2 : C == 144 || C == 156 ? 8 : 0; }
 static size_t ffn_tc_workspace_bytes(int B, int H, int W, int C, int hidden) {
-  if (hidden != 4 * C || (C != 144 && C != 72)) return 0;
-  return (size_t)(C == 144 ? 8 : 2) * B * H * W * C * sizeof(float);
+  if (hidden != 4 * C) return 0;
+  return (size_t)ffn_tc_groups(C) * B * H * W * C * sizeof(float);
 }
 
 template <int C, int CPG>
@@ -524,7 +561,7 @@ static int launch_ffn_tc_c(FfnParams p, cudaStream_t stream) {
   if constexpr (K::SPLIT) {
     const FfnLayout L(C, K::HID);
     const size_t n_tok = (size_t)p.B * p.H * p.W;
-    const size_t n_vec = n_tok * (C / 8);
+    const size_t n_vec = n_tok * C / 8;
     const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
     HRF_CUDA(launch_pdl(ffn_reduce_kernel<C>, dim3(rgrid), dim3(256), 0, stream,
                         static_cast<const float*>(p.ws), K::NG, n_tok, static_cast<const __nv_bfloat16*>(p.x),
@@ -541,6 +578,8 @@ static int launch_mixffn_tc(const FfnParams& p, cudaStream_t stream) {
     case 36: return launch_ffn_tc_c<36, 2>(p, stream);
     case 72: return launch_ffn_tc_c<72, 2>(p, stream);
     case 144: return launch_ffn_tc_c<144, 1>(p, stream);
+    case 78: return launch_ffn_tc_c<78, 2>(p, stream);
+    case 156: return launch_ffn_tc_c<156, 1>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_tc: C=%d", p.C);
 }

@@ -307,10 +307,54 @@ __device__ __forceinline__ void ln_row_streamed(const __nv_bfloat16* src, const 
   }
 }
 
+// the same for rows that are only 4-byte aligned (C = 78, 156: HRFuser-B): 32-bit loads
+template <int C, int KC, bool ONE = false>
+__device__ __forceinline__ void ln_row_streamed_w(const __nv_bfloat16* src, const float* gamma,
+                                                  const float* beta, float eps, unsigned char* tile,
+                                                  int row) {
+  static_assert(C % 2 == 0, "even channel count");
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+  auto word = [&](int i) {
+    const uint32_t u = __ldg(s32 + i);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  };
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 13
+  for (int i = 0; i < C / 2; ++i) { const float2 f = word(i); s0 += f.x; s1 += f.y; }
+  const float mean = (s0 + s1) * (1.0f / C);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll 13
+  for (int i = 0; i < C / 2; ++i) {
+    const float2 f = word(i);
+    const float d0 = f.x - mean, d1 = f.y - mean;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+  }
+  const float rstd = rsqrtf((q0 + q1) * (1.0f / C) + eps);
+#pragma unroll 1
+  for (int ch = 0; ch < KC / 8; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + 2 * j;
+      if (c < C) {
+        const float2 f = word(c / 2);
+        v[2 * j] = fmaf((f.x - mean) * rstd, gamma[c], beta[c]);
+        v[2 * j + 1] = fmaf((f.y - mean) * rstd, gamma[c + 1], beta[c + 1]);
+      } else {
+        v[2 * j] = (ONE && c == C) ? 1.f : 0.f;
+        v[2 * j + 1] = 0.f;
+      }
+    }
+    umma::st_chunk(tile, row, ch, 128, v);
+  }
+}
+
 template <int C, int KC, bool BIGC, bool ONE = false>
 __device__ __forceinline__ void ln_token(const __nv_bfloat16* src, const float* gamma,
                                          const float* beta, float eps, unsigned char* tile, int row) {
-  if constexpr (BIGC) {
+  if constexpr (BIGC && C % 8 != 0) {
+    ln_row_streamed_w<C, KC, ONE>(src, gamma, beta, eps, tile, row);
+  } else if constexpr (BIGC) {
     ln_row_streamed<C, KC, ONE>(src, gamma, beta, eps, tile, row);
   } else {
     float x[C];

@@ -122,7 +122,7 @@ class FfnLayout:
         self.b2 = o; o += c4
         # tensor-core sections (bf16 tiles; exercised on the GPU)
         KC = _ru(C, 16)
-        nch = hidden // 72 if hidden % 72 == 0 else 0
+        nch = hidden // 72 if hidden % 72 == 0 else hidden // 78 if hidden % 78 == 0 else 0
         self.tc_f32 = o
         o = _ru(o + nch * 880 + (KC if nch else 0), 4)
         self.tc_w1 = o; o += nch * 80 * KC // 2
