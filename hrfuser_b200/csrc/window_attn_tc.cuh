@@ -47,7 +47,7 @@ struct AttnTc {
   static constexpr bool SPLIT = HG < HEADS;
   static constexpr bool BIGC = C > 40;         // LayerNorm streams the row instead of holding it
   static_assert(HEADS % HG == 0, "head groups");
-  static_assert(HDP == 32, "tensor-core attention kernel is written for head_dim <= 32");
+  static_assert(HDP == 32 || HDP == 48, "tensor-core attention kernel: head_dim <= 48 (18 | 39 shipped)");
   static_assert(NQG <= 256 && NOUT <= 256, "one UMMA per projection");
   static constexpr int XT = 128 * (KC > NQG ? KC : NQG) * 2;   // XN tile, later aliased by the O tile
   static constexpr int WQ_B = NQG * KC * 2, WO_B = NOUT * NQG * 2;
@@ -61,7 +61,7 @@ struct AttnTc {
   static constexpr int o_qk = o_zn + (CROSS ? 128 * KC * 2 : 0);
   static constexpr int o_v = o_qk + HG * 2 * HT;
   static constexpr int o_bias = o_v + HG * HT;                // fp32: bq|bk|bv (this group) | bo
-  static_assert(2 * HT == 128 * 64 * 2, "P tile must fit the Q_h|K_h pair");
+  static_assert(2 * HT >= 128 * 64 * 2, "P tile must fit the Q_h|K_h pair");
   static constexpr int o_rpb = o_bias + (3 * NQG + NOUT) * 4; // fp32 [HG][169]
   static constexpr int o_ln = o_rpb + ((HG * 169 + 3) / 4 * 4) * 4;   // fp32 4 x C4
   static constexpr int C4 = (C + 3) / 4 * 4;
@@ -559,14 +559,15 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         unsigned char* dst = part == 0 ? sm + K::o_qk + h * 2 * K::HT
                            : part == 1 ? sm + K::o_qk + h * 2 * K::HT + K::HT
                                        : sm + K::o_v + h * K::HT;
-        float v[32];
-        tmem_ld32(trow + part * NQG + h * HDP, v);
+        float v[HDP];
+#pragma unroll
+        for (int c0 = 0; c0 < HDP; c0 += 16) tmem_ld16(trow + part * NQG + h * HDP + c0, v + c0);
         tmem_ld_wait();
         const float* bs = sBias + part * NQG + h * HDP;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] += bs[c];
+        for (int c = 0; c < HDP; ++c) v[c] += bs[c];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) st_chunk(dst, tid, ch, 128, v + 8 * ch);
+        for (int ch = 0; ch < HDP / 8; ++ch) st_chunk(dst, tid, ch, 128, v + 8 * ch);
       }
     }
 
@@ -660,15 +661,17 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       tc_fence_after();
       HRF_PROF(9)                                  // PV wait
       {
-        float o[32];
-        tmem_ld32(trow + g * HDP, o);
+        float o[HDP];
+#pragma unroll
+        for (int c0 = 0; c0 < HDP; c0 += 16) tmem_ld16(trow + g * HDP + c0, o + c0);
         tmem_ld_wait();
         const float is = inv_sum[h];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) o[c] *= is;
+        for (int c = 0; c < HDP; ++c) o[c] *= is;
         // O tile aliases the XN tile (dead since the projections completed)
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) st_chunk(sm + K::o_xn, tid, h * 4 + ch, 128, o + 8 * ch);
+        for (int ch = 0; ch < HDP / 8; ++ch)
+          st_chunk(sm + K::o_xn, tid, h * (HDP / 8) + ch, 128, o + 8 * ch);
       }
     }
 
@@ -712,7 +715,6 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       }
     } else {
       // fp32 partial of this head group -> workspace [NG][n_tok][C]
-      static_assert(!K::SPLIT || C % 16 == 0 || C % 8 == 0, "partial rows are stored 8 floats at a time");
       float* wrow = static_cast<float*>(p.ws) + ((size_t)hg * n_tok + (size_t)(tok >= 0 ? tok : 0)) * C;
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 8) {
@@ -720,8 +722,14 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
         tmem_ld8(trow + c0, y);
         tmem_ld_wait();
         if (tok >= 0) {
-          *reinterpret_cast<float4*>(wrow + c0) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          if constexpr (C % 8 == 0) {
+            *reinterpret_cast<float4*>(wrow + c0) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(wrow + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          } else {                     // C = 78 / 156: 8-byte aligned rows, partial last chunk
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0 + 2 * j < C) *reinterpret_cast<float2*>(wrow + c0 + 2 * j) = make_float2(y[2 * j], y[2 * j + 1]);
+          }
         }
       }
     }
@@ -750,7 +758,15 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int n
                                                           __nv_bfloat16* out) {
   pdl_launch_dependents();
   pdl_wait();
-  const size_t n_vec = n_tok * (C / 8);
+  // flat over [n_tok][C] in vectors of 8 (a vector may straddle two tokens when C % 8 != 0)
+  const size_t n_el = n_tok * C, n_vec = n_el / 8;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {         // tail when n_tok * C is not a multiple of 8
+    for (size_t e = n_vec * 8; e < n_el; ++e) {
+      float a = __bfloat162float(rs[e]) + (zz ? __bfloat162float(zz[e]) : 0.f) + bo[e % C];
+      for (int gi = 0; gi < ng; ++gi) a += ws[(size_t)gi * n_el + e];
+      out[e] = __float2bfloat16(a);
+    }
+  }
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (size_t)gridDim.x * blockDim.x) {
     const size_t e0 = v * 8;
@@ -763,7 +779,7 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int n
       for (int j = 0; j < 8; ++j) acc[j] += t[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bo + c0 + j);
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bo + (c0 + j < C ? c0 + j : c0 + j - C));
     for (int gi = 0; gi < ng; ++gi) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0));
       const float4 b = __ldg(reinterpret_cast<const float4*>(ws + (size_t)gi * n_tok * C + e0 + 4));
@@ -804,7 +820,7 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   if constexpr (NG > 1) {
     const AttnLayout L(C, HEADS, 7);
     const size_t n_tok = (size_t)p.B * p.H * p.W;
-    const size_t n_vec = n_tok * (C / 8);
+    const size_t n_vec = n_tok * C / 8;
     const int rgrid = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
     HRF_CUDA(launch_pdl(attn_reduce_kernel<C>, dim3(rgrid), dim3(256), 0, stream,
                         static_cast<const float*>(p.ws), NG, n_tok, static_cast<const __nv_bfloat16*>(p.resid),
@@ -818,13 +834,16 @@ static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
 
 // true when the tensor-core kernel covers this problem
 static bool attn_tc_supported(const AttnParams& p) {
-  if (p.win != 7 || p.C % p.heads != 0 || p.C / p.heads != 18) return false;
-  return p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144;
+  if (p.win != 7 || p.C % p.heads != 0) return false;
+  const int hd = p.C / p.heads;
+  if (hd == 18) return p.C == 18 || p.C == 36 || p.C == 72 || p.C == 144;     // HRFuser-T
+  if (hd == 39) return p.C == 78 || p.C == 156;                                // HRFuser-B
+  return false;
 }
 // fp32 workspace bytes of the split-head variants (0 when the CTA finishes the block itself)
 static size_t attn_tc_workspace_bytes(int B, int H, int W, int C, int heads) {
-  if (C / heads != 18) return 0;
-  const int ng = C == 72 ? 2 : C == 144 ? 4 : 0;
+  const int hd = heads > 0 ? C / heads : 0;
+  const int ng = hd == 18 ? (C == 72 ? 2 : C == 144 ? 4 : 0) : hd == 39 ? (C == 78 ? 2 : C == 156 ? 4 : 0) : 0;
   return (size_t)ng * B * H * W * C * sizeof(float);
 }
 
@@ -834,6 +853,8 @@ static int launch_window_attn_tc(const AttnParams& p, cudaStream_t stream) {
     case 36: return launch_attn_tc_ch<36, 2, 2>(p, stream);
     case 72: return launch_attn_tc_ch<72, 4, 2>(p, stream);
     case 144: return launch_attn_tc_ch<144, 8, 2>(p, stream);
+    case 78: return launch_attn_tc_ch<78, 2, 1>(p, stream);     // head_dim 39 -> padded to 48
+    case 156: return launch_attn_tc_ch<156, 4, 1>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "attn_tc: C=%d", p.C);
 }
