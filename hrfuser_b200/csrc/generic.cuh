@@ -9,8 +9,11 @@
 // Same packed fp32 weight sections as the fused SIMT kernels; intermediates live in a
 // caller-provided fp32 workspace.  Accuracy-first (fp32 FFMA, erff, expf).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "mixffn.cuh"
+#include "umma.cuh"
 #include "window_attn.cuh"
 
 namespace hrf {
@@ -100,8 +103,131 @@ __global__ void __launch_bounds__(256) gemm_bias_act_kernel(GemmParams p) {
   }
 }
 
+// ---- the same GEMM on the tcgen05 tensor cores (bf16 mode) ------------------------------------
+// out[128 x 128 tile] over K blocks of 64: A (fp32 activations) and Wt (fp32 k-major weights,
+// the sections the SIMT kernels use) are converted to bf16 operand tiles on the way into
+// shared memory -- no extra packed copies of the wide branches' weights -- two stages, so the
+// next block's global loads and conversion overlap the MMAs of the current one.  fp32
+// accumulation in TMEM; bias / activation / residual epilogue as above.
 template <typename TO>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+__global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
+  using namespace umma;
+  constexpr int NT = 128, KB = 64, A_B = 128 * KB * 2, B_B = NT * KB * 2;
+  extern __shared__ __align__(128) unsigned char sm[];          // 2 x (A tile | B tile)
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * NT;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, NT);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int nkb = ceil_div(p.K, KB);
+  uint32_t ph[2] = {0u, 0u};
+  // A: thread -> (row, 32 consecutive k); B: thread -> (n, 32 consecutive k)
+  const int a_row = tid >> 1, a_k = (tid & 1) * 32;
+  const int b_n = tid & 127, b_k = (tid >> 7) * 32;
+  const bool a_ok = m0 + a_row < p.M, b_ok = n0 + b_n < p.N;
+  const float* a_src = p.A + (size_t)(a_ok ? m0 + a_row : 0) * p.lda;
+  const float* b_src = p.Wt + (b_ok ? n0 + b_n : 0);
+#pragma unroll 1
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1, k0 = kb * KB;
+    float a[32], b[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {                // K % 4 == 0 (checked by the launcher)
+      const int k = k0 + a_k + j;
+      const float4 v = (a_ok && k < p.K) ? __ldg(reinterpret_cast<const float4*>(a_src + k))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[j] = v.x; a[j + 1] = v.y; a[j + 2] = v.z; a[j + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int k = k0 + b_k + j;
+      b[j] = (b_ok && k < p.K) ? __ldg(b_src + (size_t)k * p.N) : 0.f;
+    }
+    if (kb >= 2) {                                   // the MMAs of block kb-2 read this stage
+      cta_wait(&bars[buf], ph[buf]);
+      ph[buf] ^= 1;
+    }
+    unsigned char* sA = sm + buf * (A_B + B_B);
+    unsigned char* sB = sA + A_B;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      st_chunk(sA, a_row, a_k / 8 + c, 128, a + 8 * c);
+      st_chunk(sB, b_n, b_k / 8 + c, NT, b + 8 * c);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      constexpr uint32_t id = idesc_bf16(128, NT, false, false);
+      const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+#pragma unroll
+      for (int s2 = 0; s2 < KB / 16; ++s2)
+        mma_bf16(tmem, desc_kmajor(aA, 128, s2), desc_kmajor(aB, NT, s2), id, kb > 0 || s2 > 0);
+      mma_commit(&bars[buf]);
+    }
+  }
+  {                                                  // the last commit covers every MMA
+    const int buf = (nkb - 1) & 1;
+    cta_wait(&bars[buf], ph[buf]);
+  }
+  tc_fence_after();
+  // ---- epilogue: warp w -> TMEM quadrant w % 4, column group w / 4 --------------------------
+  const int q = warp & 3, gq = warp >> 2;
+  const int m = m0 + q * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  const TO* r1 = static_cast<const TO*>(p.r1);
+  const TO* r2 = static_cast<const TO*>(p.r2);
+  TO* out = static_cast<TO*>(p.out);
+#pragma unroll 1
+  for (int cc = gq; cc < NT / 8; cc += 2) {
+    float y[8];
+    tmem_ld8(trow + cc * 8, y);
+    tmem_ld_wait();
+    if (m < p.M) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = n0 + cc * 8 + j;
+        if (n < p.N) {
+          float v = y[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+          if (p.act == 1) v = fmaxf(v, 0.f);
+          else if (p.act == 2) v = gelu_erf(v);
+          const size_t off = (size_t)m * p.ldo + n;
+          if (r1) v += Elem<TO>::ld(r1 + off);
+          if (r2) v += Elem<TO>::ld(r2 + off);
+          Elem<TO>::st(out + off, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, NT);
+}
+
+// tc: bf16 mode (the caller's activations are bf16, so bf16 operand precision is the contract)
+template <typename TO>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream, bool tc = false) {
+  if (tc && p.K % 4 == 0 && p.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && !tc_disabled()) {
+    dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128));
+    HRF_REQUIRE(grid.y <= 65535, HRF_EUNSUPPORTED, "gemm: M=%d too large", p.M);
+    constexpr size_t smem = 2 * (128 * 64 * 2 + 128 * 64 * 2);
+    HRF_CUDA(ensure_smem((const void*)gemm_tc_kernel<TO>, smem));
+    gemm_tc_kernel<TO><<<grid, 256, smem, stream>>>(p);
+    count_launch();
+    HRF_CUDA(cudaGetLastError());
+    return HRF_OK;
+  }
   dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64));
   HRF_REQUIRE(grid.y <= 65535, HRF_EUNSUPPORTED, "gemm: M=%d too large", p.M);
   gemm_bias_act_kernel<TO><<<grid, 256, 0, stream>>>(p);
@@ -233,12 +359,13 @@ static int launch_window_attn_generic(const AttnParams& p, cudaStream_t st) {
   }
   HRF_CUDA(cudaGetLastError());
   int rc;
+  constexpr bool tc = std::is_same<T, __nv_bfloat16>::value;   // bf16 mode: tensor-core GEMMs
   GemmParams g{xn, blob + L.o_wq, blob + L.o_bq, nullptr, nullptr, q, n, C, C, C, C, 0};
-  if ((rc = launch_gemm<float>(g, st))) return rc;
+  if ((rc = launch_gemm<float>(g, st, tc))) return rc;
   g.A = zn; g.Wt = blob + L.o_wk; g.bias = blob + L.o_bk; g.out = k;
-  if ((rc = launch_gemm<float>(g, st))) return rc;
+  if ((rc = launch_gemm<float>(g, st, tc))) return rc;
   g.Wt = blob + L.o_wv; g.bias = blob + L.o_bv; g.out = v;
-  if ((rc = launch_gemm<float>(g, st))) return rc;
+  if ((rc = launch_gemm<float>(g, st, tc))) return rc;
   HRF_CUDA(cudaMemsetAsync(o, 0, (size_t)n * L.KO * sizeof(float), st));   // head-pad lanes
   CoreParams c{q, k, v, o, blob + L.o_bk, blob + L.o_bv, blob + L.o_rpb,
                p.B, p.H, p.W, C, p.heads, p.win, L.KO, L.hdp, p.pad_mask};
@@ -253,7 +380,7 @@ static int launch_window_attn_generic(const AttnParams& p, cudaStream_t st) {
   // out = resid (+ z) + o Wo^T + bo
   GemmParams go{o, blob + L.o_wo, blob + L.o_bo, p.resid, p.cross ? p.z : nullptr, p.out,
                 n, C, L.KO, L.KO, C, 0};
-  return launch_gemm<T>(go, st);
+  return launch_gemm<T>(go, st, tc);
 }
 
 static size_t ffn_generic_ws_floats(int B, int H, int W, int C, int hidden) {
@@ -275,8 +402,9 @@ static int launch_mixffn_generic(const FfnParams& p, cudaStream_t st) {
   count_launch();
   HRF_CUDA(cudaGetLastError());
   int rc;
+  constexpr bool tc = std::is_same<T, __nv_bfloat16>::value;   // bf16 mode: tensor-core GEMMs
   GemmParams g1{xn, blob + L.o_w1, blob + L.o_b1, nullptr, nullptr, h1, n, Hd, C, C, Hd, 2};
-  if ((rc = launch_gemm<float>(g1, st))) return rc;
+  if ((rc = launch_gemm<float>(g1, st, tc))) return rc;
   const size_t total = (size_t)n * Hd;
   const int dgrid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   dw3x3_gelu_kernel<<<dgrid, 256, 0, st>>>(h1, blob + L.o_wd, blob + L.o_bd, h2, p.B, p.H, p.W, Hd);
@@ -284,7 +412,7 @@ static int launch_mixffn_generic(const FfnParams& p, cudaStream_t st) {
   HRF_CUDA(cudaGetLastError());
   // out = x + GELU(h2 W2^T + b2)
   GemmParams g2{h2, blob + L.o_w2, blob + L.o_b2, p.x, nullptr, p.out, n, C, Hd, Hd, C, 2};
-  return launch_gemm<T>(g2, st);
+  return launch_gemm<T>(g2, st, tc);
 }
 
 }  // namespace hrf
