@@ -14,6 +14,9 @@
  *     `dtype` HRF_F32 or HRF_BF16; arithmetic is fp32 unless stated.
  *   - weights are fp32 blobs packed by the hrf_*_pack() helpers below (host
  *     pointers in, host pointer out; copy the blob to the device yourself).
+ *     The DEVICE copy of a blob must be 16-byte aligned: the tensor-core
+ *     kernels stage its bf16 operand tiles with bulk async copies
+ *     (HRF_EINVAL otherwise).
  *   - every *_fwd call is stream-ordered, non-allocating and non-blocking;
  *     the caller owns all memory.  `stream` is a cudaStream_t passed as void*.
  *   - return 0 on success, a negative HRF_E* code otherwise;
