@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
   __shared__ __align__(128) unsigned char sA[128 * 32 * 2];
   __shared__ __align__(128) unsigned char sW[COUT * 32 * 2];
   __shared__ float sBias[COUT];
+  __shared__ __align__(16) unsigned char sOut[128 * (2 * COUT + 16)];   // epilogue staging
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   HRF_PROF_DECL
@@ -123,19 +124,23 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
     phase ^= 1;
     tc_fence_after();
     HRF_PROF(4)                                    // MMA wait
-    // ---- epilogue: + bias, ReLU, bf16, 16-byte stores (one 2*COUT-byte row per thread) --
+    // ---- epilogue: + bias, ReLU, bf16.  Each thread owns one pixel row of 2*COUT bytes; the
+    // warp's 32 rows are staged in shared memory (pitch 2*COUT + 16: conflict-free both ways)
+    // and written out 512 contiguous bytes per store instruction (8 lanes x 16 B per row)
+    // instead of 32 scattered 16-byte pieces.
+    {
+      constexpr int PITCH = 2 * COUT + 16;
+      unsigned char* srow = sOut + (size_t)tid * PITCH;
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
-      float y[32];
-      tmem_ld32(trow + c0, y);
-      tmem_ld_wait();
-      if (pix < n_pix) {
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        float y[32];
+        tmem_ld32(trow + c0, y);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           y[j] += sBias[c0 + j];
           if (p.relu) y[j] = fmaxf(y[j], 0.f);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)pix * COUT + c0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
@@ -145,9 +150,22 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
           __nv_bfloat162 h3 = __floats2bfloat162_rn(y[8 * q + 6], y[8 * q + 7]);
           u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
           u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-          dst[q] = u;
+          *reinterpret_cast<uint4*>(srow + (c0 + 8 * q) * 2) = u;
         }
       }
+      __syncwarp();
+      constexpr int PIECES = 2 * COUT / 16;          // 16-byte pieces per row (8 for COUT = 64)
+      constexpr int RPI = 32 / PIECES;               // rows per store instruction
+      const int lane = tid & 31, w0 = tid & ~31;
+#pragma unroll
+      for (int k = 0; k < 32 / RPI; ++k) {
+        const int r = w0 + k * RPI + lane / PIECES, piece = lane % PIECES;
+        const int px = tile * 128 + r;
+        if (px < n_pix)
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.out) + (size_t)px * (2 * COUT) + piece * 16) =
+              *reinterpret_cast<const uint4*>(sOut + (size_t)r * PITCH + piece * 16);
+      }
+      __syncwarp();
     }
     HRF_PROF(5)                                    // epilogue
     // the barrier before the next MMA orders these TMEM reads and the sA rewrite
