@@ -229,11 +229,16 @@ int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b
           tk[e] = f32_to_bf16(wk[(size_t)n * C + k]);
           tv[e] = f32_to_bf16(wv[(size_t)n * C + k]);
         }
+        if (KC > C) {   // bias row: the kernels feed a constant 1 in column C of LN(x) / LN(z)
+          const size_t e = umma::tile_off(np, C, NQ) / 2;
+          tq[e] = f32_to_bf16(bias[np]);
+          tk[e] = f32_to_bf16(bias[NQ + np]);
+          tv[e] = f32_to_bf16(bias[2 * NQ + np]);
+        }
         for (int n2 = 0; n2 < C; ++n2)                       // out_proj: rows = out feature, K = padded O
           to[umma::tile_off(n2, np, NOUT) / 2] = f32_to_bf16(wo[(size_t)n2 * C + n]);
       }
     for (int c = 0; c < C; ++c) bias[3 * NQ + c] = bo ? bo[c] : 0.f;
-    (void)KC;
   }
   return HRF_OK;
 }

@@ -99,7 +99,6 @@ __global__ void __launch_bounds__(128, 6) stem_conv_tc_kernel(StemParams p) {
   HRF_PROF(14)                                     // setup + first gather
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     HRF_PROF_TILE
-    const int pix = tile * 128 + tid;
     float v[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = k < 27 ? vn[k] : 0.f;

@@ -46,6 +46,10 @@ struct AttnTc {
   static constexpr int WIN = 7, S = 49;
   static constexpr bool SPLIT = HG < HEADS;
   static constexpr bool BIGC = C > 40;         // LayerNorm streams the row instead of holding it
+  // q / k / v biases through the MMA: column C of the LN(x) / LN(z) tiles holds a constant 1
+  // (pad and dead rows too: a zero-padded slot projects to the bias, as in the reference) and
+  // row C of the weight tiles the bias.  Needs a spare K column (not C = 144).
+  static constexpr bool BIAS_MMA = (C + 15) / 16 * 16 > C;
   static_assert(HEADS % HG == 0, "head groups");
   static_assert(HDP == 32 || HDP == 48, "tensor-core attention kernel: head_dim <= 48 (18 | 39 shipped)");
   static_assert(NQG <= 256 && NOUT <= 256, "one UMMA per projection");
@@ -411,8 +415,10 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
              wo_b, &wbar);
   }
   {
-    for (int e = tid; e < 3 * NQG; e += 128)
-      sBias[e] = __ldg(blob + L.o_tc_bias + (e / NQG) * NQ + h0 * HDP + (e % NQG));
+    if constexpr (!K::BIAS_MMA) {
+      for (int e = tid; e < 3 * NQG; e += 128)
+        sBias[e] = __ldg(blob + L.o_tc_bias + (e / NQG) * NQ + h0 * HDP + (e % NQG));
+    }
     for (int e = tid; e < NOUT; e += 128) sBias[3 * NQG + e] = __ldg(blob + L.o_tc_bias + 3 * NQ + e);
     for (int e = tid; e < HG * 169; e += 128) sRpb[e] = __ldg(blob + L.o_rpb + h0 * 169 + e);
     for (int e = tid; e < K::C4; e += 128) {
@@ -491,23 +497,28 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
       if constexpr (PIPE) {
         float x[C];
         unpack_row<C>(xr, x);
-        ln_row_to_tile<C, KC>(x, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+        ln_row_to_tile<C, KC, K::BIAS_MMA>(x, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
         if (CROSS) {
           unpack_row<C>(zr, x);
-          ln_row_to_tile<C, KC>(x, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps, sm + K::o_zn, tid);
+          ln_row_to_tile<C, KC, K::BIAS_MMA>(x, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps, sm + K::o_zn, tid);
         }
       } else {
-        ln_token<C, KC, K::BIGC>(xq + (size_t)tok * C, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
+        ln_token<C, KC, K::BIGC, K::BIAS_MMA>(xq + (size_t)tok * C, sLn, sLn + K::C4, p.eps, sm + K::o_xn, tid);
         if (CROSS)
-          ln_token<C, KC, K::BIGC>(zz + (size_t)tok * C, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps,
+          ln_token<C, KC, K::BIGC, K::BIAS_MMA>(zz + (size_t)tok * C, sLn + 2 * K::C4, sLn + 3 * K::C4, p.eps,
                                    sm + K::o_zn, tid);
       }
     } else {
       const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < KC / 8; ++ch) {
-        st_chunk(sm + K::o_xn, tid, ch, 128, zero);
-        if (CROSS) st_chunk(sm + K::o_zn, tid, ch, 128, zero);
+        // zero row; with the bias column it still carries the constant 1
+        const bool one = K::BIAS_MMA && ch == C / 8;
+        float zc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zc[j] = (one && j == C % 8) ? 1.f : zero[j];
+        st_chunk(sm + K::o_xn, tid, ch, 128, zc);
+        if (CROSS) st_chunk(sm + K::o_zn, tid, ch, 128, zc);
       }
     }
     // requests that complete behind the tile's MMAs / softmax: this tile's residual row
@@ -563,9 +574,11 @@ __global__ void __launch_bounds__(128) window_attn_tc_kernel(AttnParams p) {
 #pragma unroll
         for (int c0 = 0; c0 < HDP; c0 += 16) tmem_ld16(trow + part * NQG + h * HDP + c0, v + c0);
         tmem_ld_wait();
-        const float* bs = sBias + part * NQG + h * HDP;
+        if constexpr (!K::BIAS_MMA) {
+          const float* bs = sBias + part * NQG + h * HDP;
 #pragma unroll
-        for (int c = 0; c < HDP; ++c) v[c] += bs[c];
+          for (int c = 0; c < HDP; ++c) v[c] += bs[c];
+        }
 #pragma unroll
         for (int ch = 0; ch < HDP / 8; ++ch) st_chunk(dst, tid, ch, 128, v + 8 * ch);
       }

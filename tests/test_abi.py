@@ -103,7 +103,8 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_attn_packer_tensor_core_tiles(built_lib):
     """bf16 operand tiles of the tcgen05 kernel: chunk-major [K/8][rows][8], heads
-    padded 18 -> 32, q pre-scaled, out_proj K index = padded O column."""
+    padded 18 -> 32, q pre-scaled, K column C = the bias (multiplies the constant-1
+    column of LN(x)), out_proj K index = padded O column."""
     from blob_emul import AttnLayout
     from hrfuser_b200 import ops
     Cc, heads = 36, 2
@@ -122,10 +123,11 @@ def test_attn_packer_tensor_core_tiles(built_lib):
         raw = blob[L.o[name]:L.o[name] + rows * cols // 2].view(torch.bfloat16).float()
         return raw.view(cols // 8, rows, 8).permute(1, 0, 2).reshape(rows, cols)   # -> [row][col]
     pad_rows = torch.tensor([h * HDP + d for h in range(heads) for d in range(hd)])
-    for name, w, s in (('tc_wq', wq, scale), ('tc_wk', wk, 1.0), ('tc_wv', wv, 1.0)):
+    for name, w, b, s in (('tc_wq', wq, bq, scale), ('tc_wk', wk, bk, 1.0), ('tc_wv', wv, bv, 1.0)):
         t = tile(name, NQ, KC)
         assert torch.equal(t[pad_rows, :Cc], (w * s).bfloat16().float())
-        assert t[:, Cc:].abs().sum() == 0
+        assert KC > Cc and torch.equal(t[pad_rows, Cc], (b * s).bfloat16().float())   # bias row
+        assert t[:, Cc + 1:].abs().sum() == 0
         keep = torch.zeros(NQ, dtype=torch.bool)
         keep[pad_rows] = True
         assert t[~keep].abs().sum() == 0
