@@ -2,7 +2,7 @@
 
     python tools/trace_report.py gpurun_out/trace.json
 
-Takes the last replay (events after the largest idle gap), prints the step span, the time
+Takes the last of the three profiled replays, prints the step span, the time
 with 0 / 1 / 2 / 3+ kernels in flight, per-kernel-family busy time and the families that run
 ALONE longest (the serial bottlenecks of the graph).
 """
@@ -14,11 +14,9 @@ import sys
 recs = json.load(open(sys.argv[1]))
 recs = [r for r in recs if r['dur'] > 0 and 'Memcpy' not in r['name'] and 'Memset' not in r['name']]
 recs.sort(key=lambda r: r['start'])
-# split replays at the largest gaps
-gaps = sorted(((recs[i + 1]['start'] - max(r['start'] + r['dur'] for r in recs[:i + 1][-50:]), i)
-               for i in range(len(recs) - 1)), reverse=True)
-cuts = sorted(i for _, i in gaps[:2])
-last = recs[cuts[-1] + 1:] if cuts else recs
+# tools/trace_step.py profiles three identical replays: the last third of the kernel records
+N_REPLAYS = 3
+last = recs[len(recs) - len(recs) // N_REPLAYS:]
 t0 = last[0]['start']
 t1 = max(r['start'] + r['dur'] for r in last)
 print(f'{len(last)} kernels, span {t1 - t0:.1f} us, sum of kernel durations {sum(r["dur"] for r in last):.1f} us')
