@@ -316,12 +316,9 @@ mixffn_tc_kernel(FfnParams p) {
 
       // ---- epilogue 1: (+ b1,) GELU, zero outside the image -> H1 -----------------------
       const float* fb = sF + c * 880;
-#pragma unroll 1
-      for (int u = gq; u < n_units; u += NGQ) {       // warp-uniform trip count
+      // two units per iteration: both TMEM loads are in flight before the first GELU chain
+      auto epi1_unit = [&](int u, float* v) {
         const int mt = u >= K::NDC ? 1 : 0, ch = u - mt * K::NDC;
-        float v[8];
-        tmem_ld8(trow + mt * N1 + ch * 8, v);
-        tmem_ld_wait();
         const int t = mt * 128 + row;                 // halo token
         if (t < K::NHALO) {
           if constexpr (K::BIAS_MMA) {
@@ -339,6 +336,23 @@ mixffn_tc_kernel(FfnParams p) {
           }
           st_chunk(sm + K::o_h1, t, ch, K::H1R, v);
         }
+      };
+#pragma unroll 1
+      for (int u = gq; u < n_units; u += 2 * NGQ) {   // warp-uniform trip count
+        const int u2 = u + NGQ;
+        const bool two = u2 < n_units;                // warp-uniform
+        float va[8], vb[8];
+        {
+          const int mt = u >= K::NDC ? 1 : 0;
+          tmem_ld8(trow + mt * N1 + (u - mt * K::NDC) * 8, va);
+        }
+        if (two) {
+          const int mt = u2 >= K::NDC ? 1 : 0;
+          tmem_ld8(trow + mt * N1 + (u2 - mt * K::NDC) * 8, vb);
+        }
+        tmem_ld_wait();
+        epi1_unit(u, va);
+        if (two) epi1_unit(u2, vb);
       }
       HRF_PROF(4)                                  // epilogue 1
       tc_fence_before();
