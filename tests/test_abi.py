@@ -138,3 +138,34 @@ def test_attn_packer_tensor_core_tiles(built_lib):
     assert torch.allclose(bias[pad_rows], bq * scale)
     assert torch.equal(bias[NQ + pad_rows], bk) and torch.equal(bias[2 * NQ + pad_rows], bv)
     assert torch.equal(bias[3 * NQ:3 * NQ + Cc], bo)
+
+
+def test_conv3x3_packer(built_lib):
+    """hrf_conv3x3_pack: fp32 k-major section (K = tap*Cin + c, BN folded) and, for the widths
+    the tcgen05 kernel covers, nine bf16 B tiles [KC/8][NOUT][8] whose row Cin of the centre tap
+    is the folded bias."""
+    import torch.nn as nn
+    from hrfuser_b200 import ops
+    from hrfuser_b200.utils import randomize_parameters
+    cin, cout = 18, 36
+    conv, bn = nn.Conv2d(cin, cout, 3, 2, 1, bias=False), nn.BatchNorm2d(cout)
+    randomize_parameters(nn.Sequential(conv, bn), 7)
+    bn.eval()
+    blob = ops.pack_conv3x3(conv, bn, bn.eps)
+    sc = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    wf = (conv.weight * sc[:, None, None, None]).detach()               # (Cout, Cin, 3, 3)
+    bf = (bn.bias - bn.running_mean * sc).detach()
+    K, Kp = 9 * cin, (9 * cin + 3) // 4 * 4
+    wt = blob[:Kp * cout].view(Kp, cout)[:K].view(9, cin, cout)          # [tap][c][n]
+    assert torch.allclose(wt, wf.permute(2, 3, 1, 0).reshape(9, cin, cout), rtol=1e-6, atol=1e-7)
+    ob = (Kp * cout + 3) // 4 * 4
+    assert torch.allclose(blob[ob:ob + cout], bf, rtol=1e-6, atol=1e-7)
+    base = ob + (cout + 3) // 4 * 4
+    nout, kc = (cout + 15) // 16 * 16, (cin + 1 + 15) // 16 * 16
+    assert blob.numel() == base + 9 * nout * kc // 2
+    tiles = blob[base:].view(torch.bfloat16).float().view(9, kc // 8, nout, 8).permute(0, 2, 1, 3).reshape(9, nout, kc)
+    ref = wf.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    assert torch.equal(tiles[:, :cout, :cin], ref.bfloat16().float())
+    assert torch.equal(tiles[4, :cout, cin], bf.bfloat16().float())       # bias row, centre tap
+    tiles[4, :cout, cin] = 0
+    assert tiles[:, :, cin:].abs().sum() == 0 and tiles[:, cout:].abs().sum() == 0
