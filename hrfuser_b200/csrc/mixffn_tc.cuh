@@ -6,14 +6,14 @@
 //   LN prologue   the 8 x 16 halo (128 tokens) is LayerNormed (a lane pair per token for
 //                 C <= 36) and written as one bf16 M=128 operand tile with a constant-1
 //                 column that carries b1 through the MMA (all-zero rows outside the image)
-//   per chunk of 72 hidden channels (hidden = 4C = 72 * nchunk):
+//   per chunk of 72 (HRFuser-T) / 78 (HRFuser-B) hidden channels (hidden = 4C):
 //     fc1 (UMMA)  [128 x KC] x W1c^T -> TMEM (N = 80)
 //     epilogue    GELU (zero outside the image: that is what the reference's zero-padded
 //                 depthwise conv sees), bf16 -> H1 [9 chunks][128 tok][8]
 //     dw 3x3      CUDA cores on H1: strips of 3 outputs x 4 channels per thread, packed
 //                 fp32x2 FMAs, + bd, GELU, bf16 -> H2 operand tile [88 x 80]
 //     fc2 (UMMA)  H2 x W2c^T accumulated over the chunks in TMEM (N = NOUT); b2 rides on
-//                 the constant-1 column 72 of H2
+//                 the constant-1 column 72 | 78 of H2
 //   epilogue      GELU, + residual, bf16 -> global
 // The 4C-wide hidden activation never leaves the SM.  BN is folded (eval mode).
 #pragma once
@@ -27,7 +27,7 @@
 namespace hrf {
 
 // CPG = hidden chunks handled by one CTA.  CPG == NCH: the CTA finishes the block.
-// CPG < NCH (C = 72, 144: few tokens, many chunks): NCH/CPG CTAs share a token tile,
+// CPG < NCH (C = 72, 78, 144, 156: few tokens or many chunks): NCH/CPG CTAs share a token tile,
 // each writes its fp32 partial fc2 product to a workspace and `ffn_reduce_kernel`
 // applies GELU / residual to the fixed-order sum.
 //

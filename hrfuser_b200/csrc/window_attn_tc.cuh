@@ -5,9 +5,10 @@
 // window B.  Per pair:
 //
 //   LN prologue       per-thread LayerNorm of its own token (no shuffles), written
-//                     as bf16 into the XN (and ZN) operand tile; pad slots -> zeros
+//                     as bf16 into the XN (and ZN) operand tile; pad slots -> zeros; column C
+//                     of every row holds a constant 1 (row C of the weight tiles = q/k/v bias)
 //   QKV  (UMMA)       [128 x KC] x Wq/Wk/Wv^T  -> TMEM  (N = heads*32 each)
-//   epilogue          + bias, bf16 -> Q / K / V operand tiles per head (hd 18 -> 32)
+//   epilogue          bf16 -> Q / K / V operand tiles per head (head_dim 18 -> 32, 39 -> 48)
 //   per head:
 //     S  (UMMA)       Q_h [128x32] x [K_A;K_B]^T -> TMEM 128 cols; each row reads only
 //                     the 64 columns of its own window
@@ -21,6 +22,8 @@
 //
 // Pad / partition / merge / crop are address arithmetic (same closed forms as
 // window_attn.cuh).  Accumulation, LayerNorm statistics and softmax are fp32.
+// Persistent over window pairs (one resident wave of CTAs); the weight tiles arrive by TMA
+// bulk copies behind the first tile's prologue; the next tile's rows are prefetched.
 #pragma once
 #include <cstdlib>
 
