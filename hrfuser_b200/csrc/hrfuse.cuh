@@ -297,6 +297,7 @@ struct DwPwParams {
   const void* x; const float* blob; void* out;
   int B, H, W, Ho, Wo, Cin, Cout, relu;
   int w_smem;
+  FastDiv d_wo, d_howo;   // filled by launch_dwpw
 };
 
 template <typename T, int CT, int TOK>
@@ -320,8 +321,9 @@ __global__ void __launch_bounds__(kPwThreads) dwpw_kernel(DwPwParams p) {
     const int r = e / hp, c = (e - r * hp) * 2;
     float2 s = make_float2(0.f, 0.f);
     if (r < m && c < p.Cin) {
-      const int t = t0 + r;
-      const int b = t / (p.Ho * p.Wo), oy = (t / p.Wo) % p.Ho, ox = t % p.Wo;
+      int b, rem, oy, ox;
+      p.d_howo.divmod(t0 + r, b, rem);
+      p.d_wo.divmod(rem, oy, ox);
       s = __ldg(reinterpret_cast<const float2*>(bd + c));
       // all nine taps are loaded before the first FMA (clamped address, zero weight
       // outside the image) so the loads overlap instead of serialising on L2 latency
@@ -368,9 +370,11 @@ static int launch_dwpw_tok(DwPwParams p, cudaStream_t stream) {
 }
 
 template <typename T>
-static int launch_dwpw(const DwPwParams& p, cudaStream_t stream) {
+static int launch_dwpw(DwPwParams p, cudaStream_t stream) {
   HRF_REQUIRE(p.Cout % 2 == 0 && p.Cin % 2 == 0, HRF_EUNSUPPORTED,
               "dwpw: Cin=%d / Cout=%d must be even", p.Cin, p.Cout);
+  p.d_wo = FastDiv(p.Wo);
+  p.d_howo = FastDiv(p.Ho * p.Wo);
   return p.B * p.Ho * p.Wo >= 148 * 2 * 64 ? launch_dwpw_tok<T, 64>(p, stream)
                                            : launch_dwpw_tok<T, 16>(p, stream);
 }
@@ -393,13 +397,20 @@ struct FuseParams {
   FastDiv d_hc, d_w, d_h, d_hw;
 };
 
-// value of one (token, channel pair) element: x + same-resolution terms + bilinear gathers
-template <typename T>
-__device__ __forceinline__ float2 fuse_value(const FuseParams& p, int b, int h, int w, size_t off, int c) {
-  float2 v = Pair<T>::ld(static_cast<const T*>(p.x) + off);
+// values of PG consecutive channel pairs of one token: x + same-resolution terms + bilinear
+// gathers.  The bilinear coordinates / weights are computed once per token and up-term, and
+// the 4 * PG gathers of a term are independent loads.
+template <typename T, int PG>
+__device__ __forceinline__ void fuse_values(const FuseParams& p, int b, int h, int w, size_t off, int c,
+                                            float2* v) {
+#pragma unroll
+  for (int k = 0; k < PG; ++k) v[k] = Pair<T>::ld(static_cast<const T*>(p.x) + off + 2 * k);
   for (int j = 0; j < p.n_same; ++j) {
-    const float2 a = Pair<T>::ld(static_cast<const T*>(p.same[j]) + off);
-    v.x += a.x; v.y += a.y;
+#pragma unroll
+    for (int k = 0; k < PG; ++k) {
+      const float2 a = Pair<T>::ld(static_cast<const T*>(p.same[j]) + off + 2 * k);
+      v[k].x += a.x; v[k].y += a.y;
+    }
   }
   for (int j = 0; j < p.n_up; ++j) {
     const int ih = p.up_H[j], iw = p.up_W[j];
@@ -412,32 +423,40 @@ __device__ __forceinline__ float2 fuse_value(const FuseParams& p, int b, int h, 
     const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
     const float hy = 1.f - ly, hx = 1.f - lx;
     const T* ub = u + (size_t)b * ih * iw * p.C + c;
-    const float2 v00 = Pair<T>::ld(ub + (size_t)(y0 * iw + x0) * p.C);
-    const float2 v01 = Pair<T>::ld(ub + (size_t)(y0 * iw + x1) * p.C);
-    const float2 v10 = Pair<T>::ld(ub + (size_t)(y1 * iw + x0) * p.C);
-    const float2 v11 = Pair<T>::ld(ub + (size_t)(y1 * iw + x1) * p.C);
-    v.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    v.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    const T* p00 = ub + (size_t)(y0 * iw + x0) * p.C;
+    const T* p01 = ub + (size_t)(y0 * iw + x1) * p.C;
+    const T* p10 = ub + (size_t)(y1 * iw + x0) * p.C;
+    const T* p11 = ub + (size_t)(y1 * iw + x1) * p.C;
+#pragma unroll
+    for (int k = 0; k < PG; ++k) {
+      const float2 v00 = Pair<T>::ld(p00 + 2 * k), v01 = Pair<T>::ld(p01 + 2 * k);
+      const float2 v10 = Pair<T>::ld(p10 + 2 * k), v11 = Pair<T>::ld(p11 + 2 * k);
+      v[k].x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+      v[k].y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    }
   }
-  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-  return v;
+  if (p.relu) {
+#pragma unroll
+    for (int k = 0; k < PG; ++k) { v[k].x = fmaxf(v[k].x, 0.f); v[k].y = fmaxf(v[k].y, 0.f); }
+  }
 }
 
-// thread = (token, channel pair); 32-bit index math (tensors are < 2^31 elements)
-template <typename T>
+// thread = (token, group of PG channel pairs); 32-bit index math (tensors are < 2^31 elements)
+template <typename T, int PG>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  const int hc = p.C / 2;
-  const int total = p.B * p.H * p.W * hc;
+  const int total = p.B * p.H * p.W * (p.C / 2 / PG);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    int t, c2, hb, w, b, h;
-    p.d_hc.divmod(e, t, c2);
+    int t, g, hb, w, b, h;
+    p.d_hc.divmod(e, t, g);                          // d_hc = groups per token
     p.d_w.divmod(t, hb, w);
     p.d_h.divmod(hb, b, h);
-    const size_t off = (size_t)t * p.C + 2 * c2;
-    const float2 v = fuse_value<T>(p, b, h, w, off, 2 * c2);
-    Pair<T>::st(static_cast<T*>(p.out) + off, v.x, v.y);
+    const size_t off = (size_t)t * p.C + 2 * PG * g;
+    float2 v[PG];
+    fuse_values<T, PG>(p, b, h, w, off, 2 * PG * g, v);
+#pragma unroll
+    for (int k = 0; k < PG; ++k) Pair<T>::st(static_cast<T*>(p.out) + off + 2 * k, v[k].x, v[k].y);
   }
 }
 
@@ -445,27 +464,30 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
 // kFuseTok consecutive tokens, keeps the values (rounded through the storage type, so both
 // copies agree) in shared memory [C][tokens] and writes every channel's run of tokens as one
 // contiguous segment -- the direct form scatters 4-byte writes H*W*4 bytes apart.
-constexpr int kFuseTok = 64;
-template <typename T>
+template <typename T, int kFuseTok, int PG>
 __global__ void __launch_bounds__(256) fuse_sum_nchw_kernel(FuseParams p) {
   extern __shared__ float sv[];                      // [C][kFuseTok + 1]
   pdl_launch_dependents();
   pdl_wait();
-  const int hc = p.C / 2, ntok = p.B * p.H * p.W, hw = p.H * p.W;
+  const int ng = p.C / 2 / PG, ntok = p.B * p.H * p.W, hw = p.H * p.W;
   const int t0 = blockIdx.x * kFuseTok;
   const int m = min(kFuseTok, ntok - t0);
-  for (int e = threadIdx.x; e < m * hc; e += blockDim.x) {
-    int r, c2, hb, w, b, h;
-    p.d_hc.divmod(e, r, c2);
+  for (int e = threadIdx.x; e < m * ng; e += blockDim.x) {
+    int r, g, hb, w, b, h;
+    p.d_hc.divmod(e, r, g);
     const int t = t0 + r;
     p.d_w.divmod(t, hb, w);
     p.d_h.divmod(hb, b, h);
-    const size_t off = (size_t)t * p.C + 2 * c2;
-    const float2 v = fuse_value<T>(p, b, h, w, off, 2 * c2);
-    Pair<T>::st(static_cast<T*>(p.out) + off, v.x, v.y);
-    const float2 vs = Pair<T>::rt(v);                // as stored
-    sv[(2 * c2) * (kFuseTok + 1) + r] = vs.x;
-    sv[(2 * c2 + 1) * (kFuseTok + 1) + r] = vs.y;
+    const size_t off = (size_t)t * p.C + 2 * PG * g;
+    float2 v[PG];
+    fuse_values<T, PG>(p, b, h, w, off, 2 * PG * g, v);
+#pragma unroll
+    for (int k = 0; k < PG; ++k) {
+      Pair<T>::st(static_cast<T*>(p.out) + off + 2 * k, v[k].x, v[k].y);
+      const float2 vs = Pair<T>::rt(v[k]);           // as stored
+      sv[(2 * (PG * g + k)) * (kFuseTok + 1) + r] = vs.x;
+      sv[(2 * (PG * g + k) + 1) * (kFuseTok + 1) + r] = vs.y;
+    }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < p.C * kFuseTok; e += blockDim.x) {
@@ -478,12 +500,37 @@ __global__ void __launch_bounds__(256) fuse_sum_nchw_kernel(FuseParams p) {
   }
 }
 
+template <typename T, int PG>
+static int launch_fuse_pg(FuseParams p, cudaStream_t stream) {
+  const int ng = p.C / 2 / PG;
+  p.d_hc = FastDiv(ng);
+  const size_t total = (size_t)p.B * p.H * p.W * ng;
+  if (p.out_nchw) {
+    const int ntok = p.B * p.H * p.W;
+    if (ntok >= 148 * 4 * 64) {                      // 64-token groups: 256-byte NCHW runs
+      const size_t smem = (size_t)p.C * (64 + 1) * sizeof(float);
+      HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T, 64, PG>, smem));
+      HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T, 64, PG>, dim3(ceil_div(ntok, 64)), dim3(256), smem, stream, p));
+    } else {                                         // small maps: more, smaller CTAs
+      const size_t smem = (size_t)p.C * (16 + 1) * sizeof(float);
+      HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T, 16, PG>, smem));
+      HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T, 16, PG>, dim3(ceil_div(ntok, 16)), dim3(256), smem, stream, p));
+    }
+  } else {
+    // 128-thread CTAs: few threads in total (one per token and pair group), spread them
+    const int grid = (int)((total + 127) / 128 < 148 * 32 ? (total + 127) / 128 : 148 * 32);
+    HRF_CUDA(launch_pdl(fuse_sum_kernel<T, PG>, dim3(grid), dim3(128), 0, stream, p));
+  }
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
 template <typename T>
 static int launch_fuse(FuseParams p, cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.H * p.W * (p.C / 2);
   HRF_REQUIRE(p.C % 2 == 0 && total * 2 < ((size_t)1 << 31), HRF_EUNSUPPORTED,
               "fuse_sum: C=%d must be even and the tensor below 2^31 elements", p.C);
-  p.d_hc = FastDiv(p.C / 2);
   p.d_w = FastDiv(p.W);
   p.d_h = FastDiv(p.H);
   p.d_hw = FastDiv(p.H * p.W);
@@ -491,18 +538,11 @@ static int launch_fuse(FuseParams p, cudaStream_t stream) {
     p.up_sh[j] = (float)p.up_H[j] / (float)p.H;
     p.up_sw[j] = (float)p.up_W[j] / (float)p.W;
   }
-  if (p.out_nchw) {
-    const size_t smem = (size_t)p.C * (kFuseTok + 1) * sizeof(float);
-    HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T>, smem));
-    const int ntok = p.B * p.H * p.W;
-    HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T>, dim3(ceil_div(ntok, kFuseTok)), dim3(256), smem, stream, p));
-  } else {
-    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    HRF_CUDA(launch_pdl(fuse_sum_kernel<T>, dim3(grid), dim3(256), 0, stream, p));
-  }
-  count_launch();
-  HRF_CUDA(cudaGetLastError());
-  return HRF_OK;
+  const int hc = p.C / 2;
+  if (hc % 9 == 0) return launch_fuse_pg<T, 9>(p, stream);     // HRFuser-T widths 18k
+  if (hc % 13 == 0) return launch_fuse_pg<T, 13>(p, stream);   // HRFuser-B widths 78k
+  if (hc % 8 == 0) return launch_fuse_pg<T, 8>(p, stream);
+  return launch_fuse_pg<T, 1>(p, stream);
 }
 
 // ---------------------------------------------------------------------------
