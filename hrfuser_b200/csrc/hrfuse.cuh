@@ -395,6 +395,7 @@ struct FuseParams {
   int B, H, W, C, n_up, n_same, relu;
   float up_sh[HRF_MAX_FUSE_TERMS], up_sw[HRF_MAX_FUSE_TERMS];   // filled by launch_fuse
   FastDiv d_hc, d_w, d_h, d_hw;
+  int tokb, tokb_log2;                                           // NCHW variant: tokens per CTA
 };
 
 // values of PG consecutive channel pairs of one token: x + same-resolution terms + bilinear
@@ -464,11 +465,12 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseParams p) {
 // kFuseTok consecutive tokens, keeps the values (rounded through the storage type, so both
 // copies agree) in shared memory [C][tokens] and writes every channel's run of tokens as one
 // contiguous segment -- the direct form scatters 4-byte writes H*W*4 bytes apart.
-template <typename T, int kFuseTok, int PG>
+template <typename T, int PG>
 __global__ void __launch_bounds__(256) fuse_sum_nchw_kernel(FuseParams p) {
   extern __shared__ float sv[];                      // [C][kFuseTok + 1]
   pdl_launch_dependents();
   pdl_wait();
+  const int kFuseTok = p.tokb;                       // tokens per CTA (a power of two)
   const int ng = p.C / 2 / PG, ntok = p.B * p.H * p.W, hw = p.H * p.W;
   const int t0 = blockIdx.x * kFuseTok;
   const int m = min(kFuseTok, ntok - t0);
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(256) fuse_sum_nchw_kernel(FuseParams p) {
   }
   __syncthreads();
   for (int e = threadIdx.x; e < p.C * kFuseTok; e += blockDim.x) {
-    const int c = e / kFuseTok, r = e - c * kFuseTok;
+    const int c = e >> p.tokb_log2, r = e & (kFuseTok - 1);
     if (r < m) {
       const int t = t0 + r;
       const int b = p.d_hw.div(t), thw = t - b * hw;
@@ -506,16 +508,17 @@ static int launch_fuse_pg(FuseParams p, cudaStream_t stream) {
   p.d_hc = FastDiv(ng);
   const size_t total = (size_t)p.B * p.H * p.W * ng;
   if (p.out_nchw) {
+    // tokens per CTA: one (token, pair group) work item per thread, fewer for small maps so
+    // that the grid still covers the SMs; a power of two >= 16
     const int ntok = p.B * p.H * p.W;
-    if (ntok >= 148 * 4 * 64) {                      // 64-token groups: 256-byte NCHW runs
-      const size_t smem = (size_t)p.C * (64 + 1) * sizeof(float);
-      HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T, 64, PG>, smem));
-      HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T, 64, PG>, dim3(ceil_div(ntok, 64)), dim3(256), smem, stream, p));
-    } else {                                         // small maps: more, smaller CTAs
-      const size_t smem = (size_t)p.C * (16 + 1) * sizeof(float);
-      HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T, 16, PG>, smem));
-      HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T, 16, PG>, dim3(ceil_div(ntok, 16)), dim3(256), smem, stream, p));
-    }
+    int tokb = 16, lg = 4;
+    while (tokb * 2 * ng <= 256 && ntok / (tokb * 2) >= 148) { tokb *= 2; ++lg; }
+    p.tokb = tokb;
+    p.tokb_log2 = lg;
+    const size_t smem = (size_t)p.C * (tokb + 1) * sizeof(float);
+    HRF_REQUIRE(smem <= 200 * 1024, HRF_EUNSUPPORTED, "fuse_sum: C=%d too wide for the NCHW copy", p.C);
+    HRF_CUDA(ensure_smem((const void*)fuse_sum_nchw_kernel<T, PG>, smem));
+    HRF_CUDA(launch_pdl(fuse_sum_nchw_kernel<T, PG>, dim3(ceil_div(ntok, tokb)), dim3(256), smem, stream, p));
   } else {
     // 128-thread CTAs: few threads in total (one per token and pair group), spread them
     const int grid = (int)((total + 127) / 128 < 148 * 32 ? (total + 127) / 128 : 148 * 32);
