@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 HRF_F32, HRF_BF16 = 0, 1
 MAX_FUSE_TERMS = 4
@@ -47,6 +47,10 @@ class ConvDesc(C.Structure):
 class StemDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('Cin', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('Cout', C.c_int32), ('relu', C.c_int32)]
+
+
+class BnDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('C', C.c_int32), ('HW', C.c_int32), ('dtype', C.c_int32)]
 
 
 class FuseDesc(C.Structure):
@@ -96,6 +100,13 @@ SIGNATURES = {
                                     C.c_void_p]),
     'hrf_bias_act_fwd': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hrf_bn_workspace_bytes': (C.c_size_t, [C.POINTER(BnDesc)]),
+    'hrf_bn_stats': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
+    'hrf_bn_bwd_stats': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'hrf_bn_affine': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p]),
     'hrf_nchw_to_nhwc': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,

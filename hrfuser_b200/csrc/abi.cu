@@ -20,6 +20,7 @@
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
 #include "window_attn.cuh"
+#include "bn_train.cuh"
 
 namespace hrf {
 
@@ -587,6 +588,44 @@ int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, v
     return launch_bias_act<__nv_bfloat16>(y, bias, residual, (size_t)n_tokens, C, relu,
                                           (cudaStream_t)stream);
   HRF_REQUIRE(false, HRF_EINVAL, "bias_act: dtype");
+}
+
+static int bn_check(const HrfBnDesc* d) {
+  HRF_REQUIRE(d != nullptr, HRF_EINVAL, "bn: null descriptor");
+  HRF_REQUIRE(d->B > 0 && d->C > 0 && d->HW > 0, HRF_EINVAL, "bn: B=%d C=%d HW=%d", d->B, d->C, d->HW);
+  HRF_REQUIRE(d->dtype == HRF_F32 || d->dtype == HRF_BF16, HRF_EINVAL, "bn: dtype");
+  return HRF_OK;
+}
+size_t hrf_bn_workspace_bytes(const HrfBnDesc* d) {
+  if (bn_check(d) != HRF_OK) return 0;
+  return bn_workspace_bytes(d->B, d->C, d->HW);
+}
+int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* sums, void* ws, size_t ws_bytes,
+                 void* stream) {
+  if (int rc = bn_check(d)) return rc;
+  HRF_REQUIRE(x && sums && ws, HRF_EINVAL, "bn_stats: null pointer");
+  HRF_REQUIRE(ws_bytes >= bn_workspace_bytes(d->B, d->C, d->HW), HRF_EINVAL, "bn_stats: workspace too small");
+  if (d->dtype == HRF_F32)
+    return launch_bn_reduce<float, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, sums, ws, (cudaStream_t)stream);
+  return launch_bn_reduce<__nv_bfloat16, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, sums, ws, (cudaStream_t)stream);
+}
+int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const float* mean,
+                     const float* invstd, double* sums, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = bn_check(d)) return rc;
+  HRF_REQUIRE(x && dy && mean && invstd && sums && ws, HRF_EINVAL, "bn_bwd_stats: null pointer");
+  HRF_REQUIRE(ws_bytes >= bn_workspace_bytes(d->B, d->C, d->HW), HRF_EINVAL, "bn_bwd_stats: workspace too small");
+  if (d->dtype == HRF_F32)
+    return launch_bn_reduce<float, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, ws, (cudaStream_t)stream);
+  return launch_bn_reduce<__nv_bfloat16, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, ws, (cudaStream_t)stream);
+}
+int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a, const float* b,
+                  const float* c0, int32_t relu, void* out, void* stream) {
+  if (int rc = bn_check(d)) return rc;
+  HRF_REQUIRE(x && a && c0 && out, HRF_EINVAL, "bn_affine: null pointer");
+  HRF_REQUIRE(!dy || b, HRF_EINVAL, "bn_affine: b is required with dy");
+  if (d->dtype == HRF_F32)
+    return launch_bn_affine<float>(d->B, d->C, d->HW, x, dy, a, b, c0, relu, out, (cudaStream_t)stream);
+  return launch_bn_affine<__nv_bfloat16>(d->B, d->C, d->HW, x, dy, a, b, c0, relu, out, (cudaStream_t)stream);
 }
 
 int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t b_mn_major,

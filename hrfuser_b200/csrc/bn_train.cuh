@@ -1,0 +1,314 @@
+// Train-mode BatchNorm / SyncBatchNorm on NCHW planes: the per-channel
+// batch statistics the reference gets from nn.BatchNorm2d / nn.SyncBatchNorm
+// (mmcv build_norm_layer; hrnet.py:338-358, hrformer.py:267-282, resnet.py:161-206) and the
+// per-channel affine passes of its forward and backward.
+//
+//   bn_reduce_kernel<T, VEC, BWD>   one CTA per (plane, chunk of 256 * 4 * VEC elements):
+//        BWD = false: chunk count / mean / M2 (the chunk stays in registers between the sum and
+//                     the centred second moment, so E[x^2] - mean^2 cancellation never happens
+//                     in fp32)
+//        BWD = true : sum(dy), sum(dy * (x - mean) * invstd)
+//        -> one float2 partial per CTA, [b][chunk][c]
+//   bn_finalize_kernel<BWD>         one warp per channel: fixed-order combination of the
+//        partials in fp64 (Chan's update for the forward) -> sums[0..C) , sums[C..2C) (fp64,
+//        additive across ranks: sum x | sum x^2, or sum dy | sum dy * xhat)
+//   bn_affine_kernel<T, VEC, TWO>   out = a[c] * x + c0[c]            (forward normalise)
+//                                   out = a[c] * dy + b[c] * x + c0[c] (backward dx)
+//
+// All three are pure streaming kernels: 16-byte loads, four in flight per thread, no reuse.
+// Deterministic: no atomics; the partial order is fixed by (b, chunk).
+#pragma once
+#include "common.cuh"
+
+namespace hrf {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnVecPerThread = 4;
+
+template <typename T>
+__device__ __forceinline__ float bn_to_float(T v) { return (float)v; }
+
+template <typename T, int VEC>
+__device__ __forceinline__ void bn_load(const T* p, float (&f)[VEC]) {
+  if constexpr (VEC == 1) {
+    f[0] = bn_to_float(__ldg(p));
+  } else {
+    static_assert(sizeof(T) * VEC == 16, "16-byte vectors");
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const T* q = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = bn_to_float(q[i]);
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void bn_store(T* p, const float (&f)[VEC]) {
+  if constexpr (VEC == 1) {
+    p[0] = (T)f[0];
+  } else {
+    uint4 u;
+    T* q = reinterpret_cast<T*>(&u);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) q[i] = (T)f[i];
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+}
+
+// block-wide sum of two floats; result valid in every thread
+__device__ __forceinline__ float2 bn_block_sum2(float a, float b, float2* red /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5;
+  __syncthreads();                      // red may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) red[w] = make_float2(a, b);
+  __syncthreads();
+  float2 s = red[0];
+#pragma unroll
+  for (int i = 1; i < kBnThreads / 32; ++i) {
+    s.x += red[i].x;
+    s.y += red[i].y;
+  }
+  return s;
+}
+
+template <typename T, int VEC, bool BWD>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                 const float* __restrict__ invstd, float2* __restrict__ part, int C, int HW,
+                 FastDiv chunks_div) {
+  constexpr int NV = kBnVecPerThread;
+  constexpr int CH = kBnThreads * NV * VEC;
+  __shared__ float2 red[kBnThreads / 32];
+  const int chunks = (int)chunks_div.d;
+  const int plane = chunks_div.div((int)blockIdx.x);
+  const int chunk = (int)blockIdx.x - plane * chunks;
+  const int b = plane / C, c = plane - b * C;
+  const int e0 = chunk * CH;
+  const int n = min(CH, HW - e0);
+  const size_t base = (size_t)plane * HW + e0;
+
+  float v[NV][VEC];
+  float s0 = 0.f, s1 = 0.f;
+  if constexpr (!BWD) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+      if (o < n) {
+        bn_load<T, VEC>(x + base + o, v[i]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s0 += v[i][j];
+      }
+    }
+    const float m = bn_block_sum2(s0, 0.f, red).x / (float)n;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+      if (o < n) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float d = v[i][j] - m;
+          s1 = fmaf(d, d, s1);
+        }
+      }
+    }
+    const float m2 = bn_block_sum2(s1, 0.f, red).x;
+    if (threadIdx.x == 0) part[((size_t)b * chunks + chunk) * C + c] = make_float2(m, m2);
+  } else {
+    const float mu = __ldg(mean + c), is = __ldg(invstd + c);
+    float g[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+      if (o < n) {
+        bn_load<T, VEC>(x + base + o, v[i]);
+        bn_load<T, VEC>(dy + base + o, g[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+      if (o < n) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          s0 += g[i][j];
+          s1 = fmaf(g[i][j], (v[i][j] - mu) * is, s1);
+        }
+      }
+    }
+    const float2 s = bn_block_sum2(s0, s1, red);
+    if (threadIdx.x == 0) part[((size_t)b * chunks + chunk) * C + c] = s;
+  }
+}
+
+// One warp per channel.  Lane l combines partials l, l + 32, ... in order, then the 32 lane
+// results are combined by a fixed shuffle tree: the result depends only on the shapes.
+template <bool BWD>
+__global__ void __launch_bounds__(128)
+bn_finalize_kernel(const float2* __restrict__ part, double* __restrict__ sums, int C, int HW,
+                   int n_part /* B * chunks */, int chunks, int chunk_elems) {
+  const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  if constexpr (BWD) {
+    double a = 0.0, b = 0.0;
+    for (int p = lane; p < n_part; p += 32) {
+      const float2 v = part[(size_t)p * C + c];
+      a += (double)v.x;
+      b += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      sums[c] = a;
+      sums[C + c] = b;
+    }
+  } else {
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int p = lane; p < n_part; p += 32) {
+      const int chunk = p % chunks;
+      const double ni = (double)min(chunk_elems, HW - chunk * chunk_elems);
+      const float2 v = part[(size_t)p * C + c];
+      const double d = (double)v.x - mean, nn = n + ni;
+      mean += d * ni / nn;
+      m2 += (double)v.y + d * d * n * ni / nn;
+      n = nn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double n2 = __shfl_xor_sync(0xffffffffu, n, o);
+      const double mean2 = __shfl_xor_sync(0xffffffffu, mean, o);
+      const double m22 = __shfl_xor_sync(0xffffffffu, m2, o);
+      const double nn = n + n2;
+      if (nn > 0.0) {
+        // symmetric in (this, other): both lanes of a pair compute the same value
+        const double d = mean2 - mean;
+        const double mnew = (n * mean + n2 * mean2) / nn;
+        m2 = m2 + m22 + d * d * n * n2 / nn;
+        mean = mnew;
+        n = nn;
+      }
+    }
+    if (lane == 0) {
+      sums[c] = n * mean;
+      sums[C + c] = m2 + n * mean * mean;
+    }
+  }
+}
+
+template <typename T, int VEC, bool TWO>
+__global__ void __launch_bounds__(kBnThreads)
+bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ a,
+                 const float* __restrict__ bcoef, const float* __restrict__ c0, T* __restrict__ out,
+                 int C, int HW, FastDiv chunks_div, int relu) {
+  constexpr int NV = kBnVecPerThread;
+  constexpr int CH = kBnThreads * NV * VEC;
+  const int chunks = (int)chunks_div.d;
+  const int plane = chunks_div.div((int)blockIdx.x);
+  const int chunk = (int)blockIdx.x - plane * chunks;
+  const int c = plane % C;
+  const int e0 = chunk * CH;
+  const int n = min(CH, HW - e0);
+  const size_t base = (size_t)plane * HW + e0;
+  const float ka = __ldg(a + c), kc = __ldg(c0 + c);
+  float kb = 0.f;
+  if constexpr (TWO) kb = __ldg(bcoef + c);
+
+  float v[NV][VEC], g[NV][VEC];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+    if (o < n) {
+      bn_load<T, VEC>(x + base + o, v[i]);
+      if constexpr (TWO) bn_load<T, VEC>(dy + base + o, g[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
+    if (o < n) {
+      float r[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if constexpr (TWO) r[j] = fmaf(ka, g[i][j], fmaf(kb, v[i][j], kc));
+        else r[j] = fmaf(ka, v[i][j], kc);
+        if (relu) r[j] = fmaxf(r[j], 0.f);
+      }
+      bn_store<T, VEC>(out + base + o, r);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+struct BnGeom {
+  int vec, chunk_elems, chunks;
+  long long blocks;
+};
+template <typename T>
+static BnGeom bn_geom(int B, int C, int HW, const void* p0, const void* p1, const void* p2) {
+  constexpr int V16 = 16 / (int)sizeof(T);
+  auto al = [](const void* p) { return !p || (uintptr_t)p % 16 == 0; };
+  BnGeom g;
+  g.vec = (HW % V16 == 0 && al(p0) && al(p1) && al(p2)) ? V16 : 1;
+  g.chunk_elems = kBnThreads * kBnVecPerThread * g.vec;
+  g.chunks = ceil_div(HW, g.chunk_elems);
+  g.blocks = (long long)B * C * g.chunks;
+  return g;
+}
+// partials are laid out for the widest chunking (vec = 1 gives the most chunks)
+static size_t bn_workspace_bytes(int B, int C, int HW) {
+  const int chunks = ceil_div(HW, kBnThreads * kBnVecPerThread);
+  return (size_t)B * chunks * C * sizeof(float2);
+}
+
+template <typename T, bool BWD>
+static int launch_bn_reduce(int B, int C, int HW, const void* x, const void* dy, const float* mean,
+                            const float* invstd, double* sums, void* ws, cudaStream_t stream) {
+  const BnGeom g = bn_geom<T>(B, C, HW, x, dy, nullptr);
+  HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
+  const FastDiv cd(g.chunks);
+  float2* part = reinterpret_cast<float2*>(ws);
+  if (g.vec > 1)
+    bn_reduce_kernel<T, 16 / (int)sizeof(T), BWD><<<(unsigned)g.blocks, kBnThreads, 0, stream>>>(
+        (const T*)x, (const T*)dy, mean, invstd, part, C, HW, cd);
+  else
+    bn_reduce_kernel<T, 1, BWD><<<(unsigned)g.blocks, kBnThreads, 0, stream>>>(
+        (const T*)x, (const T*)dy, mean, invstd, part, C, HW, cd);
+  HRF_CUDA(cudaGetLastError());
+  bn_finalize_kernel<BWD><<<ceil_div(C, 4), 128, 0, stream>>>(part, sums, C, HW, B * g.chunks,
+                                                               g.chunks, g.chunk_elems);
+  count_launch(2);
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+template <typename T>
+static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy, const float* a,
+                            const float* b, const float* c0, int relu, void* out,
+                            cudaStream_t stream) {
+  const BnGeom g = bn_geom<T>(B, C, HW, x, dy, out);
+  HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
+  const FastDiv cd(g.chunks);
+  constexpr int V16 = 16 / (int)sizeof(T);
+  const unsigned grid = (unsigned)g.blocks;
+  if (dy) {
+    if (g.vec > 1)
+      bn_affine_kernel<T, V16, true><<<grid, kBnThreads, 0, stream>>>((const T*)x, (const T*)dy, a, b, c0, (T*)out, C, HW, cd, relu);
+    else
+      bn_affine_kernel<T, 1, true><<<grid, kBnThreads, 0, stream>>>((const T*)x, (const T*)dy, a, b, c0, (T*)out, C, HW, cd, relu);
+  } else {
+    if (g.vec > 1)
+      bn_affine_kernel<T, V16, false><<<grid, kBnThreads, 0, stream>>>((const T*)x, nullptr, a, b, c0, (T*)out, C, HW, cd, relu);
+    else
+      bn_affine_kernel<T, 1, false><<<grid, kBnThreads, 0, stream>>>((const T*)x, nullptr, a, b, c0, (T*)out, C, HW, cd, relu);
+  }
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+}  // namespace hrf

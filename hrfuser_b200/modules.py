@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .bn_train import HrfBatchNorm2d, HrfSyncBatchNorm
 from .window_maps import relative_position_index, window_geometry
 
 
@@ -29,9 +30,9 @@ def make_norm(cfg, channels):
     trainable = cfg.pop('requires_grad', True)
     cfg.setdefault('eps', 1e-5)
     if kind in ('BN', 'BN2d'):
-        m = nn.BatchNorm2d(channels, **cfg)
+        m = HrfBatchNorm2d(channels, **cfg)
     elif kind == 'SyncBN':
-        m = nn.SyncBatchNorm(channels, **cfg)
+        m = HrfSyncBatchNorm(channels, **cfg)
     elif kind == 'LN':
         m = nn.LayerNorm(channels, **cfg)
     else:

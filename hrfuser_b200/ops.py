@@ -365,3 +365,62 @@ def launch_count():
 def set_pdl(enable):
     """Programmatic dependent launch on/off (hrf_set_pdl); returns the previous setting."""
     return bool(_lib.load().hrf_set_pdl(1 if enable else 0))
+
+
+# ----------------------------------------------------------------------------
+# train-mode BatchNorm statistics / affine passes (NCHW planes)
+# ----------------------------------------------------------------------------
+def _bn_desc(x):
+    if not (x.is_cuda and x.dim() >= 2 and x.is_contiguous()):
+        raise ValueError('x must be a contiguous CUDA (B, C, ...) tensor')
+    B, Cc = x.shape[0], x.shape[1]
+    hw = x.numel() // (B * Cc)
+    return _lib.BnDesc(B, Cc, hw, _dtype_code(x))
+
+
+def _bn_reduce(x, dy, mean, invstd):
+    lib = _lib.load()
+    d = _bn_desc(x)
+    ws_bytes = lib.hrf_bn_workspace_bytes(C.byref(d))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    sums = torch.empty(2 * d.C, dtype=torch.float64, device=x.device)
+    with _timed('bn_stats' if dy is None else 'bn_bwd_stats', C=d.C,
+                bytes=x.numel() * x.element_size() * (1 if dy is None else 2), flops=0.0):
+        if dy is None:
+            check(lib.hrf_bn_stats(C.byref(d), x.data_ptr(), sums.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, _stream()))
+        else:
+            check(lib.hrf_bn_bwd_stats(C.byref(d), x.data_ptr(), dy.data_ptr(), mean.data_ptr(),
+                                       invstd.data_ptr(), sums.data_ptr(), ws.data_ptr(),
+                                       ws_bytes, _stream()))
+    return sums
+
+
+def bn_stats(x):
+    """x (B, C, *) contiguous -> fp64 [2C]: per-channel sum(x) | sum(x^2) over B and *."""
+    return _bn_reduce(x, None, None, None)
+
+
+def bn_bwd_stats(x, dy, mean, invstd):
+    """-> fp64 [2C]: per-channel sum(dy) | sum(dy * (x - mean) * invstd); mean/invstd fp32 [C]."""
+    if dy.shape != x.shape or dy.dtype != x.dtype or not dy.is_contiguous():
+        raise ValueError('dy must match x (shape, dtype, contiguous)')
+    return _bn_reduce(x, dy, mean.float().contiguous(), invstd.float().contiguous())
+
+
+def bn_affine(x, a, c0, dy=None, b=None, relu=False, out=None):
+    """out = a[c]*x + c0[c]   or, with dy,  a[c]*dy + b[c]*x + c0[c]  (per-channel fp32 a, b, c0)."""
+    lib = _lib.load()
+    d = _bn_desc(x)
+    out = torch.empty_like(x) if out is None else out
+    a, c0 = a.float().contiguous(), c0.float().contiguous()
+    if dy is not None:
+        if dy.shape != x.shape or dy.dtype != x.dtype or not dy.is_contiguous():
+            raise ValueError('dy must match x (shape, dtype, contiguous)')
+        b = b.float().contiguous()
+    with _timed('bn_affine' if dy is None else 'bn_bwd_affine', C=d.C,
+                bytes=x.numel() * x.element_size() * (2 if dy is None else 3), flops=0.0):
+        check(lib.hrf_bn_affine(C.byref(d), x.data_ptr(), dy.data_ptr() if dy is not None else None,
+                                a.data_ptr(), b.data_ptr() if dy is not None else None,
+                                c0.data_ptr(), int(relu), out.data_ptr(), _stream()))
+    return out

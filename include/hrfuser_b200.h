@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 4
+#define HRF_ABI_VERSION 5
 
 enum { HRF_F32 = 0, HRF_BF16 = 1 };
 enum {
@@ -207,6 +207,34 @@ int hrf_stem_conv_fwd(const HrfStemDesc* d, const float* x_nchw, const float* bl
  * bias is fp32 [C] (device); residual may be NULL. */
 int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, void* y,
                      const float* bias, const void* residual, void* stream);
+
+/* Train-mode BatchNorm / SyncBatchNorm statistics and per-channel affine passes on
+ * contiguous NCHW planes (x is [B][C][HW]), replacing what nn.BatchNorm2d /
+ * nn.SyncBatchNorm compute in the reference's training forward and backward
+ * (mmcv build_norm_layer call sites hrnet.py:338-358, hrformer.py:267-282,
+ * resnet.py:161-206; cfg norm_cfg=dict(type='SyncBN'),
+ * configs/_base_/models/cascade_rcnn_hrfuser_fpn_nus_clr_fusion.py:2).
+ *   hrf_bn_stats:      sums[0..C) = sum_x, sums[C..2C) = sum_x^2             (fp64, device)
+ *   hrf_bn_bwd_stats:  sums[0..C) = sum_dy, sums[C..2C) = sum_dy*(x-mean)*invstd
+ * Both are additive across ranks: the caller all-reduces the 2C doubles (+ count)
+ * over NCCL for SyncBN.  Deterministic (fixed-order two-stage reduction, the
+ * forward one centred per chunk so that fp32 never sees E[x^2] - mean^2).
+ * workspace >= hrf_bn_workspace_bytes(d).
+ *   hrf_bn_affine:  out = a[c]*x + c0[c]              (dy == NULL; forward normalise)
+ *                   out = a[c]*dy + b[c]*x + c0[c]    (backward dx)
+ * a, b, c0, mean, invstd: fp32 [C] on the device.  out may alias x or dy. */
+typedef struct {
+  int32_t B, C, HW;
+  int32_t dtype;
+} HrfBnDesc;
+size_t hrf_bn_workspace_bytes(const HrfBnDesc* d);
+int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* sums, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const float* mean,
+                     const float* invstd, double* sums, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a,
+                  const float* b, const float* c0, int32_t relu, void* out, void* stream);
 
 /* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
  * through the same descriptor helpers the fused kernels use.  B is [N][K]

@@ -1,0 +1,276 @@
+"""Train-mode BatchNorm / SyncBatchNorm (hrfuser_b200/bn_train.py, hrf_bn_* kernels).
+
+CPU (`-m "not gpu"`): the host logic — statistics message, cross-rank combination, affine
+coefficients, running statistics, parameter gradients — with the three kernels replaced by
+torch stand-ins defined HERE (test infrastructure), single process and world_size 2 on gloo,
+checked against torch's own BatchNorm on the full batch.
+GPU (`-m gpu`): the kernels themselves through the C-ABI against fp64 torch reductions and
+`nn.BatchNorm2d` in training mode (forward, dx, dweight, dbias, running statistics).
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from hrfuser_b200 import bn_train, ops
+from hrfuser_b200.modules import make_norm
+
+
+# ---- torch stand-ins of the three kernels (CPU tests only) ------------------------------
+def _emul_stats(x):
+    xd = x.double().flatten(2)
+    return torch.cat([xd.sum((0, 2)), (xd * xd).sum((0, 2))])
+
+
+def _emul_bwd_stats(x, dy, mean, invstd):
+    xd, gd = x.double().flatten(2), dy.double().flatten(2)
+    xhat = (xd - mean.double()[None, :, None]) * invstd.double()[None, :, None]
+    return torch.cat([gd.sum((0, 2)), (gd * xhat).sum((0, 2))])
+
+
+def _emul_affine(x, a, c0, dy=None, b=None, relu=False, out=None):
+    sh = (1, -1) + (1,) * (x.dim() - 2)
+    y = a.view(sh) * (x if dy is None else dy) + c0.view(sh)
+    if dy is not None:
+        y = y + b.view(sh) * x
+    return y.relu() if relu else y
+
+
+@pytest.fixture
+def emulated_kernels(monkeypatch):
+    monkeypatch.setattr(ops, 'bn_stats', _emul_stats)
+    monkeypatch.setattr(ops, 'bn_bwd_stats', _emul_bwd_stats)
+    monkeypatch.setattr(ops, 'bn_affine', _emul_affine)
+
+
+def _torch_bn_reference(x, w, b, dy, eps=1e-5):
+    bn = nn.BatchNorm2d(x.shape[1], eps=eps).to(x.device).train()
+    with torch.no_grad():
+        bn.weight.copy_(w)
+        bn.bias.copy_(b)
+    xr = x.clone().requires_grad_(True)
+    y = bn(xr)
+    y.backward(dy)
+    return y.detach(), xr.grad, bn.weight.grad, bn.bias.grad, bn.running_mean, bn.running_var
+
+
+def _case(B, C, H, W, seed=0, device='cpu', offset=0.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(B, C, H, W, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g))
+         + torch.randn(1, C, 1, 1, generator=g) + offset)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    return [t.to(device) for t in (x, w, b, dy)]
+
+
+def test_modules_keep_torch_state_dict_layout():
+    for kind, base in (('BN', nn.BatchNorm2d), ('SyncBN', nn.SyncBatchNorm)):
+        m = make_norm(dict(type=kind, requires_grad=True), 18)
+        assert isinstance(m, base) and isinstance(m, nn.modules.batchnorm._BatchNorm)
+        assert list(m.state_dict()) == list(base(18).state_dict())
+        assert m.eps == 1e-5 and m.momentum == 0.1
+
+
+def test_cpu_tensors_use_torch_batchnorm():
+    x, w, b, dy = _case(3, 6, 5, 7)
+    m = make_norm(dict(type='BN'), 6).train()
+    ref = nn.BatchNorm2d(6).train()
+    assert torch.equal(m(x), ref(x))
+
+
+def test_function_host_logic_single_process(emulated_kernels):
+    x, w, b, dy = _case(4, 10, 6, 9, seed=3)
+    y_ref, dx_ref, dw_ref, db_ref, rm, rv = _torch_bn_reference(x, w, b, dy)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y, mean, var, count = bn_train._BatchNormTrainFn.apply(xr, wr, br, 1e-5, None)
+    y.backward(dy)
+    assert int(count) == 4 * 6 * 9
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(xr.grad, dx_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(wr.grad, dw_ref, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(br.grad, db_ref, rtol=1e-5, atol=1e-4)
+    # running statistics as nn.BatchNorm2d updates them (momentum 0.1, unbiased variance)
+    n = float(count)
+    torch.testing.assert_close(0.1 * mean, rm, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(0.9 + 0.1 * var * n / (n - 1), rv, rtol=1e-5, atol=1e-6)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo')
+    ops.bn_stats, ops.bn_bwd_stats, ops.bn_affine = _emul_stats, _emul_bwd_stats, _emul_affine
+    x, w, b, dy = _case(5, 8, 4, 6, seed=11)          # the global batch; ranks get 3 + 2 frames
+    lo, hi = (0, 3) if rank == 0 else (3, 5)
+    xr = x[lo:hi].clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    group = bn_train.sync_group(None)
+    assert group is not None
+    y, mean, var, count = bn_train._BatchNormTrainFn.apply(xr, wr, br, 1e-5, group)
+    y.backward(dy[lo:hi])
+    # parameter gradients are rank-local; DDP would sum / average them
+    gw, gb = wr.grad.clone(), br.grad.clone()
+    dist.all_reduce(gw)
+    dist.all_reduce(gb)
+    parts = [None, None]
+    dist.all_gather_object(parts, (y.detach(), xr.grad))
+    if rank == 0:
+        y_ref, dx_ref, dw_ref, db_ref, rm, rv = _torch_bn_reference(x, w, b, dy)
+        y_all = torch.cat([p[0] for p in parts])
+        dx_all = torch.cat([p[1] for p in parts])
+        ok = (int(count) == 5 * 4 * 6
+              and torch.allclose(y_all, y_ref, rtol=1e-5, atol=1e-5)
+              and torch.allclose(dx_all, dx_ref, rtol=1e-4, atol=1e-5)
+              and torch.allclose(gw, dw_ref, rtol=1e-5, atol=1e-4)
+              and torch.allclose(gb, db_ref, rtol=1e-5, atol=1e-4)
+              and torch.allclose(0.1 * mean, rm, rtol=1e-5, atol=1e-6))
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_sync_statistics_two_ranks_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok
+
+
+# ---- GPU: the kernels ---------------------------------------------------------------------
+GPU_SHAPES = [(2, 64, 192, 320),      # stem
+              (8, 18, 96, 160), (8, 144, 12, 20),   # branch grids (HRFuser-T nus)
+              (2, 78, 96, 160),       # HRFuser-B
+              (3, 18, 5, 7),          # HW % 4 != 0: scalar path
+              (1, 7, 1, 1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', GPU_SHAPES)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gpu_stats_kernels(shape, dtype):
+    x, w, b, dy = _case(*shape, seed=1, device='cuda')
+    x, dy = x.to(dtype), dy.to(dtype)
+    C = shape[1]
+    s = ops.bn_stats(x)
+    ref = _emul_stats(x)
+    torch.testing.assert_close(s, ref, rtol=2e-6, atol=1e-6 * x.numel() / C)
+    assert torch.equal(s, ops.bn_stats(x))                       # deterministic
+    mean = (ref[:C] / (x.numel() / C)).float()
+    invstd = torch.rsqrt(ref[C:] / (x.numel() / C) - mean.double() ** 2 + 1e-5).float()
+    sb = ops.bn_bwd_stats(x, dy, mean, invstd)
+    refb = _emul_bwd_stats(x, dy, mean, invstd)
+    torch.testing.assert_close(sb, refb, rtol=1e-5, atol=2e-6 * x.numel() / C + 1e-4)
+    assert torch.equal(sb, ops.bn_bwd_stats(x, dy, mean, invstd))
+    a, kb, c0 = torch.randn(3, C, device='cuda')
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(ops.bn_affine(x, a, c0).float(),
+                               _emul_affine(x.float(), a, c0), **tol)
+    torch.testing.assert_close(ops.bn_affine(x, a, c0, dy=dy, b=kb, relu=True).float(),
+                               _emul_affine(x.float(), a, c0, dy=dy.float(), b=kb, relu=True), **tol)
+
+
+@pytest.mark.gpu
+def test_gpu_stats_large_mean_is_stable():
+    """mean / std = 1e4: E[x^2] - mean^2 in fp32 would lose the variance entirely."""
+    g = torch.Generator().manual_seed(2)
+    x = (1000.0 + 0.1 * torch.randn(4, 16, 64, 64, generator=g)).cuda()
+    s = ops.bn_stats(x)
+    n = x.numel() / 16
+    var = s[16:] / n - (s[:16] / n) ** 2
+    ref = x.double().transpose(0, 1).flatten(1).var(1, unbiased=False)
+    torch.testing.assert_close(var, ref, rtol=1e-4, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', GPU_SHAPES[:5])
+@pytest.mark.parametrize('kind', ['BN', 'SyncBN'])
+def test_gpu_module_matches_torch_batchnorm(shape, kind):
+    x, w, b, dy = _case(*shape, seed=4, device='cuda')
+    y_ref, dx_ref, dw_ref, db_ref, rm, rv = _torch_bn_reference(x, w, b, dy)
+    m = make_norm(dict(type=kind, requires_grad=True), shape[1]).cuda().train()
+    with torch.no_grad():
+        m.weight.copy_(w)
+        m.bias.copy_(b)
+    xr = x.clone().requires_grad_(True)
+    before = ops._lib.load().hrf_launch_count()
+    y = m(xr)
+    y.backward(dy)
+    assert ops._lib.load().hrf_launch_count() - before == 6      # 2 x (reduce, finalize) + 2 affine
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(xr.grad, dx_ref, rtol=1e-4, atol=1e-5)
+    n = x.numel() / shape[1]
+    torch.testing.assert_close(m.weight.grad, dw_ref, rtol=1e-4, atol=1e-6 * n)
+    torch.testing.assert_close(m.bias.grad, db_ref, rtol=1e-4, atol=1e-6 * n)
+    torch.testing.assert_close(m.running_mean, rm, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m.running_var, rv, rtol=1e-5, atol=1e-6)
+    assert int(m.num_batches_tracked) == 1
+    # channels-last input: same numbers
+    y2 = m(x.contiguous(memory_format=torch.channels_last))
+    torch.testing.assert_close(y2, y_ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_backbone_train_step_matches_torch_batchnorm(built_lib):
+    """One training step of the (tiny-topology) backbone: every BN on the hrf_bn_* kernels vs the
+    same network with the BNs demoted to torch's nn.BatchNorm2d (what the reference runs)."""
+    import copy
+    from hrfuser_b200 import HRFuserHRFormerBased, tiny_cfg
+    from hrfuser_b200.utils import randomize_parameters, synthetic_inputs
+    c = copy.deepcopy(tiny_cfg(2))
+    c.pop('type')
+    c['norm_cfg'] = dict(type='SyncBN', requires_grad=True)
+    net = HRFuserHRFormerBased(**c)
+    randomize_parameters(net, 1)
+    net = net.cuda().train()
+    ref = copy.deepcopy(net)
+    n_bn = 0
+    for m in ref.modules():
+        if isinstance(m, bn_train.HrfSyncBatchNorm):
+            m.__class__ = nn.BatchNorm2d          # single process: SyncBN == BN
+            n_bn += 1
+    assert n_bn > 50
+    x, mods = synthetic_inputs(4, 64, 64, (3, 3), seed=1)
+    x, mods = x.cuda(), [m.cuda() for m in mods]
+    lib = ops._lib.load()
+    res = []
+    for model in (net, ref):
+        torch.manual_seed(0)                      # DropPath / Dropout masks
+        before = lib.hrf_launch_count()
+        out = model(x, mods)
+        sum((o * o).mean() for o in out).backward()
+        res.append((out, lib.hrf_launch_count() - before))
+    (out_k, launches_k), (out_r, launches_r) = res
+    assert launches_k > 3 * n_bn and launches_r == 0
+    for a, b in zip(out_k, out_r):
+        assert (a - b).norm() / b.norm() < 1e-4
+    gk, gr = dict(net.named_parameters()), dict(ref.named_parameters())
+    worst = 0.0
+    for name, p in gr.items():
+        if p.grad is None:
+            assert gk[name].grad is None
+            continue
+        worst = max(worst, float((gk[name].grad - p.grad).norm() / (p.grad.norm() + 1e-12)))
+    assert worst < 5e-3, worst
+    bk, br = dict(net.named_buffers()), dict(ref.named_buffers())
+    for name, t in br.items():
+        if name.endswith('running_var') or name.endswith('running_mean'):
+            torch.testing.assert_close(bk[name], t, rtol=1e-4, atol=1e-5)
