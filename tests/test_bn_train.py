@@ -252,24 +252,36 @@ def test_gpu_backbone_train_step_matches_torch_batchnorm(built_lib):
     x, mods = x.cuda(), [m.cuda() for m in mods]
     lib = ops._lib.load()
     res = []
+    # TF32 convolutions round their inputs to 10 mantissa bits, which turns the 1e-7 differences
+    # between two correct BN implementations into 1e-3 ones after a few layers
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     for model in (net, ref):
         torch.manual_seed(0)                      # DropPath / Dropout masks
         before = lib.hrf_launch_count()
         out = model(x, mods)
         sum((o * o).mean() for o in out).backward()
         res.append((out, lib.hrf_launch_count() - before))
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     (out_k, launches_k), (out_r, launches_r) = res
     assert launches_k > 3 * n_bn and launches_r == 0
-    for a, b in zip(out_k, out_r):
-        assert (a - b).norm() / b.norm() < 1e-4
+    errs = [float((a - b).norm() / b.norm()) for a, b in zip(out_k, out_r)]
     gk, gr = dict(net.named_parameters()), dict(ref.named_parameters())
-    worst = 0.0
-    for name, p in gr.items():
-        if p.grad is None:
-            assert gk[name].grad is None
-            continue
-        worst = max(worst, float((gk[name].grad - p.grad).norm() / (p.grad.norm() + 1e-12)))
-    assert worst < 5e-3, worst
+    # Two correct BN implementations differ by ~1e-7 per call; 60 train-mode BNs over as few as
+    # 16 samples per channel amplify that (torch BN vs an fp64-exact BN on CPU: 4e-4 over all
+    # gradients, 3e-3 on single tensors).  Biases in front of a BN and the attention k biases
+    # have exactly zero gradient, so every difference is measured against the typical gradient
+    # size; the per-op gradients are pinned to 1e-4 by test_gpu_module_matches_torch_batchnorm.
+    have = [n for n, p in gr.items() if p.grad is not None]
+    assert all(gk[n].grad is None for n in gr if n not in have)
+    norms = torch.stack([gr[n].grad.norm() for n in have])
+    diffs = torch.stack([(gk[n].grad - gr[n].grad).norm() for n in have])
+    overall = float(diffs.norm() / norms.norm())
+    rel = diffs / (norms + 1e-2 * norms.median())
+    worst = (float(rel.max()), have[int(rel.argmax())])
+    print('outputs', errs, 'all gradients', overall, 'worst tensor', worst)
+    assert overall < 2e-3 and worst[0] < 5e-2, (overall, worst)
+    assert max(errs) < 1e-4, errs
     bk, br = dict(net.named_buffers()), dict(ref.named_buffers())
     for name, t in br.items():
         if name.endswith('running_var') or name.endswith('running_mean'):
