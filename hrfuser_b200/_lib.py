@@ -103,8 +103,14 @@ SIGNATURES = {
     'hrf_bn_workspace_bytes': (C.c_size_t, [C.POINTER(BnDesc)]),
     'hrf_bn_stats': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                C.c_void_p]),
+    'hrf_bn_normalize': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_bn_bwd_stats': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
+    'hrf_bn_bwd_dx': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrf_bn_affine': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

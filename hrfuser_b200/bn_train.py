@@ -23,14 +23,6 @@ import torch.nn as nn
 from . import ops
 
 
-def _stats_from_sums(sums, count, eps):
-    """fp64 [2C] (sum | sum of squares) and the element count -> fp64 mean, biased var, invstd."""
-    C = sums.numel() // 2
-    mean = sums[:C] / count
-    var = (sums[C:] / count - mean * mean).clamp_min_(0.0)
-    return mean, var, torch.rsqrt(var + eps)
-
-
 def _all_reduce_sum(t, group):
     if group is not None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -38,63 +30,43 @@ def _all_reduce_sum(t, group):
 
 
 class _BatchNormTrainFn(torch.autograd.Function):
-    """y = BN_train(x); returns (y, mean, biased var, total count) — the last three are
-    non-differentiable outputs used for the running statistics."""
+    """y = BN_train(x).  Forward: hrf_bn_stats -> [all-reduce] -> hrf_bn_normalize (which also
+    saves mean / invstd and updates the running statistics); backward: hrf_bn_bwd_stats ->
+    [all-reduce] -> hrf_bn_bwd_dx.  No per-channel math on the host side."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, group):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group):
         x = x.contiguous()
-        C = x.shape[1]
-        local_n = x.numel() // C
-        # [sum x | sum x^2 | count]: one fp64 message per BN for SyncBN
-        msg = torch.empty(2 * C + 1, dtype=torch.float64, device=x.device)
-        msg[:2 * C] = ops.bn_stats(x)
-        msg[2 * C] = local_n
-        _all_reduce_sum(msg, group)
-        count = msg[2 * C]
-        mean, var, invstd = _stats_from_sums(msg[:2 * C], count, eps)
-        w = weight.double() if weight is not None else torch.ones_like(mean)
-        b = bias.double() if bias is not None else torch.zeros_like(mean)
-        a = w * invstd
-        y = ops.bn_affine(x, a.float(), (b - mean * a).float())
-        mean32, var32, invstd32 = mean.float(), var.float(), invstd.float()
-        ctx.save_for_backward(x, weight, mean32, invstd32, count)
+        stats = _all_reduce_sum(ops.bn_stats(x), group)      # [sum x | sum x^2 | count], fp64
+        y, mean, invstd = ops.bn_normalize(x, stats, weight, bias, eps, momentum, running_mean,
+                                           running_var)
+        ctx.save_for_backward(x, weight, mean, invstd, stats)
         ctx.group = group
-        ctx.mark_non_differentiable(mean32, var32, count)
-        return y, mean32, var32, count
+        return y
 
     @staticmethod
-    def backward(ctx, dy, _dmean, _dvar, _dcount):
-        x, weight, mean, invstd, count = ctx.saved_tensors
+    def backward(ctx, dy):
+        x, weight, mean, invstd, stats = ctx.saved_tensors
         dy = dy.contiguous()
         C = x.shape[1]
-        sums = ops.bn_bwd_stats(x, dy, mean, invstd)       # local sum dy | sum dy * xhat
         # parameter gradients are rank-local (DDP averages them), as in torch's SyncBatchNorm
-        dweight = sums[C:].to(weight.dtype) if weight is not None and ctx.needs_input_grad[1] else None
-        dbias = sums[:C].to(dy.dtype) if ctx.needs_input_grad[2] else None
+        sums, dweight, dbias = ops.bn_bwd_stats(x, dy, mean, invstd, want_param_grads=True)
         dx = None
         if ctx.needs_input_grad[0]:
-            tot = _all_reduce_sum(sums.clone(), ctx.group) if ctx.group is not None else sums
-            mdy, mdyx = tot[:C] / count, tot[C:] / count
-            g = (weight.double() if weight is not None else torch.ones_like(mdy)) * invstd.double()
-            # dx = g * (dy - mean(dy) - xhat * mean(dy * xhat)),  xhat = (x - mean) * invstd
-            kb = -g * invstd.double() * mdyx
-            kc = -g * mdy - kb * mean.double()
-            dx = ops.bn_affine(x, g.float(), kc.float(), dy=dy, b=kb.float())
-        return dx, dweight, dbias, None, None
+            _all_reduce_sum(sums, ctx.group)
+            dx = ops.bn_bwd_dx(x, dy, sums, stats[2 * C:], weight, mean, invstd)
+        return (dx, dweight if weight is not None and ctx.needs_input_grad[1] else None,
+                dbias if ctx.needs_input_grad[2] else None, None, None, None, None, None)
 
 
 def _train_forward(mod, x, group):
     if mod.momentum is None:
         raise NotImplementedError('cumulative moving average (momentum=None) is not supported')
-    y, mean, var, count = _BatchNormTrainFn.apply(x, mod.weight, mod.bias, mod.eps, group)
-    if mod.track_running_stats and mod.running_mean is not None:
-        with torch.no_grad():
-            m = mod.momentum
-            unbiased = var * (count / (count - 1).clamp_min(1.0)).float()
-            mod.running_mean.mul_(1 - m).add_(mean.to(mod.running_mean.dtype), alpha=m)
-            mod.running_var.mul_(1 - m).add_(unbiased.to(mod.running_var.dtype), alpha=m)
-            mod.num_batches_tracked += 1
+    track = mod.track_running_stats and mod.running_mean is not None
+    y = _BatchNormTrainFn.apply(x, mod.weight, mod.bias, mod.running_mean if track else None,
+                                mod.running_var if track else None, mod.eps, mod.momentum, group)
+    if track:
+        mod.num_batches_tracked.add_(1)
     return y
 
 

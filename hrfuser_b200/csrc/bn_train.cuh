@@ -12,8 +12,11 @@
 //   bn_finalize_kernel<BWD>         one warp per channel: fixed-order combination of the
 //        partials in fp64 (Chan's update for the forward) -> sums[0..C) , sums[C..2C) (fp64,
 //        additive across ranks: sum x | sum x^2, or sum dy | sum dy * xhat)
-//   bn_affine_kernel<T, VEC, TWO>   out = a[c] * x + c0[c]            (forward normalise)
+//   bn_affine_kernel<T, VEC, TWO, MODE>  out = a[c] * x + c0[c]             (forward normalise)
 //                                   out = a[c] * dy + b[c] * x + c0[c] (backward dx)
+//        with a / b / c0 given, or derived inside the kernel from the reduced statistics
+//        (COEF_FWD also saves mean / invstd and updates the running statistics), so that a BN
+//        forward is 3 launches and nothing else on the host, a backward 3 more
 //
 // All three are pure streaming kernels: 16-byte loads, four in flight per thread, no reuse.
 // Deterministic: no atomics; the partial order is fixed by (b, chunk).
@@ -147,7 +150,8 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
 template <bool BWD>
 __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const float2* __restrict__ part, double* __restrict__ sums, int C, int HW,
-                   int n_part /* B * chunks */, int chunks, int chunk_elems) {
+                   int n_part /* B * chunks */, int chunks, int chunk_elems,
+                   float* __restrict__ dweight, float* __restrict__ dbias) {
   const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
@@ -166,6 +170,8 @@ bn_finalize_kernel(const float2* __restrict__ part, double* __restrict__ sums, i
     if (lane == 0) {
       sums[c] = a;
       sums[C + c] = b;
+      if (dbias) dbias[c] = (float)a;        // rank-local parameter gradients
+      if (dweight) dweight[c] = (float)b;
     }
   } else {
     double n = 0.0, mean = 0.0, m2 = 0.0;
@@ -196,15 +202,44 @@ bn_finalize_kernel(const float2* __restrict__ part, double* __restrict__ sums, i
     if (lane == 0) {
       sums[c] = n * mean;
       sums[C + c] = m2 + n * mean * mean;
+      if (c == 0) sums[2 * C] = n;           // element count: the third part of the SyncBN message
     }
   }
 }
 
-template <typename T, int VEC, bool TWO>
+// Where the per-channel coefficients of bn_affine_kernel come from.
+//   COEF_GIVEN: a / b / c0 arrays.
+//   COEF_FWD  : the (all-reduced) statistics message [sum x | sum x^2 | count] (fp64) + weight,
+//               bias, eps: y = (x - mean) * invstd * w + b.  The CTA of plane c, chunk 0 also
+//               stores mean / invstd for the backward and updates the running statistics.
+//   COEF_BWD  : the (all-reduced) [sum dy | sum dy * xhat] (fp64) + count, weight, mean, invstd:
+//               dx = w * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)).
+// One thread per CTA evaluates the handful of fp64 operations; the rest wait at a barrier with
+// their loads already in flight.
+enum { COEF_GIVEN = 0, COEF_FWD = 1, COEF_BWD = 2 };
+struct BnCoef {
+  const float* a;
+  const float* b;
+  const float* c0;
+  const double* sums;      // fwd: 2C + 1 (count last); bwd: 2C
+  const double* count;     // bwd: element count (device scalar)
+  const float* weight;     // may be NULL (1)
+  const float* bias;       // may be NULL (0)
+  const float* mean;       // bwd: saved
+  const float* invstd;     // bwd: saved
+  float* save_mean;        // fwd: out
+  float* save_invstd;      // fwd: out
+  float* running_mean;     // fwd: in / out, may be NULL
+  float* running_var;
+  float eps, momentum;
+};
+
+template <typename T, int VEC, bool TWO, int MODE>
 __global__ void __launch_bounds__(kBnThreads)
-bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ a,
-                 const float* __restrict__ bcoef, const float* __restrict__ c0, T* __restrict__ out,
-                 int C, int HW, FastDiv chunks_div, int relu) {
+bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef k,
+                 T* __restrict__ out, int C, int HW, FastDiv chunks_div, int relu) {
+  static_assert(MODE != COEF_BWD || TWO, "the backward reads x and dy");
+  static_assert(MODE != COEF_FWD || !TWO, "the forward reads x only");
   constexpr int NV = kBnVecPerThread;
   constexpr int CH = kBnThreads * NV * VEC;
   const int chunks = (int)chunks_div.d;
@@ -214,10 +249,6 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
   const int e0 = chunk * CH;
   const int n = min(CH, HW - e0);
   const size_t base = (size_t)plane * HW + e0;
-  const float ka = __ldg(a + c), kc = __ldg(c0 + c);
-  float kb = 0.f;
-  if constexpr (TWO) kb = __ldg(bcoef + c);
-
   float v[NV][VEC], g[NV][VEC];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -227,6 +258,54 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
       if constexpr (TWO) bn_load<T, VEC>(dy + base + o, g[i]);
     }
   }
+  // out = ka * (TWO ? dy : x - km) + kb * (x - km) + kc: centring x before the multiply keeps
+  // the result exact to fp32 rounding when |mean| >> std
+  float ka, kb = 0.f, kc, km = 0.f;
+  if constexpr (MODE == COEF_GIVEN) {
+    ka = __ldg(k.a + c);
+    kc = __ldg(k.c0 + c);
+    if constexpr (TWO) kb = __ldg(k.b + c);
+  } else {
+    __shared__ float coef[4];
+    if (threadIdx.x == 0) {
+      const double w = k.weight ? (double)__ldg(k.weight + c) : 1.0;
+      if constexpr (MODE == COEF_FWD) {
+        const double cnt = k.sums[2 * C];
+        const double mean = k.sums[c] / cnt;
+        const double var = fmax(k.sums[C + c] / cnt - mean * mean, 0.0);
+        const double invstd = 1.0 / sqrt(var + (double)k.eps);
+        const double a = w * invstd;
+        coef[0] = (float)a;
+        coef[1] = 0.f;
+        coef[2] = k.bias ? __ldg(k.bias + c) : 0.f;
+        coef[3] = (float)mean;
+        if (plane == c && chunk == 0) {            // b == 0: once per channel
+          k.save_mean[c] = (float)mean;
+          k.save_invstd[c] = (float)invstd;
+          if (k.running_mean) {
+            const double m = (double)k.momentum;
+            const double unbiased = var * (cnt / fmax(cnt - 1.0, 1.0));
+            k.running_mean[c] = (float)((1.0 - m) * (double)k.running_mean[c] + m * mean);
+            k.running_var[c] = (float)((1.0 - m) * (double)k.running_var[c] + m * unbiased);
+          }
+        }
+      } else {
+        const double cnt = *k.count;
+        const double mean = (double)__ldg(k.mean + c), invstd = (double)__ldg(k.invstd + c);
+        const double mdy = k.sums[c] / cnt, mdyx = k.sums[C + c] / cnt;
+        const double gs = w * invstd;
+        coef[0] = (float)gs;
+        coef[1] = (float)(-gs * invstd * mdyx);
+        coef[2] = (float)(-gs * mdy);
+        coef[3] = (float)mean;
+      }
+    }
+    __syncthreads();
+    ka = coef[0];
+    kb = coef[1];
+    kc = coef[2];
+    km = coef[3];
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int o = (i * kBnThreads + (int)threadIdx.x) * VEC;
@@ -234,8 +313,9 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
       float r[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        if constexpr (TWO) r[j] = fmaf(ka, g[i][j], fmaf(kb, v[i][j], kc));
-        else r[j] = fmaf(ka, v[i][j], kc);
+        const float xc = v[i][j] - km;
+        if constexpr (TWO) r[j] = fmaf(ka, g[i][j], fmaf(kb, xc, kc));
+        else r[j] = fmaf(ka, xc, kc);
         if (relu) r[j] = fmaxf(r[j], 0.f);
       }
       bn_store<T, VEC>(out + base + o, r);
@@ -267,7 +347,8 @@ static size_t bn_workspace_bytes(int B, int C, int HW) {
 
 template <typename T, bool BWD>
 static int launch_bn_reduce(int B, int C, int HW, const void* x, const void* dy, const float* mean,
-                            const float* invstd, double* sums, void* ws, cudaStream_t stream) {
+                            const float* invstd, double* sums, float* dweight, float* dbias, void* ws,
+                            cudaStream_t stream) {
   const BnGeom g = bn_geom<T>(B, C, HW, x, dy, nullptr);
   HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
   const FastDiv cd(g.chunks);
@@ -280,34 +361,42 @@ static int launch_bn_reduce(int B, int C, int HW, const void* x, const void* dy,
         (const T*)x, (const T*)dy, mean, invstd, part, C, HW, cd);
   HRF_CUDA(cudaGetLastError());
   bn_finalize_kernel<BWD><<<ceil_div(C, 4), 128, 0, stream>>>(part, sums, C, HW, B * g.chunks,
-                                                               g.chunks, g.chunk_elems);
+                                                               g.chunks, g.chunk_elems, dweight, dbias);
   count_launch(2);
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
 }
 
-template <typename T>
-static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy, const float* a,
-                            const float* b, const float* c0, int relu, void* out,
-                            cudaStream_t stream) {
+template <typename T, int MODE>
+static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy, const BnCoef& k,
+                            int relu, void* out, cudaStream_t stream) {
   const BnGeom g = bn_geom<T>(B, C, HW, x, dy, out);
   HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
   const FastDiv cd(g.chunks);
   constexpr int V16 = 16 / (int)sizeof(T);
   const unsigned grid = (unsigned)g.blocks;
-  if (dy) {
-    if (g.vec > 1)
-      bn_affine_kernel<T, V16, true><<<grid, kBnThreads, 0, stream>>>((const T*)x, (const T*)dy, a, b, c0, (T*)out, C, HW, cd, relu);
-    else
-      bn_affine_kernel<T, 1, true><<<grid, kBnThreads, 0, stream>>>((const T*)x, (const T*)dy, a, b, c0, (T*)out, C, HW, cd, relu);
-  } else {
-    if (g.vec > 1)
-      bn_affine_kernel<T, V16, false><<<grid, kBnThreads, 0, stream>>>((const T*)x, nullptr, a, b, c0, (T*)out, C, HW, cd, relu);
-    else
-      bn_affine_kernel<T, 1, false><<<grid, kBnThreads, 0, stream>>>((const T*)x, nullptr, a, b, c0, (T*)out, C, HW, cd, relu);
+  const T* xp = (const T*)x;
+  const T* dp = (const T*)dy;
+  T* op = (T*)out;
+  if constexpr (MODE != COEF_FWD) {
+    if (dy) {
+      if (g.vec > 1)
+        bn_affine_kernel<T, V16, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, relu);
+      else
+        bn_affine_kernel<T, 1, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, relu);
+      count_launch();
+      HRF_CUDA(cudaGetLastError());
+      return HRF_OK;
+    }
   }
-  count_launch();
-  HRF_CUDA(cudaGetLastError());
+  if constexpr (MODE != COEF_BWD) {
+    if (g.vec > 1)
+      bn_affine_kernel<T, V16, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, relu);
+    else
+      bn_affine_kernel<T, 1, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, relu);
+    count_launch();
+    HRF_CUDA(cudaGetLastError());
+  }
   return HRF_OK;
 }
 

@@ -378,34 +378,93 @@ def _bn_desc(x):
     return _lib.BnDesc(B, Cc, hw, _dtype_code(x))
 
 
-def _bn_reduce(x, dy, mean, invstd):
-    lib = _lib.load()
-    d = _bn_desc(x)
-    ws_bytes = lib.hrf_bn_workspace_bytes(C.byref(d))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    sums = torch.empty(2 * d.C, dtype=torch.float64, device=x.device)
-    with _timed('bn_stats' if dy is None else 'bn_bwd_stats', C=d.C,
-                bytes=x.numel() * x.element_size() * (1 if dy is None else 2), flops=0.0):
-        if dy is None:
-            check(lib.hrf_bn_stats(C.byref(d), x.data_ptr(), sums.data_ptr(), ws.data_ptr(),
-                                   ws_bytes, _stream()))
-        else:
-            check(lib.hrf_bn_bwd_stats(C.byref(d), x.data_ptr(), dy.data_ptr(), mean.data_ptr(),
-                                       invstd.data_ptr(), sums.data_ptr(), ws.data_ptr(),
-                                       ws_bytes, _stream()))
-    return sums
+_BN_WS = {}
+
+
+def _bn_workspace(lib, d, device):
+    """Partials buffer, cached per (device, stream): the calls on one stream are ordered."""
+    need = lib.hrf_bn_workspace_bytes(C.byref(d))
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _BN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _BN_WS[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+    return ws
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f'{name} must be a contiguous fp32 CUDA tensor')
+    return t.data_ptr()
+
+
+def _like_x(dy, x):
+    if dy.shape != x.shape or dy.dtype != x.dtype or not dy.is_contiguous():
+        raise ValueError('dy must match x (shape, dtype, contiguous)')
 
 
 def bn_stats(x):
-    """x (B, C, *) contiguous -> fp64 [2C]: per-channel sum(x) | sum(x^2) over B and *."""
-    return _bn_reduce(x, None, None, None)
+    """x (B, C, *) contiguous -> fp64 [2C + 1]: per-channel sum(x) | sum(x^2) | element count.
+    The SyncBN message: additive across ranks."""
+    lib = _lib.load()
+    d = _bn_desc(x)
+    ws = _bn_workspace(lib, d, x.device)
+    stats = torch.empty(2 * d.C + 1, dtype=torch.float64, device=x.device)
+    with _timed('bn_stats', C=d.C, bytes=x.numel() * x.element_size(), flops=0.0):
+        check(lib.hrf_bn_stats(C.byref(d), x.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                               ws.numel(), _stream()))
+    return stats
 
 
-def bn_bwd_stats(x, dy, mean, invstd):
-    """-> fp64 [2C]: per-channel sum(dy) | sum(dy * (x - mean) * invstd); mean/invstd fp32 [C]."""
-    if dy.shape != x.shape or dy.dtype != x.dtype or not dy.is_contiguous():
-        raise ValueError('dy must match x (shape, dtype, contiguous)')
-    return _bn_reduce(x, dy, mean.float().contiguous(), invstd.float().contiguous())
+def bn_normalize(x, stats, weight, bias, eps, momentum=0.0, running_mean=None, running_var=None,
+                 relu=False):
+    """y = BN(x) from the (all-reduced) `bn_stats` message; -> (y, mean, invstd); updates the
+    running statistics in place when given."""
+    lib = _lib.load()
+    d = _bn_desc(x)
+    y = torch.empty_like(x)
+    mean = torch.empty(d.C, dtype=torch.float32, device=x.device)
+    invstd = torch.empty_like(mean)
+    with _timed('bn_affine', C=d.C, bytes=2 * x.numel() * x.element_size(), flops=0.0):
+        check(lib.hrf_bn_normalize(C.byref(d), x.data_ptr(), stats.data_ptr(), _f32c(weight, 'weight'),
+                                   _f32c(bias, 'bias'), float(eps), float(momentum),
+                                   _f32c(running_mean, 'running_mean'),
+                                   _f32c(running_var, 'running_var'), mean.data_ptr(),
+                                   invstd.data_ptr(), int(relu), y.data_ptr(), _stream()))
+    return y, mean, invstd
+
+
+def bn_bwd_stats(x, dy, mean, invstd, want_param_grads=False):
+    """-> fp64 [2C]: per-channel sum(dy) | sum(dy * (x - mean) * invstd), and with
+    `want_param_grads` the fp32 (dweight, dbias) copies of the same (rank-local) numbers."""
+    lib = _lib.load()
+    d = _bn_desc(x)
+    _like_x(dy, x)
+    ws = _bn_workspace(lib, d, x.device)
+    sums = torch.empty(2 * d.C, dtype=torch.float64, device=x.device)
+    grads = torch.empty(2, d.C, dtype=torch.float32, device=x.device) if want_param_grads else None
+    with _timed('bn_bwd_stats', C=d.C, bytes=2 * x.numel() * x.element_size(), flops=0.0):
+        check(lib.hrf_bn_bwd_stats(C.byref(d), x.data_ptr(), dy.data_ptr(), _f32c(mean, 'mean'),
+                                   _f32c(invstd, 'invstd'), sums.data_ptr(),
+                                   grads[0].data_ptr() if want_param_grads else None,
+                                   grads[1].data_ptr() if want_param_grads else None,
+                                   ws.data_ptr(), ws.numel(), _stream()))
+    return (sums, grads[0], grads[1]) if want_param_grads else sums
+
+
+def bn_bwd_dx(x, dy, sums, count, weight, mean, invstd):
+    """dx of train-mode BN from the (all-reduced) `bn_bwd_stats` sums; `count` is the fp64
+    device scalar the forward message carried (stats[2C:])."""
+    lib = _lib.load()
+    d = _bn_desc(x)
+    _like_x(dy, x)
+    dx = torch.empty_like(x)
+    with _timed('bn_bwd_affine', C=d.C, bytes=3 * x.numel() * x.element_size(), flops=0.0):
+        check(lib.hrf_bn_bwd_dx(C.byref(d), x.data_ptr(), dy.data_ptr(), sums.data_ptr(),
+                                count.data_ptr(), _f32c(weight, 'weight'), _f32c(mean, 'mean'),
+                                _f32c(invstd, 'invstd'), dx.data_ptr(), _stream()))
+    return dx
 
 
 def bn_affine(x, a, c0, dy=None, b=None, relu=False, out=None):
@@ -415,8 +474,7 @@ def bn_affine(x, a, c0, dy=None, b=None, relu=False, out=None):
     out = torch.empty_like(x) if out is None else out
     a, c0 = a.float().contiguous(), c0.float().contiguous()
     if dy is not None:
-        if dy.shape != x.shape or dy.dtype != x.dtype or not dy.is_contiguous():
-            raise ValueError('dy must match x (shape, dtype, contiguous)')
+        _like_x(dy, x)
         b = b.float().contiguous()
     with _timed('bn_affine' if dy is None else 'bn_bwd_affine', C=d.C,
                 bytes=x.numel() * x.element_size() * (2 if dy is None else 3), flops=0.0):

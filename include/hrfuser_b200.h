@@ -214,25 +214,42 @@ int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, v
  * (mmcv build_norm_layer call sites hrnet.py:338-358, hrformer.py:267-282,
  * resnet.py:161-206; cfg norm_cfg=dict(type='SyncBN'),
  * configs/_base_/models/cascade_rcnn_hrfuser_fpn_nus_clr_fusion.py:2).
- *   hrf_bn_stats:      sums[0..C) = sum_x, sums[C..2C) = sum_x^2             (fp64, device)
- *   hrf_bn_bwd_stats:  sums[0..C) = sum_dy, sums[C..2C) = sum_dy*(x-mean)*invstd
- * Both are additive across ranks: the caller all-reduces the 2C doubles (+ count)
- * over NCCL for SyncBN.  Deterministic (fixed-order two-stage reduction, the
- * forward one centred per chunk so that fp32 never sees E[x^2] - mean^2).
+ *   hrf_bn_stats:      stats[0..C) = sum_x, stats[C..2C) = sum_x^2, stats[2C] = B*HW
+ *                      (2C + 1 doubles, device: the SyncBN message)
+ *   hrf_bn_bwd_stats:  sums[0..C) = sum_dy, sums[C..2C) = sum_dy*(x-mean)*invstd (2C doubles);
+ *                      dbias / dweight (fp32 [C], may be NULL) receive the same numbers: the
+ *                      rank-local parameter gradients
+ * Both are additive across ranks: for SyncBN the caller all-reduces them over NCCL between
+ * the statistics call and the apply call.  Deterministic (fixed-order two-stage reduction,
+ * the forward one centred per chunk so that fp32 never sees E[x^2] - mean^2).
  * workspace >= hrf_bn_workspace_bytes(d).
- *   hrf_bn_affine:  out = a[c]*x + c0[c]              (dy == NULL; forward normalise)
- *                   out = a[c]*dy + b[c]*x + c0[c]    (backward dx)
- * a, b, c0, mean, invstd: fp32 [C] on the device.  out may alias x or dy. */
+ *   hrf_bn_normalize:  y = (x - mean) * invstd * weight + bias from the (reduced) stats;
+ *                      stores mean / invstd (fp32 [C]) for the backward and, when
+ *                      running_mean / running_var are given, updates them in place with
+ *                      `momentum` and the unbiased variance, as nn.BatchNorm2d does.
+ *                      weight / bias may be NULL (1 / 0).
+ *   hrf_bn_bwd_dx:     dx = weight*invstd*(dy - sum_dy/n - xhat * sum_dy_xhat/n) from the
+ *                      (reduced) sums; count points at the forward's stats[2C].
+ *   hrf_bn_affine:     out = a[c]*x + c0[c]  (dy == NULL)  or  a[c]*dy + b[c]*x + c0[c],
+ *                      caller-supplied fp32 [C] coefficients.
+ * out / y / dx may alias their inputs. */
 typedef struct {
   int32_t B, C, HW;
   int32_t dtype;
 } HrfBnDesc;
 size_t hrf_bn_workspace_bytes(const HrfBnDesc* d);
-int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* sums, void* workspace,
+int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* stats, void* workspace,
                  size_t workspace_bytes, void* stream);
+int hrf_bn_normalize(const HrfBnDesc* d, const void* x, const double* stats, const float* weight,
+                     const float* bias, float eps, float momentum, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, int32_t relu,
+                     void* y, void* stream);
 int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const float* mean,
-                     const float* invstd, double* sums, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     const float* invstd, double* sums, float* dweight, float* dbias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int hrf_bn_bwd_dx(const HrfBnDesc* d, const void* x, const void* dy, const double* sums,
+                  const double* count, const float* weight, const float* mean,
+                  const float* invstd, void* dx, void* stream);
 int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a,
                   const float* b, const float* c0, int32_t relu, void* out, void* stream);
 

@@ -1,5 +1,5 @@
-"""HBM throughput of the train-mode BatchNorm kernels (hrf_bn_stats / hrf_bn_bwd_stats /
-hrf_bn_affine) at the training shapes of the backbone, against MEASURED_PEAKS.json.
+"""HBM throughput of the train-mode BatchNorm kernels (hrf_bn_stats / hrf_bn_normalize /
+hrf_bn_bwd_stats / hrf_bn_bwd_dx) at the training shapes of the backbone, against MEASURED_PEAKS.json.
 
 Each shape rotates over enough input sets to exceed the 126 MB L2; times are CUDA events
 around a CUDA graph of the rotating calls (no launch gaps).
@@ -63,16 +63,18 @@ def main():
         n_sets = min(n_sets, 64)
         xs = [torch.randn(B, C, H, W, device='cuda').to(dt) for _ in range(n_sets)]
         dys = [torch.randn(B, C, H, W, device='cuda').to(dt) for _ in range(n_sets)]
-        outs = [torch.empty_like(xs[0]) for _ in range(2)]
         mean = torch.zeros(C, device='cuda')
         invstd = torch.ones(C, device='cuda')
-        k = torch.randn(3, C, device='cuda')
+        w, bias = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
+        rm, rv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
+        stats = ops.bn_stats(xs[0])
+        sums = ops.bn_bwd_stats(xs[0], dys[0], mean, invstd)
         cases = {
             'bn_stats': (lambda i: ops.bn_stats(xs[i]), 1),
+            'bn_normalize': (lambda i: ops.bn_normalize(xs[i], stats, w, bias, 1e-5, 0.1, rm, rv), 2),
             'bn_bwd_stats': (lambda i: ops.bn_bwd_stats(xs[i], dys[i], mean, invstd), 2),
-            'bn_affine': (lambda i: ops.bn_affine(xs[i], k[0], k[2], out=outs[i % 2]), 2),
-            'bn_bwd_affine': (lambda i: ops.bn_affine(xs[i], k[0], k[2], dy=dys[i], b=k[1],
-                                                      out=outs[i % 2]), 3),
+            'bn_bwd_dx': (lambda i: ops.bn_bwd_dx(xs[i], dys[i], sums, stats[2 * C:], w, mean,
+                                                  invstd), 3),
         }
         for name, (fn, passes) in cases.items():
             us = graph_time_us(fn, n_sets)
@@ -84,7 +86,7 @@ def main():
             rows.append(row)
             print(f'{name:14s} {label:42s} {us:9.2f} us  {gbs:8.1f} GB/s  {gbs / peak:6.1%} of {peak:.0f}',
                   flush=True)
-        del xs, dys, outs
+        del xs, dys
         torch.cuda.empty_cache()
     if a.json:
         with open(a.json, 'w') as f:
