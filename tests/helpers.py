@@ -49,14 +49,14 @@ def assert_parity(got, ref, mode, what=''):
     return e
 
 
-def make_block(kind, C, heads, M=2, seed=0, with_pad_mask=False):
+def make_block(kind, C, heads, M=2, seed=0, with_pad_mask=False, win=7):
     """A randomised HRFormerBlock ('lsa') or HRFuserFusionBlock ('mwca') + its
     state_dict under the prefix 'blk'."""
     torch.manual_seed(seed)
     if kind == 'lsa':
-        blk = HRFormerBlock(C, C, heads, 7, 4, 0., BN, LN, with_pad_mask=with_pad_mask)
+        blk = HRFormerBlock(C, C, heads, win, 4, 0., BN, LN, with_pad_mask=with_pad_mask)
     else:
-        blk = HRFuserFusionBlock(C, C, heads, 7, 4, 0., BN, LN, num_fused_modalities=M)
+        blk = HRFuserFusionBlock(C, C, heads, win, 4, 0., BN, LN, num_fused_modalities=M)
     randomize_parameters(blk, seed)
     blk.eval()
     sd = {'blk.' + k: v for k, v in blk.state_dict().items()}

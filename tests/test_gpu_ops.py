@@ -24,21 +24,21 @@ def _nlc(t):
     return t.reshape(t.shape[0], -1, t.shape[-1])
 
 
-def _ref_lsa(x, sd, heads, H, W, pad_mask=False):
+def _ref_lsa(x, sd, heads, H, W, pad_mask=False, win=7):
     t = _nlc(x)
     n = O.layer_norm(t, sd, 'blk.norm1')
-    return (t + O.window_attention(n, n, sd, 'blk.attn', H, W, heads, False,
+    return (t + O.window_attention(n, n, sd, 'blk.attn', H, W, heads, False, Wh=win, Ww=win,
                                    with_pad_mask=pad_mask)).view_as(x)
 
 
-def _ref_mwca(x, zs, sd, heads, H, W):
+def _ref_mwca(x, zs, sd, heads, H, W, win=7):
     cam = _nlc(x)
     acc = cam.clone()
     for k, z in enumerate(zs):
         zt = _nlc(z)
         acc = acc + zt + O.window_attention(O.layer_norm(cam, sd, f'blk.norm1.{k}'),
                                             O.layer_norm(zt, sd, f'blk.norm2.{k}'),
-                                            sd, f'blk.attn.{k}', H, W, heads, True)
+                                            sd, f'blk.attn.{k}', H, W, heads, True, Wh=win, Ww=win)
     return acc.view_as(x)
 
 
@@ -81,6 +81,35 @@ def test_mwca(built_lib, H, W, C, heads, M, mode):
     with torch.no_grad():
         ref = _ref_mwca(x.float(), [z.float() for z in zs], sd, heads, H, W)
     assert_parity(got, ref, mode, f'mwca {H}x{W} C{C} M{M}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('win,H,W,C,heads', [
+    (14, 96, 160, 18, 1), (14, 48, 80, 36, 2), (14, 24, 40, 72, 4), (14, 12, 20, 144, 8),   # configs[4]
+    (14, 24, 40, 78, 2), (14, 12, 20, 312, 8),                                              # head_dim 39
+    (5, 13, 9, 36, 2), (16, 20, 33, 18, 1), (3, 7, 7, 72, 4), (1, 4, 5, 18, 1)])            # 16: largest
+def test_window_sizes(built_lib, win, H, W, C, heads, mode):
+    """Windows other than 7 (BASELINE.json configs[4] sweeps 7 and 14; the C-ABI takes
+    win^2 <= 256): LSA and 2-modality MWCA against the oracle."""
+    from hrfuser_b200 import ops
+    B = 2
+    e = _engine_stub()
+    blk, sd = make_block('lsa', C, heads, seed=win + C, win=win)
+    fblk, fsd = make_block('mwca', C, heads, M=2, seed=win + C + 1, win=win)
+    p_lsa, p_mwca = e._hrformer_block(blk), e._fusion_block(fblk)
+    e._upload()
+    assert p_lsa['win'] == win and p_mwca['win'] == win
+    x = tokens(B, H, W, C, seed=1).to(DT[mode])
+    zs = [tokens(B, H, W, C, seed=2 + k).to(DT[mode]) for k in range(2)]
+    got = ops.window_attention(x.cuda(), None, [s.t for s in p_lsa['attn']], heads, win=win)
+    got2 = ops.window_attention(x.cuda(), [z.cuda() for z in zs], [s.t for s in p_mwca['attn']],
+                                heads, win=win)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = _ref_lsa(x.float(), sd, heads, H, W, win=win)
+        ref2 = _ref_mwca(x.float(), [z.float() for z in zs], fsd, heads, H, W, win=win)
+    assert_parity(got, ref, mode, f'lsa win{win} {H}x{W} C{C}')
+    assert_parity(got2, ref2, mode, f'mwca win{win} {H}x{W} C{C}')
 
 
 def test_lsa_pad_mask(built_lib):

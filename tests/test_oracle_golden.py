@@ -105,3 +105,70 @@ def test_backbone_full_size_statistics():
         assert rel_err((yd ** 2).mean((0, 2, 3)), _t(E2E[f'full_t_nus_out{i}_chan_sqmean'])) < 1e-5
         idx = _t(E2E[f'full_t_nus_out{i}_idx'])
         assert rel_err(y.flatten()[idx], _t(E2E[f'full_t_nus_out{i}_val'])) < TOL
+
+
+# ---- windows other than 7 (tests/golden/make_golden_win.py) ---------------------------------
+OPS_WIN = np.load(os.path.join(G, 'ops_win.npz'))
+WIN_CASES = ['w14_c36', 'w14_c18', 'w5_c36', 'w16_c18']
+
+
+def _win_blocks(name):
+    win, C, heads, H, W = (int(v) for v in OPS_WIN[name + '_cfg'])
+    blk = HRFormerBlock(C, C, heads, win, 4, 0., BN, LN)
+    randomize_parameters(blk, 21)
+    fus = HRFuserFusionBlock(C, C, heads, win, 4, 0., BN, LN, num_fused_modalities=2, proj_drop_rate=0.1)
+    randomize_parameters(fus, 22)
+    assert abs(_checksum(blk) - float(OPS_WIN[name + '_checksum'])) < 1e-6
+    assert abs(_checksum(fus) - float(OPS_WIN[name + '_fus_checksum'])) < 1e-6
+    return win, C, heads, H, W, blk.eval(), fus.eval()
+
+
+@pytest.mark.parametrize('name', WIN_CASES)
+def test_window_sizes_oracle(name):
+    """oracle window attention with Wh = Ww != 7 against the reference's blocks"""
+    win, C, heads, H, W, blk, fus = _win_blocks(name)
+    sd = {'blk.' + k: v for k, v in blk.state_dict().items()}
+    x = _t(OPS_WIN[name + '_x'])
+    t = x.flatten(2).transpose(1, 2)
+    n = O.layer_norm(t, sd, 'blk.norm1')
+    a = t + O.window_attention(n, n, sd, 'blk.attn', H, W, heads, cross=False, Wh=win, Ww=win)
+    assert rel_err(a, _t(OPS_WIN[name + '_after_attn'])) < TOL
+    y = a + O.cross_ffn(O.layer_norm(a, sd, 'blk.norm2'), sd, 'blk.ffn', H, W)
+    assert rel_err(y.transpose(1, 2).reshape(x.shape), _t(OPS_WIN[name + '_y'])) < TOL
+    fsd = {'blk.' + k: v for k, v in fus.state_dict().items()}
+    acc = t.clone()
+    for k in range(2):
+        z = _t(OPS_WIN[f'{name}_z{k}']).flatten(2).transpose(1, 2)
+        acc = acc + z + O.window_attention(O.layer_norm(t, fsd, f'blk.norm1.{k}'),
+                                           O.layer_norm(z, fsd, f'blk.norm2.{k}'), fsd,
+                                           f'blk.attn.{k}', H, W, heads, cross=True, Wh=win, Ww=win)
+    acc = acc + O.cross_ffn(O.layer_norm(acc, fsd, 'blk.norm3'), fsd, 'blk.ffn', H, W)
+    assert rel_err(acc.transpose(1, 2).reshape(x.shape), _t(OPS_WIN[name + '_fus_y'])) < TOL
+
+
+@pytest.mark.parametrize('name', WIN_CASES)
+def test_window_sizes_packers(built_lib, name):
+    """the C packers + engine wiring for win != 7 (blob-level CPU emulation of the device ops)
+    and the training-path modules against the same goldens"""
+    import blob_emul
+    from hrfuser_b200.engine import BackboneEngine
+    win, C, heads, H, W, blk, fus = _win_blocks(name)
+    e = BackboneEngine.__new__(BackboneEngine)
+    e._host_blobs, e._blob_slots = [], []
+    e.device, e.dtype = torch.device('cpu'), torch.float32
+    p_lsa, p_fus = e._hrformer_block(blk), e._fusion_block(fus)
+    e._upload()
+    assert p_lsa['win'] == win
+    x = _t(OPS_WIN[name + '_x'])
+    xt = x.permute(0, 2, 3, 1).contiguous()
+    a = blob_emul.window_attention(xt, None, [s.t for s in p_lsa['attn']], heads, win=win)
+    assert rel_err(a.reshape(1, H * W, C), _t(OPS_WIN[name + '_after_attn'])) < 1e-5
+    zs = [_t(OPS_WIN[f'{name}_z{k}']).permute(0, 2, 3, 1).contiguous() for k in range(2)]
+    acc = blob_emul.window_attention(xt, zs, [s.t for s in p_fus['attn']], heads, win=win)
+    f = p_fus['ffn']
+    y = blob_emul.mixffn(acc, f['blob'].t, f['hidden'], f['eps'])
+    assert rel_err(y.permute(0, 3, 1, 2), _t(OPS_WIN[name + '_fus_y'])) < 1e-5
+    with torch.no_grad():
+        assert rel_err(blk(x), _t(OPS_WIN[name + '_y'])) < TOL
+        assert rel_err(fus(x, [_t(OPS_WIN[f'{name}_z{k}']) for k in range(2)]),
+                       _t(OPS_WIN[name + '_fus_y'])) < TOL

@@ -54,6 +54,7 @@ def main():
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--iters', type=int, default=30)
     ap.add_argument('--grids', default='nus,stf')
+    ap.add_argument('--wins', default='7', help='window sizes, e.g. 7,14')
     ap.add_argument('--out', default='')
     a = ap.parse_args()
     dt = torch.bfloat16 if a.precision == 'bf16' else torch.float32
@@ -61,14 +62,15 @@ def main():
     ridge = pk['bf16_tflops'] * 1e12 / (pk['hbm_gbs'] * 1e9)
     out = open(a.out, 'w') if a.out else None
     B = a.batch
-    for gname in a.grids.split(','):
+    for gname, win in [(g, int(w)) for w in a.wins.split(',') for g in a.grids.split(',')]:
+        S4 = 4 * win * win                                   # QK^T + PV flops per token and channel
         for (H, W), (C, heads) in zip(GRIDS[gname], WIDTHS):
             n_tok = B * H * W
             nbytes = n_tok * C * dt.itemsize
             n_sets = max(2, int(2 * 126e6 // max(nbytes, 1)) + 1)
             n_sets = min(n_sets, 64)
             xs = [torch.randn(B, H, W, C, device='cuda').to(dt) for _ in range(n_sets)]
-            cases = [('lsa', 0), ('mwca', 1), ('mwca', 2), ('mwca', 3), ('mixffn', 0)]
+            cases = [('lsa', 0), ('mwca', 1), ('mwca', 2), ('mwca', 3)] + ([('mixffn', 0)] if win == 7 else [])
             for kind, M in cases:
                 e = stub()
                 if kind == 'mixffn':
@@ -78,25 +80,25 @@ def main():
                     fn = lambda i: ops.mixffn(xs[i], f['blob'].t, f['hidden'], f['eps'])
                     flops, byts = n_tok * (16 * C * C + 72 * C), 2 * nbytes
                 elif kind == 'lsa':
-                    blk, _ = make_block('lsa', C, heads)
+                    blk, _ = make_block('lsa', C, heads, win=win)
                     pk_ = e._hrformer_block(blk)
                     e._upload()
                     blobs = [s.t for s in pk_['attn']]
-                    fn = lambda i: ops.window_attention(xs[i], None, blobs, heads)
-                    flops, byts = n_tok * (8 * C * C + 196 * C), 2 * nbytes
+                    fn = lambda i: ops.window_attention(xs[i], None, blobs, heads, win=win)
+                    flops, byts = n_tok * (8 * C * C + S4 * C), 2 * nbytes
                 else:
-                    blk, _ = make_block('mwca', C, heads, M=M)
+                    blk, _ = make_block('mwca', C, heads, M=M, win=win)
                     pk_ = e._fusion_block(blk)
                     e._upload()
                     blobs = [s.t for s in pk_['attn']]
                     zs = [xs[(k + 1) % n_sets] for k in range(M)]
-                    fn = lambda i: ops.window_attention(xs[i], zs, blobs, heads)
-                    flops, byts = M * n_tok * (8 * C * C + 196 * C), (2 + M) * nbytes
+                    fn = lambda i: ops.window_attention(xs[i], zs, blobs, heads, win=win)
+                    flops, byts = M * n_tok * (8 * C * C + S4 * C), (2 + M) * nbytes
                 ms = timed(fn, n_sets, a.iters)
                 gbs, tfs = byts / ms / 1e6, flops / ms / 1e9
                 bound = 'hbm' if flops / byts < ridge else 'tensor'
                 rec = dict(kind=kind, modalities=M, grid=gname, B=B, H=H, W=W, C=C, heads=heads,
-                           win=7, precision=a.precision, ms=round(ms, 5), GBps=round(gbs, 1),
+                           win=win, precision=a.precision, ms=round(ms, 5), GBps=round(gbs, 1),
                            TFLOPs=round(tfs, 2), bound=bound,
                            frac_hbm=round(gbs / pk['hbm_gbs'], 4),
                            frac_tensor=round(tfs / pk['bf16_tflops'], 5))
