@@ -165,6 +165,11 @@ static int attn_path(const HrfAttnDesc* d) {
   AttnParams p{};
   p.C = d->C; p.heads = d->heads; p.win = d->win;
   if (d->dtype == HRF_BF16 && attn_tc_supported(p) && !tc_disabled()) return PATH_TC;
+  // bf16 mode, windows other than 7: un-fused path with every contraction on tcgen05
+  // (projection GEMMs + attn_core_tc_kernel) instead of the FFMA fused kernel
+  if (d->dtype == HRF_BF16 && d->win != 7 && !tc_disabled() &&
+      core_tc_geom(d->win, d->C / d->heads).smem <= 200 * 1024)
+    return PATH_GENERIC;
   const AttnLayout L(d->C, d->heads, d->win);
   const size_t smem = L.smem_floats(d->n_kv > 0, kAttnThreads / 32) * sizeof(float);
   return (L.ldx <= 256 && smem <= 227 * 1024) ? PATH_FUSED_SIMT : PATH_GENERIC;

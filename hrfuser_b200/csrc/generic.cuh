@@ -4,8 +4,10 @@
 // count (C <= ~250 for the SIMT kernels, head_dim 18 for the tcgen05 ones).  HRFuser-B's
 // low-resolution branches (C = 312, 624; 16 heads of 39) go through this path instead:
 //   LayerNorm rows -> tiled fp32 GEMMs (+bias, activation, residuals) -> per-(window, head)
-//   attention core that gathers its 49 slots from the token tensors (pad slots contribute
-//   k = b_k, v = b_v exactly like the reference's zero padding after the norm).
+//   attention core that gathers its window slots from the token tensors (pad slots contribute
+//   k = b_k, v = b_v exactly like the reference's zero padding after the norm).  In bf16
+//   mode the GEMMs and the core (attn_core_tc_kernel: QK^T and PV as UMMAs, any window up to
+//   16 x 16) run on tcgen05; this is also the bf16 path of every window size other than 7.
 // Same packed fp32 weight sections as the fused SIMT kernels; intermediates live in a
 // caller-provided fp32 workspace.  Accuracy-first (fp32 FFMA, erff, expf).
 #pragma once
@@ -334,6 +336,215 @@ static size_t attn_generic_ws_floats(int B, int H, int W, int C, int heads, int 
   return n * C * (cross ? 5 : 4) + n * L.KO;      // xn (zn) q k v + o
 }
 
+// ---- attention core on the tensor cores (bf16 mode): one CTA per (window, head) ------------
+// Any window with S = win^2 <= 256 slots and any head_dim: S is padded to SP (multiple of 16,
+// the UMMA N / K granule), head_dim to HDP.  Per 128-row query tile:
+//   UMMA  S = Q K^T   (M 128, N SP, K HDP; Q and K K-major tiles)          -> TMEM
+//   rows: + relative position bias (table in shared memory), mask, max, exp, sum; the
+//         unnormalised P goes back to shared memory as a bf16 K-major tile
+//   UMMA  O = P V     (M 128, N HDP, K SP; V is the K-layout tile described MN-major)
+//         into the TMEM columns S occupied (every row has been read by then)
+//   rows: x 1/sum -> o (fp32, head padded), only for real tokens
+// Pad slots inside the window carry k = b_k, v = b_v (the reference pads after the norm).
+struct CoreTcGeom {
+  int S, SP, HDP, MT, T;
+  uint32_t tmem_cols;
+  size_t q_bytes, kv_bytes, p_bytes, smem;
+  FastDiv hdiv;            // by head_dim
+};
+static CoreTcGeom core_tc_geom(int win, int hd) {
+  CoreTcGeom g;
+  g.S = win * win;
+  g.SP = round_up(g.S, 16);
+  g.HDP = round_up(hd, 16);
+  g.MT = ceil_div(g.S, 128);
+  g.T = (2 * win - 1) * (2 * win - 1);
+  g.hdiv = FastDiv(hd);
+  g.tmem_cols = 32;
+  while ((int)g.tmem_cols < (g.SP > g.HDP ? g.SP : g.HDP)) g.tmem_cols <<= 1;
+  g.q_bytes = (size_t)g.MT * 128 * g.HDP * 2;
+  g.kv_bytes = (size_t)g.SP * g.HDP * 2;
+  g.p_bytes = (size_t)128 * g.SP * 2;
+  g.smem = g.q_bytes + 2 * g.kv_bytes + g.p_bytes + (size_t)round_up(g.T, 4) * 4 +
+           (size_t)g.MT * 128 * 4 + (size_t)g.SP * 4;
+  return g;
+}
+
+__global__ void __launch_bounds__(128) attn_core_tc_kernel(CoreParams p, CoreTcGeom g) {
+  using namespace umma;
+  extern __shared__ __align__(128) unsigned char core_tc_sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int win = p.win, S = g.S, SP = g.SP, HDP = g.HDP, MT = g.MT, hd = p.C / p.heads;
+  unsigned char* Qt = core_tc_sm;                       // MT x [HDP/8][128][8]
+  unsigned char* Kt = Qt + g.q_bytes;                   // [HDP/8][SP][8]
+  unsigned char* Vt = Kt + g.kv_bytes;                  // same bytes, described MN-major
+  unsigned char* Pt = Vt + g.kv_bytes;                  // [SP/8][128][8]
+  float* rpb = reinterpret_cast<float*>(Pt + g.p_bytes);
+  int* tok = reinterpret_cast<int*>(rpb + round_up(g.T, 4));       // [MT * 128]
+  int* joff = tok + MT * 128;                                      // [SP]
+  const int tid = threadIdx.x, warp = warp_idx_uniform();
+  const int h = blockIdx.y, wdx = blockIdx.x;
+  const int nWh = ceil_div(p.H, win), nWw = ceil_div(p.W, win);
+  const int pad_h = nWh * win - p.H, pad_w = nWw * win - p.W;
+  const bool use_mask = p.pad_mask && pad_h > 0 && pad_w > 0;
+  const int b = wdx / (nWh * nWw), wy = (wdx / nWw) % nWh, wx = wdx % nWw;
+  // tok: token index, -1 = zero-padded slot of the window, -2 = row beyond the window
+  for (int s = tid; s < MT * 128; s += 128) {
+    int t = -2;
+    if (s < S) {
+      const int y = wy * win + s / win - pad_h / 2, x = wx * win + s % win - pad_w / 2;
+      t = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? (b * p.H + y) * p.W + x : -1;
+    }
+    tok[s] = t;
+  }
+  for (int e = tid; e < g.T; e += 128) rpb[e] = __ldg(p.rpb + (size_t)h * g.T + e);
+  // joff[j]: offset of key slot j in a row of the bias table; keys beyond S: 0 (masked below)
+  for (int j = tid; j < SP; j += 128) joff[j] = j < S ? (j / win) * (2 * win - 1) + j % win : 0;
+  if (warp == 0) tmem_alloc(&tmem_base_s, g.tmem_cols);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // operand tiles: zero fill (row / column padding), then every real element by a thread of
+  // its own, head_dim fastest: a warp reads runs of hd consecutive floats (a per-row gather
+  // costs one L1 wavefront per thread and load instead)
+  for (size_t off = (size_t)tid * 16; off < g.q_bytes + 2 * g.kv_bytes; off += 128 * 16)
+    *reinterpret_cast<uint4*>(Qt + off) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  {
+    const int cb = h * hd;
+    // four elements per trip: their 12 global loads are issued before the first store
+    for (int e0 = tid; e0 < S * hd; e0 += 4 * 128) {
+      int sl[4], d[4], t[4];
+      float gq[4], gk[4], gv[4], pk[4], pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 128 < S * hd ? e0 + u * 128 : e0;
+        g.hdiv.divmod(e, sl[u], d[u]);
+        t[u] = tok[sl[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t off = (size_t)(t[u] >= 0 ? t[u] : 0) * p.C + cb + d[u];
+        gq[u] = __ldg(p.q + off);
+        gk[u] = __ldg(p.k + off);
+        gv[u] = __ldg(p.v + off);
+        pk[u] = __ldg(p.bk + cb + d[u]);
+        pv[u] = __ldg(p.bv + cb + d[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (e0 + u * 128 < S * hd) {
+          const bool real = t[u] >= 0;
+          *reinterpret_cast<__nv_bfloat16*>(Qt + (size_t)(sl[u] >> 7) * 128 * HDP * 2 +
+                                            tile_off(sl[u] & 127, d[u], 128)) = __float2bfloat16_rn(real ? gq[u] : 0.f);
+          *reinterpret_cast<__nv_bfloat16*>(Kt + tile_off(sl[u], d[u], SP)) = __float2bfloat16_rn(real ? gk[u] : pk[u]);
+          *reinterpret_cast<__nv_bfloat16*>(Vt + tile_off(sl[u], d[u], SP)) = __float2bfloat16_rn(real ? gv[u] : pv[u]);
+        }
+      }
+    }
+  }
+  const uint32_t q_addr = smem_u32(Qt), k_addr = smem_u32(Kt), v_addr = smem_u32(Vt), p_addr = smem_u32(Pt);
+  const uint32_t idesc_s = idesc_bf16(128, SP, false, false), idesc_o = idesc_bf16(128, HDP, false, true);
+  const int tw = 2 * win - 1;
+  uint32_t phase = 0;
+  for (int mt = 0; mt < MT; ++mt) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    const uint32_t tmem = tmem_base_s;
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      for (int ks = 0; ks < HDP / 16; ++ks)
+        mma_bf16(tmem, desc_kmajor(q_addr + (uint32_t)mt * 128u * (uint32_t)HDP * 2u, 128, ks),
+                 desc_kmajor(k_addr, SP, ks), idesc_s, ks > 0);
+      mma_commit(&bar);
+    }
+    cta_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    const int i = mt * 128 + tid, ic = i < S ? i : S - 1;
+    const int ti = tok[i];
+    const int ih = ic / win, iw = ic - ih * win;
+    const float* rrow = rpb + (ih + win - 1) * tw + (iw + win - 1);      // - joff[j]
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    constexpr float kLog2e = 1.4426950408889634f;
+    // pass 1: row maximum of (score + bias) in the log2 domain; branch-free so that the
+    // shared-memory lookups of the 16 columns overlap
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < SP; c0 += 32) {
+      float v[32];
+      const bool two = c0 + 16 < SP;                      // SP is a multiple of 16, not of 32
+      tmem_ld16(lane_addr + c0, v);
+      if (two) tmem_ld16(lane_addr + c0 + 16, v + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = (jj < 16 || two) ? c0 + jj : c0;
+        float s = (v[jj < 16 || two ? jj : 0] + rrow[-joff[j]]) * kLog2e;
+        const bool dead = j >= S || (use_mask && tok[j] < 0);
+        s = dead ? -INFINITY : s;
+        mx = fmaxf(mx, s);
+      }
+    }
+    // pass 2: p = 2^(s - max) (0 for dead keys), row sum, bf16 P tile
+    float sum = 0.f;
+    for (int c0 = 0; c0 < SP; c0 += 32) {
+      float v[32];
+      const bool two = c0 + 16 < SP;
+      tmem_ld16(lane_addr + c0, v);
+      if (two) tmem_ld16(lane_addr + c0 + 16, v + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const bool live = jj < 16 || two;
+        const int j = live ? c0 + jj : c0;
+        float s = fmaf(v[live ? jj : 0] + rrow[-joff[j]], kLog2e, -mx);
+        const bool dead = !live || j >= S || (use_mask && tok[j] < 0);
+        s = dead ? -INFINITY : s;
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s));
+        v[jj] = e;
+        sum += e;
+      }
+      st_chunk(Pt, tid, c0 / 8, 128, v);
+      st_chunk(Pt, tid, c0 / 8 + 1, 128, v + 8);
+      if (two) {
+        st_chunk(Pt, tid, c0 / 8 + 2, 128, v + 16);
+        st_chunk(Pt, tid, c0 / 8 + 3, 128, v + 24);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();                       // every row of S has been read: O may overwrite it
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      for (int ks = 0; ks < SP / 16; ++ks)
+        mma_bf16(tmem, desc_kmajor(p_addr, 128, ks), desc_mnmajor(v_addr, SP, ks), idesc_o, ks > 0);
+      mma_commit(&bar);
+    }
+    cta_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    for (int c0 = 0; c0 < HDP; c0 += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c0, v);
+      tmem_ld_wait();
+      if (ti >= 0) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (c0 + jj < hd) p.o[(size_t)ti * p.KO + h * p.hdp + c0 + jj] = v[jj] * inv;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, g.tmem_cols);
+}
+
 template <typename T>
 static int launch_window_attn_generic(const AttnParams& p, cudaStream_t st) {
   const AttnLayout L(p.C, p.heads, p.win);
@@ -369,12 +580,18 @@ static int launch_window_attn_generic(const AttnParams& p, cudaStream_t st) {
   HRF_CUDA(cudaMemsetAsync(o, 0, (size_t)n * L.KO * sizeof(float), st));   // head-pad lanes
   CoreParams c{q, k, v, o, blob + L.o_bk, blob + L.o_bv, blob + L.o_rpb,
                p.B, p.H, p.W, C, p.heads, p.win, L.KO, L.hdp, p.pad_mask};
-  const int S = p.win * p.win, ld = L.hd | 1;
-  const size_t smem = ((size_t)3 * S * ld + 4 * S + S) * sizeof(float);
-  HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "attn core: window %d x head_dim %d", p.win, L.hd);
-  HRF_CUDA(ensure_smem((const void*)attn_core_kernel, smem));
   dim3 grid(p.B * ceil_div(p.H, p.win) * ceil_div(p.W, p.win), p.heads);
-  attn_core_kernel<<<grid, 128, smem, st>>>(c);
+  const CoreTcGeom tg = core_tc_geom(p.win, L.hd);
+  if (tc && !tc_disabled() && tg.smem <= 200 * 1024 && tg.HDP <= 256) {
+    HRF_CUDA(ensure_smem((const void*)attn_core_tc_kernel, tg.smem));
+    attn_core_tc_kernel<<<grid, 128, tg.smem, st>>>(c, tg);
+  } else {
+    const int S = p.win * p.win, ld = L.hd | 1;
+    const size_t smem = ((size_t)3 * S * ld + 4 * S + S) * sizeof(float);
+    HRF_REQUIRE(smem <= 227 * 1024, HRF_EUNSUPPORTED, "attn core: window %d x head_dim %d", p.win, L.hd);
+    HRF_CUDA(ensure_smem((const void*)attn_core_kernel, smem));
+    attn_core_kernel<<<grid, 128, smem, st>>>(c);
+  }
   count_launch();
   HRF_CUDA(cudaGetLastError());
   // out = resid (+ z) + o Wo^T + bo

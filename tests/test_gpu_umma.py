@@ -7,7 +7,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('b_mn', [0, 1])
 @pytest.mark.parametrize('N,K', [(32, 16), (32, 32), (96, 32), (48, 48), (128, 32), (32, 128),
-                                 (192, 48), (80, 128), (256, 64)])
+                                 (192, 48), (80, 128), (256, 64),
+                                 (208, 32), (32, 208), (48, 208), (256, 48), (48, 256)])   # window-14 core
 def test_umma_selftest(built_lib, N, K, b_mn):
     from hrfuser_b200 import _lib
     g = torch.Generator().manual_seed(N * 1000 + K)
