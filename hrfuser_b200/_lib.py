@@ -9,9 +9,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
-HRF_F32, HRF_BF16 = 0, 1
+HRF_F32, HRF_BF16, HRF_U8 = 0, 1, 2
 MAX_FUSE_TERMS = 4
 
 
@@ -51,6 +51,12 @@ class StemDesc(C.Structure):
 
 class BnDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('C', C.c_int32), ('HW', C.c_int32), ('dtype', C.c_int32)]
+
+
+class InputDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
+                ('Hp', C.c_int32), ('Wp', C.c_int32), ('src_dtype', C.c_int32),
+                ('to_rgb', C.c_int32), ('pad_val', C.c_float)]
 
 
 class FuseDesc(C.Structure):
@@ -115,6 +121,8 @@ SIGNATURES = {
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p]),
+    'hrf_input_prologue_fwd': (C.c_int, [C.POINTER(InputDesc), C.c_void_p, _F, _F, C.c_void_p,
+                                         C.c_void_p]),
     'hrf_nchw_to_nhwc': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,
                                                      C.c_void_p]),
     'hrf_nhwc_to_nchw': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,

@@ -21,6 +21,7 @@
 #include "generic.cuh"
 #include "window_attn.cuh"
 #include "bn_train.cuh"
+#include "input_prologue.cuh"
 
 namespace hrf {
 
@@ -679,6 +680,29 @@ int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t
                       void* stream) {
   HRF_REQUIRE(A && B && D, HRF_EINVAL, "selftest: null pointer");
   return launch_umma_selftest(A, B, D, N, K, b_mn_major, (cudaStream_t)stream);
+}
+
+int hrf_input_prologue_fwd(const HrfInputDesc* d, const void* src, const float* mean,
+                           const float* std, float* dst, void* stream) {
+  HRF_REQUIRE(d && src && mean && std && dst, HRF_EINVAL, "input_prologue: null pointer");
+  HRF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, HRF_EINVAL, "input_prologue: empty source");
+  HRF_REQUIRE(d->C >= 1 && d->C <= INPUT_MAX_C, HRF_EUNSUPPORTED, "input_prologue: 1..4 channels, got %d", d->C);
+  HRF_REQUIRE(d->Hp >= d->H && d->Wp >= d->W, HRF_EINVAL, "input_prologue: padded size %dx%d smaller than the source %dx%d",
+              d->Hp, d->Wp, d->H, d->W);
+  HRF_REQUIRE(d->Wp % 4 == 0, HRF_EUNSUPPORTED, "input_prologue: padded width %d is not a multiple of 4", d->Wp);
+  HRF_REQUIRE(!d->to_rgb || d->C == 3, HRF_EINVAL, "input_prologue: to_rgb needs a 3-channel image");
+  HRF_REQUIRE(d->src_dtype == HRF_U8 || d->src_dtype == HRF_F32, HRF_EINVAL, "input_prologue: source dtype");
+  InputNorm nm{};
+  for (int c = 0; c < d->C; ++c) {
+    HRF_REQUIRE(std[c] != 0.f, HRF_EINVAL, "input_prologue: std[%d] is zero", c);
+    nm.mean[c] = mean[c];
+    nm.stdinv[c] = 1.0 / (double)std[c];   // mmcv.imnormalize: 1 / np.float64(std); cv2.multiply keeps it in fp64
+  }
+  if (d->src_dtype == HRF_U8)
+    return launch_input_prologue_t<uint8_t>(d->B, d->H, d->W, d->C, d->Hp, d->Wp, src, nm, d->to_rgb, d->pad_val,
+                                            dst, (cudaStream_t)stream);
+  return launch_input_prologue_t<float>(d->B, d->H, d->W, d->C, d->Hp, d->Wp, src, nm, d->to_rgb, d->pad_val, dst,
+                                        (cudaStream_t)stream);
 }
 
 int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, const void* src,

@@ -10,8 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnDesc, ConvDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, PwDesc, StemDesc,
-                   check)
+from ._lib import (AttnDesc, ConvDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, HRF_U8, InputDesc,
+                   PwDesc, StemDesc, check)
 
 _DT = {torch.float32: HRF_F32, torch.bfloat16: HRF_BF16}
 _F = C.POINTER(C.c_float)
@@ -336,6 +336,37 @@ def bias_act_(y, bias, residual=None, relu=True):
                                    bias.data_ptr(), residual.data_ptr() if residual is not None
                                    else None, _stream()))
     return y
+
+
+def input_prologue(src, mean, std, to_rgb=False, size_divisor=32, pad_val=0.0, out=None):
+    """(B, H, W, C) uint8 / fp32 sensor frames on the device -> normalised, padded fp32 NCHW
+    (B, C, ceil(H/div)*div, ceil(W/div)*div): `Normalize` + `Pad(size_divisor)` +
+    `DefaultFormatBundle` + collate of the reference's data pipeline in one kernel
+    (transforms.py:652-667,719-744, formating.py:211-227)."""
+    lib = _lib.load()
+    if not (src.is_cuda and src.dim() == 4 and src.is_contiguous()):
+        raise ValueError('src must be a contiguous CUDA (B,H,W,C) tensor')
+    if src.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f'unsupported sensor frame dtype {src.dtype}')
+    B, H, W, Cc = src.shape
+    mean = [float(m) for m in mean]
+    std = [float(v) for v in std]
+    if len(mean) != Cc or len(std) != Cc:
+        raise ValueError(f'mean / std must have {Cc} entries')
+    div = int(size_divisor) if size_divisor else 1
+    Hp, Wp = -(-H // div) * div, -(-W // div) * div
+    if out is None:
+        out = torch.empty(B, Cc, Hp, Wp, dtype=torch.float32, device=src.device)
+    elif tuple(out.shape) != (B, Cc, Hp, Wp) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError('out must be a contiguous fp32 (B,C,Hp,Wp) tensor')
+    d = InputDesc(B, H, W, Cc, Hp, Wp, HRF_U8 if src.dtype == torch.uint8 else HRF_F32, int(bool(to_rgb)),
+                  float(pad_val))
+    m = (C.c_float * Cc)(*mean)
+    s = (C.c_float * Cc)(*std)
+    with _timed('input_prologue', C=Cc, launches=1,
+                bytes=float(src.numel() * src.element_size() + out.numel() * 4), flops=float(2 * src.numel())):
+        check(lib.hrf_input_prologue_fwd(C.byref(d), src.data_ptr(), m, s, out.data_ptr(), _stream()))
+    return out
 
 
 def nchw_to_nhwc(x, dtype=None):

@@ -32,9 +32,9 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 5
+#define HRF_ABI_VERSION 6
 
-enum { HRF_F32 = 0, HRF_BF16 = 1 };
+enum { HRF_F32 = 0, HRF_BF16 = 1, HRF_U8 = 2 /* hrf_input_prologue_fwd source only */ };
 enum {
   HRF_OK = 0,
   HRF_EINVAL = -1,      /* bad descriptor / null pointer            */
@@ -259,6 +259,34 @@ int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float
  * N, K multiples of 16, <= 256.  Device pointers. */
 int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K,
                       int32_t b_mn_major, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Input prologue: Normalize -> Pad(size_divisor) ->
+ * DefaultFormatBundle -> batch for one sensor stream, one pass on the device.
+ * Replaces, per step and per sensor key ('img', 'lidar_img', 'radar_img', 'gated_img'):
+ *   Normalize.__call__            mmdet/datasets/pipelines/transforms.py:719-744
+ *     (mmcv.imnormalize, mmcv-full 1.3.17: astype(float32), optional BGR->RGB,
+ *      cv2.subtract(img, mean) in fp32, cv2.multiply(img, 1/float64(std)) in fp64)
+ *   Pad._pad_img                  transforms.py:652-667 (impad_to_multiple: pad_val bottom / right,
+ *                                 applied after Normalize)
+ *   DefaultFormatBundle.__call__  formating.py:211-227  (uint8 -> float32, HWC -> CHW)
+ *   and the collate stack of equally sized frames.
+ * src: (B, H, W, C) contiguous, HRF_U8 or HRF_F32, C in 1..4 (device pointer).
+ * mean / std: C host floats (the config's img_norm_cfg values as float32);
+ * stdinv = 1.0 / (double)std[c] is formed here exactly as the reference does.
+ * to_rgb reverses the channel order (3-channel images only).
+ * dst: (B, C, Hp, Wp) fp32, Hp >= H, Wp >= W, Wp a multiple of 4 (the reference pads to
+ * multiples of 32); pixels outside H x W are pad_val.
+ * y = fl32((double)fl32(x - mean[c]) * stdinv[c]), OpenCV's roundings: bit-exact to the reference. */
+typedef struct {
+  int32_t B, H, W, C;     /* source frames                                   */
+  int32_t Hp, Wp;         /* padded output size                              */
+  int32_t src_dtype;      /* HRF_U8 | HRF_F32                                */
+  int32_t to_rgb;         /* 1: BGR -> RGB before normalising                */
+  float pad_val;          /* Pad's pad_val['img'] (0 in every shipped config)*/
+} HrfInputDesc;
+int hrf_input_prologue_fwd(const HrfInputDesc* d, const void* src, const float* mean,
+                           const float* std, float* dst, void* stream);
 
 /* Layout converters at the boundary of the path. */
 int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t src_dtype,
