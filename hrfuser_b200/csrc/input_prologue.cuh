@@ -15,7 +15,9 @@
 // HBM-bound: reads B*H*W*C source elements (u8 or fp32) once, writes B*C*Hp*Wp fp32 once.
 // One thread per 4 consecutive output pixels of a row: the C*4 source elements of those
 // pixels are one contiguous run (a warp reads 128 consecutive pixels = one contiguous
-// segment), and each channel plane gets one 16-byte store, 512 bytes per warp.
+// segment), and each channel plane gets one 16-byte store, 512 bytes per warp.  The grid is one
+// thread per quad (no grid-stride loop): the kernel is 9-55 us long, so what matters is that all
+// loads are in flight at once, not CTA reuse.
 #pragma once
 #include "common.cuh"
 
@@ -38,14 +40,17 @@ __global__ void __launch_bounds__(256) input_prologue_kernel(const S* __restrict
                                                              float* __restrict__ dst, InputNorm nm,
                                                              int H, int W, int Hp, int Wp,
                                                              int to_rgb, float pad_val,
-                                                             long long n_quads) {
-  const int wq = Wp >> 2;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
-       q += (long long)gridDim.x * blockDim.x) {
-    const int xq = (int)(q % wq);
-    const long long r = q / wq;
-    const int y = (int)(r % Hp);
-    const long long b = r / Hp;
+                                                             int n_quads, FastDiv div_wq,
+                                                             FastDiv div_hp) {
+  // one quad (4 pixels of a row, all channels) per thread, no loop: every load of the launch is
+  // issued up front; 32-bit index arithmetic with magic-number division
+  {
+    const int q = (int)(blockIdx.x * 256u + threadIdx.x);
+    if (q >= n_quads) return;
+    int r, xq, bi, y;
+    div_wq.divmod(q, r, xq);
+    div_hp.divmod(r, bi, y);
+    const long long b = bi;
     const int x0 = xq << 2;
     float v[C][4];
 #pragma unroll
@@ -109,16 +114,17 @@ template <typename S>
 static int launch_input_prologue_t(int B, int H, int W, int C, int Hp, int Wp, const void* src,
                                    const InputNorm& nm, int to_rgb, float pad_val, float* dst,
                                    cudaStream_t stream) {
-  const long long n_quads = (long long)B * Hp * (Wp >> 2);
-  const int sms = 148;
-  const long long want = (n_quads + 255) / 256;
-  const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+  const long long n_quads_ll = (long long)B * Hp * (Wp >> 2);
+  HRF_REQUIRE(n_quads_ll < (1ll << 31) - 256, HRF_EUNSUPPORTED, "input_prologue: more than 2^33 output pixels");
+  const int n_quads = (int)n_quads_ll;
+  const int grid = (n_quads + 255) / 256;
+  const FastDiv dq(Wp >> 2), dh(Hp);
   const S* s = (const S*)src;
   switch (C) {
-    case 1: input_prologue_kernel<S, 1><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads); break;
-    case 2: input_prologue_kernel<S, 2><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads); break;
-    case 3: input_prologue_kernel<S, 3><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads); break;
-    case 4: input_prologue_kernel<S, 4><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads); break;
+    case 1: input_prologue_kernel<S, 1><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads, dq, dh); break;
+    case 2: input_prologue_kernel<S, 2><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads, dq, dh); break;
+    case 3: input_prologue_kernel<S, 3><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads, dq, dh); break;
+    case 4: input_prologue_kernel<S, 4><<<grid, 256, 0, stream>>>(s, dst, nm, H, W, Hp, Wp, to_rgb, pad_val, n_quads, dq, dh); break;
     default: HRF_REQUIRE(false, HRF_EUNSUPPORTED, "input_prologue: 1..4 channels");
   }
   count_launch();
