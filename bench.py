@@ -186,6 +186,8 @@ def run_ours(args):
     rank, world, local = hdist.init_from_env()
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    # one process per GPU, on the GPU's own NUMA node (pinned buffers are allocated below)
+    numa = 'off (HRF_NUMA_BIND=0)' if os.environ.get('HRF_NUMA_BIND') == '0' else hdist.bind_to_gpu_numa(local)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     cfg, net, (H, Wd), mod_ch = build_net(args.workload, args.precision, dev, seed=0)
     engine = net.engine()
@@ -348,7 +350,7 @@ def run_ours(args):
                        'timing': 'CUDA events around K graph replays, max over ranks'},
             'e2e': {'value': total_frames / (e2e_ms / 1e3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': bytes_in, 'd2h_bytes_per_step': d2h_bytes,
-                    'ms_per_step': e2e_ms / K,
+                    'ms_per_step': e2e_ms / K, 'host_affinity_rank0': numa,
                     'how': f'{n_slots} pipelined slots (stream + graph each): pinned fp32 host '
                            'inputs -> H2D -> forward -> D2H of the 4 fp32 maps; wall clock '
                            'around K steps incl. final sync, max over ranks'},

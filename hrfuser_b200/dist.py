@@ -31,6 +31,49 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def _cpu_ranges(cpus):
+    cpus = sorted(cpus)
+    out, i = [], 0
+    while i < len(cpus):
+        j = i
+        while j + 1 < len(cpus) and cpus[j + 1] == cpus[j] + 1:
+            j += 1
+        out.append(str(cpus[i]) if i == j else f'{cpus[i]}-{cpus[j]}')
+        i = j + 1
+    return ','.join(out)
+
+
+def bind_to_gpu_numa(local_rank):
+    """Restrict this process to the CPUs NVML reports as local to GPU `local_rank` (its NUMA
+    node), so the pinned host buffers it allocates afterwards are first-touched next to the
+    GPU's PCIe root and the H2D / D2H copies of the end-to-end path do not cross the socket
+    interconnect.  With 8 ranks each moving ~90 MB per 3 ms step that link is what saturates
+    first.  Call it before allocating pinned memory.  Returns a description of what was
+    done ('cpus 0-55' / the reason nothing was); never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (max(os.cpu_count() or 64, 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        near = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = near & allowed
+        if not cpus:
+            return f'unbound (GPU-local cpus {_cpu_ranges(near)} not in this cpuset)'
+        if cpus == allowed:
+            return f'cpus {_cpu_ranges(cpus)} (whole cpuset is GPU-local)'
+        os.sched_setaffinity(0, cpus)
+        return f'cpus {_cpu_ranges(cpus)}'
+    except Exception as e:      # no NVML, no permission: run unbound
+        return f'unbound ({type(e).__name__}: {e})'
+
+
 def shard_bounds(n_frames, rank, world):
     """Contiguous, balanced [lo, hi) slice of a global batch for `rank`."""
     base, rem = divmod(n_frames, world)

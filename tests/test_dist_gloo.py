@@ -75,3 +75,15 @@ def test_two_rank_shard_and_gather(built_lib, n_frames):
     assert ok
     assert all(s[0] == n_frames for s in shapes)
     assert t == 2.0
+
+
+def test_numa_binding_helper_never_raises_and_formats_ranges():
+    from hrfuser_b200 import dist as hdist
+    assert hdist._cpu_ranges({0, 1, 2, 5, 7, 8}) == '0-2,5,7-8'
+    assert hdist._cpu_ranges(set()) == ''
+    import os
+    before = os.sched_getaffinity(0)
+    msg = hdist.bind_to_gpu_numa(0)          # no GPU / no NVML here: must report, not raise
+    assert isinstance(msg, str) and msg
+    if msg.startswith('unbound'):
+        assert os.sched_getaffinity(0) == before
