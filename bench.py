@@ -187,7 +187,12 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     # one process per GPU, on the GPU's own NUMA node (pinned buffers are allocated below)
-    numa = 'off (HRF_NUMA_BIND=0)' if os.environ.get('HRF_NUMA_BIND') == '0' else hdist.bind_to_gpu_numa(local)
+    # (N = 1 stays unbound: nothing competes for the host links, and the CPU baseline below
+    # should see every host core)
+    if world == 1 or os.environ.get('HRF_NUMA_BIND') == '0':
+        numa = 'unbound (single rank)' if world == 1 else 'off (HRF_NUMA_BIND=0)'
+    else:
+        numa = hdist.bind_to_gpu_numa(local)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     cfg, net, (H, Wd), mod_ch = build_net(args.workload, args.precision, dev, seed=0)
     engine = net.engine()
