@@ -1,0 +1,150 @@
+"""HRFPN neck, drop-in for `mmdet/models/necks/hrfpn.py:13-100`.
+
+Same class / registry name (`HRFPN`), ctor arguments and state_dict layout
+(`reduction_conv.conv.{weight,bias}`, `fpn_convs.{i}.conv.{weight,bias}`: mmcv `ConvModule`
+without norm / activation), same `forward(inputs) -> tuple of num_outs maps`.
+
+The reference's front half (`hrfpn.py:77-86`) upsamples the three coarse maps to the finest
+grid, concatenates all four (270 channels at 96 x 160 for HRFuser-T: 133 MB per 8 frames in
+fp32, the largest tensor after the backbone) and runs the 1x1 `reduction_conv` on it.
+Bilinear interpolation is linear and acts per channel, so it commutes with a 1x1 convolution:
+
+    W . cat(x0, up(x1), up(x2), up(x3)) + b  ==  (W0 x0 + b) + up(W1 x1) + up(W2 x2) + up(W3 x3)
+
+with W_i the column slice of W for branch i.  Eval forward on the GPU therefore runs four 1x1
+convolutions at their *own* resolution (`hrf_pw_fwd`: 15x fewer FLOPs, 2.1 instead of 17 GFLOP
+per 8 frames) and one `hrf_fuse_sum_fwd` (the exchange kernel of the backbone: x + bilinear
+gathers, here without ReLU); the upsampled maps and the concatenation never exist.  The
+pooling pyramid and the 3x3 `fpn_convs` (dense 256 -> 256 convolutions: cuDNN territory, like
+the Bottlenecks of SURVEY 8 a11) stay torch ops on the result.
+
+No fallback: the eval forward raises without the built library / a CUDA tensor
+(`_lib.HrfError`); `train()` / grad-enabled calls take the reference's formulation in torch
+autograd, as the backbone does.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+class _ConvModule(nn.Module):
+    """mmcv `ConvModule(..., norm_cfg=None, act_cfg=None)`: a conv under the attribute `conv`."""
+
+    def __init__(self, cin, cout, k, padding=0, stride=1):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class HRFPN(nn.Module):
+    def __init__(self, in_channels, out_channels, num_outs=5, pooling_type='AVG', conv_cfg=None,
+                 norm_cfg=None, with_cp=False, stride=1,
+                 init_cfg=dict(type='Caffe2Xavier', layer='Conv2d'), precision='fp32'):
+        super().__init__()
+        assert isinstance(in_channels, list)                     # hrfpn.py:49
+        if conv_cfg is not None or norm_cfg is not None:
+            raise NotImplementedError('HRFPN: conv_cfg / norm_cfg other than None (no shipped '
+                                      'hrfuser config sets them)')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_ins = len(in_channels)
+        self.num_outs = num_outs
+        self.with_cp = with_cp
+        self.conv_cfg, self.norm_cfg, self.init_cfg = conv_cfg, norm_cfg, init_cfg
+        self.precision = precision
+        self.reduction_conv = _ConvModule(sum(in_channels), out_channels, 1)
+        self.fpn_convs = nn.ModuleList(
+            _ConvModule(out_channels, out_channels, 3, padding=1, stride=stride)
+            for _ in range(num_outs))
+        self.pooling = F.max_pool2d if pooling_type == 'MAX' else F.avg_pool2d
+        self._blobs = None
+
+    def init_weights(self):
+        """Caffe2Xavier on every Conv2d (mmcv: kaiming_uniform, a=1, fan_in, bias 0)."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, a=1, mode='fan_in', nonlinearity='leaky_relu')
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    # ------------------------------------------------------------ packed weights
+    def invalidate(self):
+        self._blobs = None
+
+    def load_state_dict(self, *a, **k):
+        self._blobs = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._blobs = None
+        return super()._apply(fn, *a, **k)
+
+    def _packed(self, device):
+        """per-branch column slices of the reduction conv as `hrf_pw` blobs (bias on branch 0)"""
+        if self._blobs is None or self._blobs[0].device != device:
+            conv = self.reduction_conv.conv
+            blobs, off = [], 0
+            for i, c in enumerate(self.in_channels):
+                part = nn.Conv2d(c, self.out_channels, 1, bias=(i == 0 and conv.bias is not None))
+                with torch.no_grad():
+                    part.weight.copy_(conv.weight[:, off:off + c])
+                    if part.bias is not None:
+                        part.bias.copy_(conv.bias)
+                blobs.append(ops.pack_pw(part, None).to(device))
+                off += c
+            self._blobs = blobs
+        return self._blobs
+
+    # ------------------------------------------------------------------ forward
+    def reduce(self, inputs):
+        """`reduction_conv(cat(x0, up(x1), ...))` of hrfpn.py:79-86 -> fp32 NCHW"""
+        x0 = inputs[0]
+        if not x0.is_cuda:
+            raise _lib.HrfError('HRFPN: the eval forward runs on the hrfuser_b200 CUDA kernels only '
+                                '(no CPU fallback); move the inputs to a CUDA device')
+        dt = torch.bfloat16 if self.precision == 'bf16' else torch.float32
+        blobs = self._packed(x0.device)
+        ys = []
+        for t, blob in zip(inputs, blobs):
+            tok = ops.nchw_to_nhwc(t.contiguous(), dtype=dt)
+            ys.append(ops.pointwise(tok, blob, self.out_channels))
+        for i, t in enumerate(inputs[1:], 1):          # F.interpolate(scale_factor=2**i)
+            if (t.shape[2] << i, t.shape[3] << i) != tuple(x0.shape[2:]):
+                raise ValueError(f'HRFPN: input {i} is {tuple(t.shape[2:])}, expected '
+                                 f'{(x0.shape[2] >> i, x0.shape[3] >> i)}')
+        out = ops.fuse_sum(ys[0], ups=ys[1:], relu=False) if len(ys) > 1 else ys[0]
+        return ops.nhwc_to_nchw(out, dtype=torch.float32)
+
+    def forward(self, inputs):
+        assert len(inputs) == self.num_ins                      # hrfpn.py:78
+        if self.training or torch.is_grad_enabled() and any(t.requires_grad for t in inputs):
+            return self._forward_autograd(inputs)
+        with torch.no_grad():
+            out = self.reduce(list(inputs))
+            outs = [out] + [self.pooling(out, kernel_size=2 ** i, stride=2 ** i)
+                            for i in range(1, self.num_outs)]
+            return tuple(self.fpn_convs[i](outs[i]) for i in range(self.num_outs))
+
+    def _forward_autograd(self, inputs):
+        """training path: the reference's formulation (hrfpn.py:77-100) on torch autograd"""
+        outs = [inputs[0]]
+        for i in range(1, self.num_ins):
+            outs.append(F.interpolate(inputs[i], scale_factor=2 ** i, mode='bilinear'))
+        out = self.reduction_conv(torch.cat(outs, dim=1))
+        outs = [out] + [self.pooling(out, kernel_size=2 ** i, stride=2 ** i)
+                        for i in range(1, self.num_outs)]
+        return tuple(self.fpn_convs[i](outs[i]) for i in range(self.num_outs))
+
+
+def register_with_mmdet():
+    """Register the class under its reference name when mmdet is importable."""
+    try:
+        from mmdet.models.builder import NECKS
+    except Exception:
+        return False
+    NECKS.register_module(name='HRFPN', force=True, module=HRFPN)
+    return True

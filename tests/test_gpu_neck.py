@@ -1,0 +1,81 @@
+"""GPU parity of the HRFPN neck (hrfuser_b200/neck.py: four hrf_pw_fwd + one hrf_fuse_sum_fwd for
+the upsample / concat / reduction front half) against the reference-made golden and, at the
+full HRFuser-T / HRFuser-B sizes, against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_parity
+from oracle import neck_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'neck.npz'))
+CASES = {'t': ([18, 36, 72, 144], 64), 'b_small': ([78, 156, 312, 624], 16)}
+
+
+def _net(chans, oc, precision, sd=None, seed=0):
+    from hrfuser_b200.neck import HRFPN
+    net = HRFPN(in_channels=chans, out_channels=oc, precision=precision).eval()
+    if sd is None:
+        torch.manual_seed(seed)
+        for p in net.parameters():
+            torch.nn.init.normal_(p, std=0.05)
+    else:
+        net.load_state_dict(sd)
+    return net
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_against_reference_golden(built_lib, name, mode):
+    chans, oc = CASES[name]
+    sd = {k[len(name) + 4:]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith(name + '.sd.')}
+    xs = [torch.from_numpy(GOLD[f'{name}.in{i}']).cuda() for i in range(4)]
+    net = _net(chans, oc, mode, sd).cuda()
+    before = built_lib.hrf_launch_count()
+    with torch.no_grad():
+        got = net(xs)
+    assert built_lib.hrf_launch_count() - before == 4 + 4 + 1 + 1      # layouts, pw, fuse_sum, layout
+    assert isinstance(got, tuple) and len(got) == 5
+    for i, g in enumerate(got):
+        assert g.dtype == torch.float32
+        assert_parity(g, torch.from_numpy(GOLD[f'{name}.out{i}']), mode, f'hrfpn {name} out{i}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('chans,grid,B', [
+    ([18, 36, 72, 144], (96, 160), 8),       # HRFuser-T nuScenes, 8 frames (cfg2)
+    ([18, 36, 72, 144], (96, 312), 2),       # HRFuser-T STF (cfg3)
+    ([78, 156, 312, 624], (96, 160), 2),     # HRFuser-B nuScenes (cfg4)
+])
+def test_reduction_full_size_against_oracle(built_lib, chans, grid, B, mode):
+    net = _net(chans, 256, mode, seed=1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    torch.manual_seed(2)
+    xs = [torch.randn(B, c, grid[0] >> i, grid[1] >> i) for i, c in enumerate(chans)]
+    want = neck_oracle.hrfpn_reduce(sd, xs)
+    with torch.no_grad():
+        got = net.reduce([x.cuda() for x in xs])
+    assert_parity(got, want, mode, f'hrfpn reduce {chans[0]} {grid}')
+
+
+def test_whole_neck_full_size_and_zero_input(built_lib):
+    chans = [18, 36, 72, 144]
+    net = _net(chans, 256, 'fp32', seed=3)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    torch.manual_seed(4)
+    xs = [torch.randn(1, c, 96 >> i, 160 >> i) for i, c in enumerate(chans)]
+    xs[2].zero_()
+    want = neck_oracle.hrfpn_forward(sd, xs)
+    with torch.no_grad():
+        got = net([x.cuda() for x in xs])
+    for i, (g, w) in enumerate(zip(got, want)):
+        # the 3x3 convs run in torch on both sides; cuDNN vs CPU conv differ by fp32 reassociation
+        e = float((g.cpu() - w).norm() / w.norm())
+        assert e < 2e-5, (i, e)
+    with pytest.raises(ValueError):
+        net([xs[0].cuda(), xs[1].cuda(), xs[2].cuda(), xs[2].cuda()])
