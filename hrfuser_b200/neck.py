@@ -123,7 +123,9 @@ class HRFPN(nn.Module):
         assert len(inputs) == self.num_ins                      # hrfpn.py:78
         if self.training or torch.is_grad_enabled() and any(t.requires_grad for t in inputs):
             return self._forward_autograd(inputs)
-        with torch.no_grad():
+        # fp32 mode: the cuDNN 3x3 convs must not drop to TF32 (3e-4 off; the engine does the same)
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True,
+                                                         allow_tf32=self.precision != 'fp32'):
             out = self.reduce(list(inputs))
             outs = [out] + [self.pooling(out, kernel_size=2 ** i, stride=2 ** i)
                             for i in range(1, self.num_outs)]
