@@ -62,7 +62,6 @@ class HRFPN(nn.Module):
             for _ in range(num_outs))
         self.pooling = F.max_pool2d if pooling_type == 'MAX' else F.avg_pool2d
         self._blobs = None
-        self._streams = None
 
     def init_weights(self):
         """Caffe2Xavier on every Conv2d (mmcv: kaiming_uniform, a=1, fan_in, bias 0)."""
@@ -113,25 +112,11 @@ class HRFPN(nn.Module):
                                  f'{(x0.shape[2] >> i, x0.shape[3] >> i)}')
         dt = torch.bfloat16 if self.precision == 'bf16' else torch.float32
         blobs = self._packed(x0.device)
-        # the four branches are independent and the three coarse ones are latency-bound
-        # (30-36 us for 1-30 % of the tokens): fork them onto side streams, join before the sum
-        cur = torch.cuda.current_stream(x0.device)
-        if self._streams is None or self._streams[0].device != x0.device:
-            self._streams = [torch.cuda.Stream(device=x0.device) for _ in range(self.num_ins - 1)]
-
-        def branch(t, blob):
-            return ops.pointwise(ops.nchw_to_nhwc(t.contiguous(), dtype=dt), blob, self.out_channels)
-
-        ys = [None] * self.num_ins
-        for i in range(1, self.num_ins):
-            st = self._streams[i - 1]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                ys[i] = branch(inputs[i], blobs[i])
-            ys[i].record_stream(cur)
-        ys[0] = branch(inputs[0], blobs[0])
-        for st in self._streams:
-            cur.wait_stream(st)
+        # one stream: forking the three coarse (latency-bound) branches onto side streams was
+        # measured and dropped (profiles/r01_neck_bench_streams.jsonl: HRFuser-B 0.85 -> 0.71 ms,
+        # HRFuser-T 0.41 -> 0.39 ms in bf16 but 0.69 -> 0.87 ms in fp32)
+        ys = [ops.pointwise(ops.nchw_to_nhwc(t.contiguous(), dtype=dt), blob, self.out_channels)
+              for t, blob in zip(inputs, blobs)]
         out = ops.fuse_sum(ys[0], ups=ys[1:], relu=False) if len(ys) > 1 else ys[0]
         return ops.nhwc_to_nchw(out, dtype=torch.float32)
 
