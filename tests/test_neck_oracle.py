@@ -78,3 +78,24 @@ def test_ctor_contract():
         HRFPN(in_channels=18, out_channels=8)                        # hrfpn.py:49
     with pytest.raises(AssertionError):
         HRFPN(in_channels=[18, 36], out_channels=8).train()([torch.zeros(1, 18, 4, 4)])   # hrfpn.py:78
+
+
+def test_backbone_feeds_neck_training_path():
+    """extract_feat of the reference (two_stage.py:76-84): neck(backbone(img, mods)) on the
+    torch-autograd path, gradients reaching the backbone through the neck"""
+    import copy
+    from hrfuser_b200 import HRFuserHRFormerBased, tiny_cfg
+    c = copy.deepcopy(tiny_cfg(2))
+    c.pop('type')
+    c['norm_cfg'] = dict(type='BN', requires_grad=True)
+    torch.manual_seed(0)
+    backbone = HRFuserHRFormerBased(**c).train()
+    neck = HRFPN(in_channels=[18, 36, 72, 144], out_channels=16).train()
+    neck.init_weights()
+    img, mods = torch.randn(1, 3, 64, 64), [torch.randn(1, 3, 64, 64) for _ in range(2)]
+    feats = backbone(img, mods)
+    assert [f.shape[1] for f in feats] == [18, 36, 72, 144]
+    outs = neck(feats)
+    assert [tuple(o.shape) for o in outs] == [(1, 16, 16 >> i, 16 >> i) for i in range(5)]
+    sum(o.sum() for o in outs).backward()
+    assert backbone.conv1.weight.grad is not None and neck.fpn_convs[4].conv.weight.grad is not None
