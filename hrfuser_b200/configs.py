@@ -71,6 +71,9 @@ def backbone_cfg(variant='t', dataset='nus', norm='BN'):
 WORKLOADS = {
     'hrfuser_t_nus_r640': ('t', 'nus', 384, 640),
     'hrfuser_t_stf_r1248': ('t', 'stf', 384, 1248),
+    # BASELINE.json's literal "1248x666" (un-cropped STF frame padded to /32); the shipped
+    # pipeline crops to 384x1248 (kitti_detection_2d_c1248_clrg_fusion.py:24,55)
+    'hrfuser_t_stf_r1248_full': ('t', 'stf', 672, 1248),
     'hrfuser_b_nus_r640': ('b', 'nus', 384, 640),
 }
 

@@ -49,3 +49,15 @@ def test_paddings_of_the_shipped_grids():
     for (H, W), (Hp, Wp) in want.items():
         g = wm.window_geometry(H, W)
         assert (g.Hp, g.Wp) == (Hp, Wp)
+
+
+@pytest.mark.parametrize('H,W', [(168, 312), (84, 156), (42, 78), (21, 39)])
+def test_full_stf_frame_grids_product_equals_oracle(H, W):
+    """workload 'hrfuser_t_stf_r1248_full' (BASELINE.json's literal 1248x666 -> 672x1248): no
+    reference golden for these grids, so the product closed form is held to the oracle's
+    gather map (itself pinned on the eight shipped grids above) and to the bijection."""
+    inv = wm.window_to_token(H, W)
+    assert np.array_equal(inv, O.window_gather_map(H, W))
+    win, slot = wm.token_to_window(H, W)
+    assert np.array_equal(inv[win.reshape(-1), slot.reshape(-1)], np.arange(H * W))
+    assert (inv >= 0).sum() == H * W
