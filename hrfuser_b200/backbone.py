@@ -16,6 +16,8 @@ if that library is not built; there is no CPU or eager fallback for inference.
 In `train()` the autograd-capable torch forwards of `modules.py` run (batch
 statistics / SyncBN / DropPath), as DESIGN.md section "training" explains.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -57,6 +59,7 @@ class HRFuserHRFormerBased(nn.Module):
         self.with_pad_mask = extra.get('with_pad_mask', False)
         self.precision = precision
         self._engine = None
+        self._graphs = {}
 
         # The reference computes stochastic-depth rates from a drop_path_rate
         # that the HRFuser subclass never forwards (hrfuser_hrformer_based.py:
@@ -199,16 +202,20 @@ class HRFuserHRFormerBased(nn.Module):
         return self
 
     def invalidate_engine(self):
-        """Drop the packed device weights (call after mutating parameters in place)."""
+        """Drop the packed device weights and the captured CUDA graphs (call after mutating
+        parameters in place)."""
         self._engine = None
+        self._graphs = {}
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self.invalidate_engine()
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
+    def _load_from_state_dict(self, *a, **k):
+        # reached for every module of the tree when a PARENT (the detector, mmcv's
+        # load_checkpoint) loads a checkpoint; Module.load_state_dict of a child is not
+        self.invalidate_engine()
+        return super()._load_from_state_dict(*a, **k)
 
     def engine(self):
         if self._engine is None:
@@ -224,10 +231,51 @@ class HRFuserHRFormerBased(nn.Module):
             x_mod = []
         if self.num_fused_modalities != len(x_mod):
             raise Exception('num_fused_modalities does not fit the given input length')
-        if self.training or torch.is_grad_enabled() and any(
-                p.requires_grad for p in (x, *x_mod)):
+        if self.training or torch.is_grad_enabled() and (
+                any(t.requires_grad for t in (x, *x_mod)) or
+                any(p.requires_grad for p in self.parameters())):
+            # (eval() with trainable parameters and grad enabled -- fine-tuning with frozen BN
+            # statistics -- builds an autograd graph, as the reference does; inference runs
+            # under torch.no_grad(), as mmdet's test loop does)
             return self._forward_autograd(x, list(x_mod))
-        return self.engine().forward(x, list(x_mod))
+        return self._forward_engine(x, list(x_mod))
+
+    # CUDA-graph cache of the inference forward: the second call with a given input signature
+    # captures the whole engine forward into one graph over static input buffers; later calls
+    # copy the inputs in (host tensors go straight from pinned memory), replay, and return
+    # clones of the four maps (`graph_outputs='view'` returns the static buffers themselves:
+    # valid until the next forward).  HRF_GRAPH=0 or `use_cuda_graph = False` keeps the
+    # eager launch sequence.
+    use_cuda_graph = os.environ.get('HRF_GRAPH', '1') != '0'
+    graph_outputs = 'clone'
+    max_graphs = 4
+
+    def _forward_engine(self, x, mods):
+        eng = self.engine()
+        if not (self.use_cuda_graph and eng.device.type == 'cuda') or torch.cuda.is_current_stream_capturing():
+            return eng.forward(x, mods)
+        key = (tuple(x.shape), tuple(tuple(m.shape) for m in mods))
+        ent = self._graphs.get(key)
+        if ent is None:                              # first sight: run eagerly, remember
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = 0
+            return eng.forward(x, mods)
+        if ent == 0:
+            from .engine import GraphedForward
+            with torch.cuda.device(eng.device):
+                sx = torch.empty(x.shape, dtype=torch.float32, device=eng.device)
+                sm = [torch.empty(m.shape, dtype=torch.float32, device=eng.device) for m in mods]
+                sx.copy_(x, non_blocking=True)
+                for d, m in zip(sm, mods):
+                    d.copy_(m, non_blocking=True)
+                ent = self._graphs[key] = GraphedForward(eng, sx, sm)
+        else:
+            ent.x.copy_(x, non_blocking=True)
+            for d, m in zip(ent.mods, mods):
+                d.copy_(m, non_blocking=True)
+        outs = ent()
+        return list(outs) if self.graph_outputs == 'view' else [o.clone() for o in outs]
 
     def _forward_autograd(self, x, mods):
         """Training path (torch ops, autograd).  Same wiring as the engine; see

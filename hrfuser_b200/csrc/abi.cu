@@ -15,7 +15,7 @@
 #include "umma_selftest.cuh"
 #include "window_attn_tc.cuh"
 #include "mixffn_tc.cuh"
-#include "mixffn_tcd.cuh"
+#include "mixffn_v2.cuh"
 #include "conv3x3_tc.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
@@ -40,9 +40,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 cudaError_t ensure_smem(const void* kern, size_t bytes) {
   static std::mutex mu;
-  static std::map<const void*, size_t> done;
+  // cudaFuncSetAttribute applies to the CURRENT device: key the cache on (device, kernel)
+  static std::map<std::pair<int, const void*>, size_t> done;
   std::lock_guard<std::mutex> lk(mu);
-  auto it = done.find(kern);
+  int dev = 0;
+  if (cudaError_t de = cudaGetDevice(&dev); de != cudaSuccess) return de;
+  const std::pair<int, const void*> key(dev, kern);
+  auto it = done.find(key);
   if (it != done.end() && it->second >= bytes) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   // ask for the largest shared-memory carve-out: the driver's default split sizes it for ONE
@@ -51,7 +55,7 @@ cudaError_t ensure_smem(const void* kern, size_t bytes) {
   static const bool carve = [] { const char* v = std::getenv("HRF_CARVEOUT"); return !(v && v[0] == '0'); }();
   if (e == cudaSuccess && carve)
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess) done[kern] = bytes;
+  if (e == cudaSuccess) done[key] = bytes;
   // HRF_DEBUG_OCC=<threads>: print the resident CTAs per SM the runtime predicts for this kernel
   static const int occ_threads = [] { const char* v = std::getenv("HRF_DEBUG_OCC"); return v ? std::atoi(v) : 0; }();
   if (e == cudaSuccess && occ_threads > 0) {
@@ -95,6 +99,24 @@ static inline uint16_t f32_to_bf16(float f) {
   std::memcpy(&u, &f, 4);
   u += 0x7FFFu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+}
+
+// round-to-nearest-even fp32 -> fp16 bits, saturating to the largest finite value
+static inline uint16_t f32_to_f16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  u &= 0x7FFFFFFFu;
+  if (u >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);           // >= 65520 (or inf / nan) -> 65504
+  if (u < 0x38800000u) {                                             // subnormal half or zero
+    if (u < 0x33000000u) return (uint16_t)sign;
+    const int shift = 126 - (int)(u >> 23);                          // 14 .. 24
+    const uint32_t mant = (u & 0x7FFFFFu) | 0x800000u;
+    const uint32_t half = mant >> shift, rem = mant & ((1u << shift) - 1u), mid = 1u << (shift - 1);
+    return (uint16_t)(sign | (half + ((rem > mid || (rem == mid && (half & 1u))) ? 1u : 0u)));
+  }
+  const uint32_t r = u + 0xFFFu + ((u >> 13) & 1u);                  // round to nearest even at bit 13
+  return (uint16_t)(sign | ((r - 0x38000000u) >> 13));
 }
 
 // eval-mode BatchNorm as y = x*scale + shift
@@ -385,19 +407,32 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b, cons
       // tile; the kernels keep a constant 1 in that column of the hidden activations
       tile2[umma::tile_off(c, L.tc_CH, NOUT) / 2] = f32_to_bf16(b2p[c]);
     }
-    // depthwise-conv tiles (see FfnLayout::o_tc_dg)
-    uint16_t* dg = reinterpret_cast<uint16_t*>(blob + L.o_tc_dg);
-    for (int ch = 0; ch < (L.tc_CH == 72 ? L.tc_nchunk : 0); ++ch) {   // experimental kernel: 72 only
-      const float* fb = f + (size_t)ch * 880;
-      for (int s = 0; s < 5; ++s)
-        for (int n = 0; n < 16; ++n) {
-          const int jj = 16 * s + n;
-          if (jj >= 72) continue;
-          uint16_t* base = dg + ((size_t)ch * 50 + s * 10) * 256;
-          for (int t = 0; t < 9; ++t)
-            base[t * 256 + umma::tile_off(n, n, 16) / 2] = f32_to_bf16(fb[80 + t * 80 + jj]);
-          base[9 * 256 + umma::tile_off(n, 8, 16) / 2] = f32_to_bf16(fb[800 + jj]);
+    // second-generation kernel (mixffn_v2.cuh): LN affine folded into W1 / b1, every section
+    // pre-multiplied by 0.5, hidden path in fp16
+    if (L.tc_CH == 72) {
+      uint16_t* v1 = reinterpret_cast<uint16_t*>(blob + L.o_v2_w1);
+      uint16_t* v2 = reinterpret_cast<uint16_t*>(blob + L.o_v2_w2);
+      uint16_t* cv = reinterpret_cast<uint16_t*>(blob + L.o_v2_cv);
+      for (int ch = 0; ch < L.tc_nchunk; ++ch) {
+        uint16_t* w1t = v1 + (size_t)ch * 80 * KC;
+        uint16_t* w2t = v2 + (size_t)ch * NOUT * 80;
+        uint16_t* cvt = cv + (size_t)ch * 800;                // wd[9][80] | bd[80]
+        for (int jj = 0; jj < 72; ++jj) {
+          const int j = ch * 72 + jj;
+          double bfold = (double)((b1 ? b1[j] : 0.f) * s1[j] + t1[j]);
+          for (int k = 0; k < C; ++k) {
+            const float w = w1[(size_t)j * C + k] * s1[j];
+            w1t[umma::tile_off(jj, k, 80) / 2] = f32_to_bf16(0.5f * w * ln_w[k]);
+            bfold += (double)w * (double)ln_b[k];
+          }
+          w1t[umma::tile_off(jj, C, 80) / 2] = f32_to_bf16(0.5f * (float)bfold);
+          for (int t = 0; t < 9; ++t) cvt[t * 80 + jj] = f32_to_f16(0.5f * wd[(size_t)j * 9 + t] * s2[j]);
+          cvt[720 + jj] = f32_to_f16(0.5f * ((bd ? bd[j] : 0.f) * s2[j] + t2[j]));
+          for (int n = 0; n < C; ++n)
+            w2t[umma::tile_off(n, jj, NOUT) / 2] = f32_to_f16(0.5f * w2[(size_t)n * Hd + j] * s3[n]);
         }
+      }
+      for (int c = 0; c < C; ++c) v2[umma::tile_off(c, 72, NOUT) / 2] = f32_to_f16(0.5f * b2p[c]);
     }
   }
   return HRF_OK;
@@ -425,7 +460,7 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
   FfnParams p{x, blob, out, workspace, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
   cudaStream_t st = (cudaStream_t)stream;
   switch (ffn_path(d)) {
-    case PATH_TC: return ffn_tcd_supported(p) ? launch_mixffn_tcd(p, st) : launch_mixffn_tc(p, st);
+    case PATH_TC: return ffn_v2_supported(p) ? launch_mixffn_v2(p, st) : launch_mixffn_tc(p, st);
     case PATH_FUSED_SIMT:
       return d->dtype == HRF_F32 ? launch_mixffn<float>(p, st) : launch_mixffn<__nv_bfloat16>(p, st);
   }

@@ -43,15 +43,19 @@ struct FfnLayout {
     o = round_up(o, 4);
     o_tc_w1 = o; o += tc_nchunk * 80 * tc_KC / 2;
     o_tc_w2 = o; o += tc_nchunk * tc_NOUT * 80 / 2;
-    // depthwise 3x3 as tensor-core work: per chunk, per 16-channel column group s (5), ten
-    // [16 x 16] bf16 B tiles: taps 0..8 = diag(wd[tap][16s..16s+15]), tile 9 = the bias tile
-    // (row k = 8 holds bd[16s..], it multiplies the constant-1 column 72 of the activations)
-    o_tc_dg = o; o += tc_nchunk * 50 * 256 / 2;
+    // second-generation kernel (mixffn_v2.cuh), per 72-channel chunk: bf16 W1 tile [KC/8][80][8]
+    // with the LayerNorm affine folded in (row C = folded bias), fp16 W2 tile [10][NOUT][8]
+    // (row 72 of chunk 0 = b2), fp16 depthwise table wd[9][80] | bd[80]; every section is
+    // pre-multiplied by 0.5 (the GELU behind it takes x / 2)
+    const int v2 = (tc_CH == 72) ? tc_nchunk : 0;
+    o_v2_w1 = o; o += v2 * 80 * tc_KC / 2;
+    o_v2_w2 = o; o += v2 * tc_NOUT * 80 / 2;
+    o_v2_cv = o; o += v2 * 400;
     total = o;
     ldx = stride4odd(Cp);
     ldh = stride4odd(HC);
   }
-  int tc_KC, tc_NOUT, tc_CH, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2, o_tc_dg;
+  int tc_KC, tc_NOUT, tc_CH, tc_nchunk, o_tc_f32, o_tc_w1, o_tc_w2, o_v2_w1, o_v2_w2, o_v2_cv;
 };
 
 constexpr int kFfnThreads = 256;

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace hrf {
 namespace umma {
@@ -57,11 +58,20 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a lost commit must become an error (trap), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// -DHRF_DEBUG_WAIT (debug library only): a short limit, and the timed-out wait names itself.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = -1) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
+#ifdef HRF_DEBUG_WAIT
+    if (clock64() - t0 > 200000000LL) {
+      printf("[hrf] mbarrier wait timed out: tag %d parity %u block %d thread %d\n", tag, parity,
+             (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+#else
     if (clock64() - t0 > 4000000000LL) __trap();
+#endif
   }
 }
 // Whole-CTA wait for an MMA commit: only warp 0 watches the mbarrier (suspended in
@@ -88,6 +98,34 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+
+// ---- TMA tensor-tile copies (cp.async.bulk.tensor, 3-D tiled maps built by abi.cu) ---------
+// The token tensors [B][H][W][C] are described to the TMA unit as 3-D tensors
+// (W*C/2 32-bit words, H, B): a box of `boxw` tokens x `boxh` rows lands in shared memory as
+// dense rows, and everything outside the image (negative or too large coordinates) arrives
+// as zeros -- the halo / window padding needs no address arithmetic and no predicates.
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2,
+                                             const void* src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed store has been read (the buffer may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed store is complete (globally visible at kernel end anyway; used before exit)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- single-thread issue -----------------------------------------------------------
 // tcgen05.mma / commit are issued by one thread.  Guarding them with `threadIdx.x == 0` makes
@@ -147,6 +185,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) |
          ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// the same with fp16 inputs (the MixFFN hidden path: H2 x W2)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread

@@ -161,6 +161,8 @@ class BackboneEngine:
         self.pre_neck_fusion = m.pre_neck_fusion
         # independent branches / streams run on forked CUDA streams (see _par)
         self.concurrent = device_ops is None and os.environ.get('HRF_SERIAL', '0') != '1'
+        # frames per sub-batch of the stem phase (0 = the whole batch at once)
+        self.stem_chunk = int(os.environ.get('HRF_STEM_CHUNK', '0'))
         self._free_streams, self._keep = [], []
         self._upload()
 
@@ -361,12 +363,16 @@ class BackboneEngine:
             x_img = c(x_img)
         return x_img
 
-    def _fuse(self, letter, cam_thunks, stream):
+    def _fuse(self, letter, cam_thunks, stream, pre_ms=None):
         """cam_thunks[i]() -> camera tokens of branch i.  Returns the fused branches
-        and the modality tensors of branch 0 (inputs of the next modality stage)."""
+        and the modality tensors of branch 0 (inputs of the next modality stage).
+        `pre_ms[k][i]`: modality tokens already taken through their transition (stage a)."""
         def branch(i):
             ms = []
             for k in range(self.M):
+                if pre_ms is not None:
+                    ms.append(pre_ms[k][i])
+                    continue
                 tr = self.trans_mod[letter][k][i]
                 ms.append(stream[k] if tr is None else
                           self._tokens(self._apply_chain(tr, self._image(stream[k]))))
@@ -389,12 +395,38 @@ class BackboneEngine:
         self._keep = []
         M = self.M
         with ctx, dctx:
-            stems = self._par(
-                [lambda: self._apply_chain(self.stem, x)] +
-                [lambda k=k: self._tokens(self._apply_chain(self.stem_mod[k], mods[k]))
-                 for k in range(M)])
-            x, stream = stems[0], stems[1:]
-            xs, firsts = self._fuse('a', [lambda t=t: self._tokens(t(x)) for t in self.trans1], stream)
+            # Stems + first transitions, per stream, in sub-batches of `stem_chunk` frames: the
+            # 64 / 256-channel maps of a sub-batch (15.7 MB per 2 frames at 96 x 160) then stay
+            # in the 126 MB L2 from the convolution that writes them to the one that reads
+            # them; only the narrow 18 / 36-channel transition outputs are concatenated.
+            B = x.shape[0]
+            ck = self.stem_chunk if 0 < self.stem_chunk < B else B
+            nb_a = len(self.trans1)
+
+            def cam_stream():
+                parts = []
+                for b0 in range(0, B, ck):
+                    y = self._apply_chain(self.stem, x[b0:b0 + ck])
+                    parts.append([self._tokens(t(y)) for t in self.trans1])
+                return parts[0] if len(parts) == 1 else \
+                    [torch.cat([q[i] for q in parts]) for i in range(nb_a)]
+
+            def mod_stream(k):
+                parts = []
+                for b0 in range(0, B, ck):
+                    y = self._apply_chain(self.stem_mod[k], mods[k][b0:b0 + ck])
+                    outs = []
+                    for i in range(nb_a):
+                        tr = self.trans_mod['a'][k][i]
+                        outs.append(self._tokens(y) if tr is None else
+                                    self._tokens(self._apply_chain(tr, y)))
+                    parts.append(outs)
+                return parts[0] if len(parts) == 1 else \
+                    [torch.cat([q[i] for q in parts]) for i in range(nb_a)]
+
+            stems = self._par([cam_stream] + [lambda k=k: mod_stream(k) for k in range(M)])
+            cams, pre_ms = stems[0], stems[1:]
+            xs, firsts = self._fuse('a', [lambda i=i: cams[i] for i in range(nb_a)], None, pre_ms)
             res = self._par([lambda: self._run_stage(self.stage[2], xs)] +
                             [lambda k=k: self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0]
                              for k in range(M)])

@@ -61,7 +61,7 @@ class HRFPN(nn.Module):
             _ConvModule(out_channels, out_channels, 3, padding=1, stride=stride)
             for _ in range(num_outs))
         self.pooling = F.max_pool2d if pooling_type == 'MAX' else F.avg_pool2d
-        self._blobs = None
+        self._blobs, self._blobs_ver = None, None
 
     def init_weights(self):
         """Caffe2Xavier on every Conv2d (mmcv: kaiming_uniform, a=1, fan_in, bias 0)."""
@@ -75,9 +75,22 @@ class HRFPN(nn.Module):
     def invalidate(self):
         self._blobs = None
 
-    def load_state_dict(self, *a, **k):
+    def train(self, mode=True):
+        # an optimizer updates reduction_conv in place between two evaluations: never carry
+        # packed weights across a train() phase (the backbone does the same with its engine)
         self._blobs = None
-        return super().load_state_dict(*a, **k)
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        # reached for every module of the tree when a PARENT (the detector, mmcv's
+        # load_checkpoint) loads a checkpoint; Module.load_state_dict of a child is not
+        self._blobs = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _weights_version(self):
+        conv = self.reduction_conv.conv
+        return (conv.weight._version, conv.weight.data_ptr(),
+                None if conv.bias is None else (conv.bias._version, conv.bias.data_ptr()))
 
     def _apply(self, fn, *a, **k):
         self._blobs = None
@@ -85,7 +98,9 @@ class HRFPN(nn.Module):
 
     def _packed(self, device):
         """per-branch column slices of the reduction conv as `hrf_pw` blobs (bias on branch 0)"""
-        if self._blobs is None or self._blobs[0].device != device:
+        # keyed on the parameters' version counters as well: any in-place update repacks
+        ver = self._weights_version()
+        if self._blobs is None or self._blobs[0].device != device or self._blobs_ver != ver:
             conv = self.reduction_conv.conv
             blobs, off = [], 0
             for i, c in enumerate(self.in_channels):
@@ -96,7 +111,7 @@ class HRFPN(nn.Module):
                         part.bias.copy_(conv.bias)
                 blobs.append(ops.pack_pw(part, None).to(device))
                 off += c
-            self._blobs = blobs
+            self._blobs, self._blobs_ver = blobs, ver
         return self._blobs
 
     # ------------------------------------------------------------------ forward
@@ -122,7 +137,10 @@ class HRFPN(nn.Module):
 
     def forward(self, inputs):
         assert len(inputs) == self.num_ins                      # hrfpn.py:78
-        if self.training or torch.is_grad_enabled() and any(t.requires_grad for t in inputs):
+        if self.training or torch.is_grad_enabled() and (
+                any(t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())):
+            # (eval() with trainable parameters and grad enabled -- fine-tuning with frozen BN
+            # statistics -- must build a graph, as the reference does)
             return self._forward_autograd(inputs)
         # fp32 mode: the cuDNN 3x3 convs must not drop to TF32 (3e-4 off; the engine does the same)
         with torch.no_grad(), torch.backends.cudnn.flags(enabled=True,

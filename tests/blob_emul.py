@@ -127,7 +127,10 @@ class FfnLayout:
         o = _ru(o + nch * 880 + (KC if nch else 0), 4)
         self.tc_w1 = o; o += nch * 80 * KC // 2
         self.tc_w2 = o; o += nch * KC * 80 // 2
-        self.tc_dg = o; o += nch * 50 * 256 // 2
+        v2 = nch if hidden % 72 == 0 else 0          # second-generation kernel sections
+        self.v2_w1 = o; o += v2 * 80 * KC // 2
+        self.v2_w2 = o; o += v2 * KC * 80 // 2
+        self.v2_cv = o; o += v2 * 400
         self.tc = dict(KC=KC, NOUT=KC, nchunk=nch)
         self.total = o
 

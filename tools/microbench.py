@@ -56,6 +56,9 @@ def main():
     ap.add_argument('--grids', default='nus,stf')
     ap.add_argument('--wins', default='7', help='window sizes, e.g. 7,14')
     ap.add_argument('--out', default='')
+    ap.add_argument('--kinds', default='lsa,mwca,mixffn', help='subset of lsa,mwca,mixffn')
+    ap.add_argument('--widths', default='18,36,72,144', help='channel widths to run')
+    ap.add_argument('--mods', default='1,2,3', help='MWCA modality counts')
     a = ap.parse_args()
     dt = torch.bfloat16 if a.precision == 'bf16' else torch.float32
     pk = peaks()
@@ -65,12 +68,15 @@ def main():
     for gname, win in [(g, int(w)) for w in a.wins.split(',') for g in a.grids.split(',')]:
         S4 = 4 * win * win                                   # QK^T + PV flops per token and channel
         for (H, W), (C, heads) in zip(GRIDS[gname], WIDTHS):
+            if str(C) not in a.widths.split(','):
+                continue
             n_tok = B * H * W
             nbytes = n_tok * C * dt.itemsize
             n_sets = max(2, int(2 * 126e6 // max(nbytes, 1)) + 1)
             n_sets = min(n_sets, 64)
             xs = [torch.randn(B, H, W, C, device='cuda').to(dt) for _ in range(n_sets)]
             cases = [('lsa', 0), ('mwca', 1), ('mwca', 2), ('mwca', 3)] + ([('mixffn', 0)] if win == 7 else [])
+            cases = [c for c in cases if c[0] in a.kinds.split(',') and (c[0] != 'mwca' or str(c[1]) in a.mods.split(','))]
             for kind, M in cases:
                 e = stub()
                 if kind == 'mixffn':

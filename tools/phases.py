@@ -25,8 +25,8 @@ from microbench import GRIDS, WIDTHS, stub  # noqa: E402
 NAMES = {
     'ffn': ['LN prologue', 'sync', 'fc1 issue', 'fc1 wait', 'epilogue 1', 'sync', 'dw conv', 'sync',
             'fc2 issue', 'fc2 wait', 'epilogue 2', '-', '-', '-'],
-    'ffn_tcd': ['LN prologue', 'sync', 'fc1 issue', 'fc1 wait', 'epilogue 1', 'sync', 'conv issue',
-                'conv wait', 'epilogue dw', 'sync', 'fc2 issue', 'fc2 wait', 'epilogue 2', '-'],
+    'ffn_v2': ['TMA wait + LN', 'sync', 'fc1 issue', 'fc1 wait', 'epilogue 1', 'sync', 'dw conv', 'sync',
+               'fc2 issue', 'fc2 wait', 'epilogue 2', 'sync + store', '-', '-'],
     'attn': ['LN prologue', 'sync', 'qkv issue', 'qkv wait', 'qkv/PV epilogue', 'sync+S issue', 'S wait',
              'softmax', 'sync+PV issue', 'PV wait', 'PV epi (last)', 'sync+out issue', 'out wait',
              'out epilogue'],
@@ -58,7 +58,7 @@ elif a.kind == 'ffn':
     f = e._ffn(blk.norm2, blk.ffn)
     e._upload()
     fn = lambda: ops.mixffn(x, f['blob'].t, f['hidden'], f['eps'])
-    names = NAMES['ffn_tcd' if os.environ.get('HRF_FFN_DW_TC') == '1' and Cc == 18 else 'ffn']
+    names = NAMES['ffn_v2' if os.environ.get('HRF_FFN_V2', '1') != '0' and Cc == 18 else 'ffn']
 elif a.kind == 'lsa':
     blk, _ = make_block('lsa', Cc, heads)
     pk = e._hrformer_block(blk)
