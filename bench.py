@@ -9,16 +9,26 @@ One "step" = one backbone forward over one batch of synthetic frames
 mode).  Prints ONE JSON line (rank 0).
 
   value      frames/s, whole job, inputs resident in HBM, one CUDA graph replay per step
-  e2e        frames/s through the public API with HOST (pinned) inputs: H2D of the
-             three fp32 input tensors and D2H of the four fp32 feature maps inside
-             the timed region (three pipelined slots)
+  e2e        frames/s through the public API, `HRFuserHRFormerBased.forward(x_host, mods_host)`,
+             with HOST (pinned) fp32 inputs: H2D of the input tensors and D2H of the four fp32
+             feature maps inside the timed region (the caller pipelines three streams; the
+             forward keeps one captured CUDA graph per input signature and stream)
+  e2e_raw    the same through `pipeline.RawBackbone`: the host ships RAW frames (uint8 camera,
+             fp32 lidar / radar at the un-padded size) and Normalize / Pad / format run on the
+             device inside the same graph (49.8 MB instead of 70.8 MB per step)
+  gpu_eager_baseline   the reference module (or, when no reference is reachable, its torch
+             mirror hrfuser_b200/modules.py) in PyTorch eager on the same GPU, fp32 and bf16
+             autocast, same batch -- SURVEY.md 8(d)'s "real bar"
   roofline   dominant hrfuser_b200 kernel group: algorithmic bytes per launch
               / mean launch duration measured with CUDA events
              around every C-ABI call of one un-graphed step, vs MEASURED_PEAKS.json
-  cpu_baseline   the oracle port (oracle/hrfuser_oracle.py, fp32 torch CPU) on the
-             box's host cores, bounded sample -- reported, not the target
-`--impl reference` times that CPU port alone (the reference itself is Python +
-mmcv and cannot travel to the GPU box).
+  cpu_baseline   the UNMODIFIED reference module on the box's host cores when a reference tree
+             is reachable ($HRFUSER_REF, /root/reference, baseline/_ref: kind "reference"), else
+             the oracle port (oracle/hrfuser_oracle.py, kind "port"); bounded sample --
+             reported, not the target
+`--impl reference` times that CPU arm alone, one frame per step.
+`--workload hrfuser_t_stf_r1248` (configs[2]) and `--workload hrfuser_b_nus_r640 --train`
+(configs[3]: SyncBN training step, forward + backward + SGD) select the other configs.
 """
 import argparse
 import copy
@@ -37,6 +47,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'hrfuser_t_backbone_frames_per_s'
 L2_BYTES = 126e6
+# raw (un-padded) sensor frame size per workload (H, W): the reference pads to /32 on the way in
+RAW_SIZES = {'hrfuser_t_nus_r640': (360, 640), 'hrfuser_b_nus_r640': (360, 640)}
 
 
 def peaks():
@@ -123,59 +135,117 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_port_fps(workload, budget_s=12.0, max_iters=8):
-    """frames/s of the CPU port (oracle) on a bounded sample: batch-1 forwards."""
-    from hrfuser_b200.utils import synthetic_inputs
-    use_all_host_threads()
-    from oracle import hrfuser_oracle as O
+def cpu_arm(workload):
+    """(forward(x, mods) -> maps, kind, what): the reference's own CPU implementation of the path
+    when a reference tree is reachable, else the oracle port."""
     cfg, net, (H, W), mod_ch = build_net(workload, 'fp32')
     sd = net.state_dict()
+    try:
+        from oracle import ref_loader
+        root = ref_loader.find_reference()
+        if root is not None:
+            ref = ref_loader.build_reference_backbone(cfg, root)
+            ref.load_state_dict(sd)
+            return (lambda x, mods: ref(x, list(mods))), 'reference', \
+                f'unmodified reference HRFuserHRFormerBased from {root}', (H, W), mod_ch
+    except Exception as e:                       # noqa: BLE001 -- any import problem: use the port
+        sys.stderr.write(f'bench.py: reference not loadable ({type(e).__name__}: {e}); using the port\n')
+    from oracle import hrfuser_oracle as O
+    return (lambda x, mods: O.backbone_forward(sd, cfg, x, list(mods))), 'port', \
+        'oracle/hrfuser_oracle.py', (H, W), mod_ch
+
+
+def cpu_baseline_fps(workload, budget_s=12.0, max_iters=8):
+    """frames/s of the CPU arm on a bounded sample: batch-1 fp32 forwards."""
+    from hrfuser_b200.utils import synthetic_inputs
+    use_all_host_threads()
+    fwd, kind, what, (H, W), mod_ch = cpu_arm(workload)
     x, mods = synthetic_inputs(1, H, W, mod_ch, seed=0)
     with torch.no_grad():
-        O.backbone_forward(sd, cfg, x, mods)                 # warm-up
+        fwd(x, mods)                                         # warm-up
         ts, t_end = [], time.perf_counter() + budget_s
         while len(ts) < max_iters and (time.perf_counter() < t_end or len(ts) < 3):
             t0 = time.perf_counter()
-            O.backbone_forward(sd, cfg, x, mods)
+            fwd(x, mods)
             ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
-    return dict(value=1.0 / med, unit='frames/s', cores=torch.get_num_threads(), kind='port',
+    return dict(value=1.0 / med, unit='frames/s', cores=torch.get_num_threads(), kind=kind,
                 sample=f'{len(ts)} batch-1 fp32 forwards of {workload} ({H}x{W}), median '
-                       f'{med * 1e3:.0f} ms, oracle/hrfuser_oracle.py on {os.cpu_count()} host CPUs')
+                       f'{med * 1e3:.0f} ms, {what} on {os.cpu_count()} host CPUs')
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path, all host threads."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from hrfuser_b200.utils import synthetic_inputs
-    from oracle import hrfuser_oracle as O
     use_all_host_threads()
-    cfg, net, (H, W), mod_ch = build_net(args.workload, 'fp32')
-    sd = net.state_dict()
+    fwd, kind, what, (H, W), mod_ch = cpu_arm(args.workload)
     x, mods = synthetic_inputs(1, H, W, mod_ch, seed=0)
-    steps = min(args.steps, 10)
+    steps, warm = args.steps, min(max(args.warmup, 1), 3)
+    budget = float(os.environ.get('HRF_REF_BUDGET_S', '240'))
     with torch.no_grad():
-        for _ in range(min(args.warmup, 2)):
-            O.backbone_forward(sd, cfg, x, mods)
-        t0 = time.perf_counter()
+        for _ in range(warm):
+            fwd(x, mods)
+        t0, done = time.perf_counter(), 0
         for _ in range(steps):
-            O.backbone_forward(sd, cfg, x, mods)
+            fwd(x, mods)
+            done += 1
+            if time.perf_counter() - t0 > budget:          # bounded: never past a few minutes
+                break
         dt = time.perf_counter() - t0
-    fps = steps / dt
-    sample = (f'each step = 1 frame (batch-1 fp32 forward, {H}x{W}) of the CPU port '
-              f'oracle/hrfuser_oracle.py; {steps} steps')
+    fps = done / dt
+    sample = (f'each step = 1 frame (batch-1 fp32 forward, {H}x{W}) of {what}; {done} steps')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s',
-        'n_gpus': args.gpus, 'steps': steps, 'warmup': min(args.warmup, 2),
-        'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'n_gpus': args.gpus, 'steps': done, 'warmup': warm,
+        'ms_per_step': dt / done * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'frames_per_step': 1, 'modalities': len(mod_ch) + 1},
         'cpu_baseline': dict(value=fps, unit='frames/s', cores=torch.get_num_threads(),
-                             kind='port', sample=sample),
+                             kind=kind, sample=sample),
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
+
+
+def gpu_eager_baseline(workload, B, dev, iters=5):
+    """The reference's own execution model on the same GPU: the module in PyTorch eager,
+    fp32 and bf16 autocast."""
+    from hrfuser_b200.utils import synthetic_inputs
+    cfg, net, (H, W), mod_ch = build_net(workload, 'fp32')
+    impl, mod = 'mirror (hrfuser_b200/modules.py, torch eager)', None
+    try:
+        from oracle import ref_loader
+        root = ref_loader.find_reference()
+        if root is not None:
+            mod = ref_loader.build_reference_backbone(cfg, root)
+            mod.load_state_dict(net.state_dict())
+            impl = f'unmodified reference module from {root}'
+    except Exception:                            # noqa: BLE001
+        mod = None
+    fwd = (lambda x, m: mod(x, list(m))) if mod is not None else (lambda x, m: net._forward_autograd(x, list(m)))
+    (mod if mod is not None else net).to(dev)
+    x, mods = synthetic_inputs(B, H, W, mod_ch, seed=7)
+    x, mods = x.to(dev), [m.to(dev) for m in mods]
+    res = {}
+    with torch.no_grad():
+        for name, ctx in (('fp32', torch.autocast('cuda', enabled=False)),
+                          ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
+            with ctx:
+                for _ in range(2):
+                    fwd(x, mods)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    fwd(x, mods)
+                b.record()
+                torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            res[name] = dict(ms_per_step=round(ms, 3), frames_per_s=round(B / ms * 1e3, 1))
+    res['impl'], res['frames_per_step'] = impl, B
+    return res
 
 
 def run_ours(args):
@@ -250,38 +320,62 @@ def run_ours(args):
     dev_ms = hdist.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop() if sampler else None
 
-    # ---- (b) end to end: pinned host inputs -> H2D -> forward -> D2H ----------
+    # ---- (b) end to end through the public API: pinned host inputs -> forward -> D2H ---------
+    # `net(x_host, mods_host)`: the forward copies the pinned host tensors straight into the
+    # static buffers of its captured graph (H2D), replays it and returns clones of the four
+    # maps; the caller pipelines n_slots streams (one graph instance per stream) and reads the
+    # maps back into pinned host memory.
     n_slots = int(os.environ.get('HRF_E2E_SLOTS', '3'))   # pipelined steps in flight (2: 2189, 3: 2480, 4: 2449 frames/s)
-    slots = []
-    for s in range(n_slots):
-        st = torch.cuda.Stream()
-        with torch.cuda.stream(st):
-            xin = [torch.empty_like(t) for t in dev_sets[0]]
-            # own memory pool: the slots replay concurrently on different streams
-            g = GraphedForward(engine, xin[0], xin[1:], pool=None)
-            outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in g.out]
-        slots.append((st, xin, g, outs_host))
-    torch.cuda.synchronize()
-    d2h_bytes = sum(o.numel() * o.element_size() for o in slots[0][3])
+    slot_streams = [torch.cuda.Stream() for _ in range(n_slots)]
+    out_shapes = [tuple(o.shape) for o in graphs[0].out]
+    outs_host = [[torch.empty(sh, dtype=torch.float32).pin_memory() for sh in out_shapes]
+                 for _ in range(n_slots)]
+    d2h_bytes = sum(o.numel() * o.element_size() for o in outs_host[0])
+
+    def time_e2e(step_fn):
+        for i in range(max(Wm, 3 * n_slots)):             # >= 2 calls per stream: the second captures
+            step_fn(i)
+        torch.cuda.synchronize()
+        hdist.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            step_fn(i)
+        torch.cuda.synchronize()
+        ms = hdist.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        hdist.barrier()
+        return ms
 
     def e2e_step(i):
-        st, xin, g, outs_host = slots[i % n_slots]
-        with torch.cuda.stream(st):
-            for d, h in zip(xin, host_sets[i % R]):
-                d.copy_(h, non_blocking=True)
-            g()
-            for h, d in zip(outs_host, g.out):
+        with torch.cuda.stream(slot_streams[i % n_slots]), torch.no_grad():
+            hs = host_sets[i % R]
+            outs = net(hs[0], hs[1:])
+            for h, d in zip(outs_host[i % n_slots], outs):
                 h.copy_(d, non_blocking=True)
-    for i in range(Wm):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    hdist.barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_ms = hdist.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
-    hdist.barrier()
+    e2e_ms = time_e2e(e2e_step)
+
+    # ---- (b') raw-frame leg: uint8 camera + fp32 lidar / radar at the un-padded size ---------
+    from hrfuser_b200.pipeline import Normalize, RawBackbone
+    raw_hw = RAW_SIZES.get(args.workload, (H, Wd))
+    keys = ['img'] + [f'mod{k}_img' for k in range(len(mod_ch))]
+    norms = [Normalize([123.675, 116.28, 103.53], [58.395, 57.12, 57.375], to_rgb=True, keys=['img'])]
+    norms += [Normalize([0.5] * c, [2.0] * c, to_rgb=False, keys=[keys[k + 1]], sensor_type='lidar')
+              for k, c in enumerate(mod_ch)]
+    rb = RawBackbone(net, norms)
+    g = torch.Generator().manual_seed(5 + rank)
+    raw_sets = []
+    for r in range(R):
+        d = {'img': torch.randint(0, 256, (B, *raw_hw, 3), generator=g, dtype=torch.uint8).pin_memory()}
+        for k, c in enumerate(mod_ch):
+            d[keys[k + 1]] = torch.randn(B, *raw_hw, c, generator=g).pin_memory()
+        raw_sets.append(d)
+    raw_bytes = sum(t.numel() * t.element_size() for t in raw_sets[0].values())
+
+    def raw_step(i):
+        with torch.cuda.stream(slot_streams[i % n_slots]):
+            outs = rb(raw_sets[i % R])
+            for h, d in zip(outs_host[i % n_slots], outs):
+                h.copy_(d, non_blocking=True)
+    raw_ms = time_e2e(raw_step)
 
     # ---- (c) per-kernel roofline: CUDA events around every C-ABI call ----------
     kernels, roof = {}, None
@@ -340,7 +434,13 @@ def run_ours(args):
     total_frames = float(hdist.gather_frames(frames).sum())
 
     if rank == 0:
-        cpu = cpu_port_fps(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_baseline_fps(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+        eager = None
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                eager = gpu_eager_baseline(args.workload, B, dev)
+            except Exception as e:               # noqa: BLE001 -- a baseline must not fail the run
+                eager = {'error': f'{type(e).__name__}: {e}'}
         out = {
             'metric': METRIC, 'value': total_frames / (dev_ms / 1e3), 'unit': 'frames/s',
             'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': dev_ms / K,
@@ -356,15 +456,106 @@ def run_ours(args):
             'e2e': {'value': total_frames / (e2e_ms / 1e3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': bytes_in, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': e2e_ms / K, 'host_affinity_rank0': numa,
-                    'how': f'{n_slots} pipelined slots (stream + graph each): pinned fp32 host '
-                           'inputs -> H2D -> forward -> D2H of the 4 fp32 maps; wall clock '
-                           'around K steps incl. final sync, max over ranks'},
+                    'how': f'through HRFuserHRFormerBased.forward(x_host, mods_host) on {n_slots} '
+                           'caller streams (the forward keeps one captured graph per signature and '
+                           'stream): pinned fp32 host inputs -> H2D -> forward -> D2H of the 4 fp32 '
+                           'maps; wall clock around K steps incl. final sync, max over ranks'},
+            'e2e_raw': {'value': total_frames / (raw_ms / 1e3), 'unit': 'frames/s',
+                        'h2d_bytes_per_step': raw_bytes, 'd2h_bytes_per_step': d2h_bytes,
+                        'ms_per_step': raw_ms / K,
+                        'how': f'through pipeline.RawBackbone on {n_slots} caller streams: pinned RAW '
+                               f'host frames ({raw_hw[0]}x{raw_hw[1]}: uint8 camera, fp32 modalities) -> '
+                               'H2D -> hrf_input_prologue_fwd + forward in one graph -> D2H of the maps'},
+            'gpu_eager_baseline': eager,
             'gpu_launches': launches_per_step * K,
             'hrf_kernel_launches_per_step': launches_per_step,
             'wall_ms_timed_region': wall_ms,
             'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu,
         }
         print(json.dumps(out))
+    hdist.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_train(args):
+    """configs[3]: HRFuser-B nuScenes SyncBN training step (forward + backward + SGD) with the
+    scene batch sharded over the ranks; the SyncBN statistics all-reduce over NCCL is the
+    path's only data-path collective (plus the gradient all-reduce of DDP).  A step = one
+    optimizer step over B frames per GPU.  `torch_syncbn` times the same module with
+    torch.nn.SyncBatchNorm in place of the hrf_bn_* kernels."""
+    import torch.nn as nn
+    from hrfuser_b200 import HRFuserHRFormerBased, WORKLOADS, backbone_cfg, bn_train, ops
+    from hrfuser_b200 import dist as hdist
+    from hrfuser_b200.utils import randomize_parameters, synthetic_inputs
+    rank, world, local = hdist.init_from_env()
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    variant, dataset, H, Wd = WORKLOADS[args.workload]
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    c = backbone_cfg(variant, dataset)
+    c.pop('type')
+    c['norm_cfg'] = dict(type='SyncBN', requires_grad=True)
+    mod_ch = tuple(c.get('mod_in_channels', [3, 3]))
+
+    def build(torch_bn):
+        net = HRFuserHRFormerBased(**copy.deepcopy(c))
+        randomize_parameters(net, 1)
+        if torch_bn:
+            for m in net.modules():
+                if isinstance(m, bn_train.HrfSyncBatchNorm):
+                    m.__class__ = nn.SyncBatchNorm
+        net = net.to(dev).train()
+        if world > 1:
+            net = nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
+        return net, torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9)
+
+    x, mods = synthetic_inputs(B, H, Wd, mod_ch, seed=10 + rank)
+    x, mods = x.to(dev), [m.to(dev) for m in mods]
+
+    def timed(net, opt):
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = net(x, mods)
+            sum((o * o).mean() for o in out).backward()
+            opt.step()
+        for _ in range(Wm):
+            step()
+        torch.cuda.synchronize()
+        hdist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launch_count()
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        hdist.barrier()
+        return hdist.max_over_ranks(e0.elapsed_time(e1), dev), ops.launch_count() - n0
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    net, opt = build(False)
+    ms, launches = timed(net, opt)
+    clocks = sampler.stop() if sampler else None
+    del net, opt
+    torch.cuda.empty_cache()
+    net, opt = build(True)
+    ms_t, _ = timed(net, opt)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'hrfuser_b_syncbn_train_frames_per_s', 'value': world * B * K / (ms / 1e3),
+            'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'gpu_launches': launches,
+            'config': {'workload': args.workload, 'mode': 'train (forward + backward + SGD step)',
+                       'frames_per_gpu_per_step': B, 'input': f'{H}x{Wd}', 'norm': 'SyncBN',
+                       'parallelism': f'DDP x{world}: SyncBN statistics all-reduce (one fp64 all-reduce of 2C+1 '
+                                      'values per BN and pass) + gradient all-reduce, NCCL',
+                       'weights': 'random-init (seeded)'},
+            'torch_syncbn': {'ms_per_step': ms_t / K, 'frames_per_s': world * B * K / (ms_t / 1e3),
+                             'what': 'same module and step with torch.nn.SyncBatchNorm'},
+            'clocks': clocks,
+        }))
     hdist.barrier()
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -380,12 +571,17 @@ def main():
     ap.add_argument('--batch', type=int, default=8, help='frames per GPU per step')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eager-baseline', action='store_true')
+    ap.add_argument('--train', action='store_true',
+                    help='configs[3]: SyncBN training step (forward + backward + SGD), see run_train')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     if not torch.cuda.is_available():
         sys.exit('bench.py: no CUDA device; the product path has no CPU fallback '
                  '(use --impl reference for the CPU port)')
+    if args.train:
+        return run_train(args)
     run_ours(args)
 
 

@@ -248,13 +248,16 @@ class HRFuserHRFormerBased(nn.Module):
     # eager launch sequence.
     use_cuda_graph = os.environ.get('HRF_GRAPH', '1') != '0'
     graph_outputs = 'clone'
-    max_graphs = 4
+    max_graphs = 8
 
     def _forward_engine(self, x, mods):
         eng = self.engine()
         if not (self.use_cuda_graph and eng.device.type == 'cuda') or torch.cuda.is_current_stream_capturing():
             return eng.forward(x, mods)
-        key = (tuple(x.shape), tuple(tuple(m.shape) for m in mods))
+        # one graph (static buffers, memory pool) per input signature AND stream: a caller that
+        # pipelines steps over several streams gets independent instances
+        key = (tuple(x.shape), tuple(tuple(m.shape) for m in mods),
+               torch.cuda.current_stream(eng.device).cuda_stream)
         ent = self._graphs.get(key)
         if ent is None:                              # first sight: run eagerly, remember
             if len(self._graphs) >= self.max_graphs:

@@ -384,7 +384,13 @@ class BackboneEngine:
         return t.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
 
     @torch.no_grad()
-    def forward(self, x, mods):
+    def forward(self, x, mods, taps=None):
+        """`taps`, if a dict, receives the per-stage feature maps under the names the oracle
+        uses (`fusion_a/b/c`, `stage2/3/4`, `stage_b/c`: lists of fp32 NCHW clones) -- north_star's
+        "per-stage backbone feature maps" parity is checked on these (tests/test_gpu_backbone.py)."""
+        def tap(name, toks):
+            if taps is not None:
+                taps[name] = [t.permute(0, 3, 1, 2).float().contiguous() for t in toks]
         if len(mods) != self.M:
             raise Exception('num_fused_modalities does not fit the given input length')
         fp32_cuda = self.precision == 'fp32' and self.device.type == 'cuda'
@@ -427,10 +433,13 @@ class BackboneEngine:
             stems = self._par([cam_stream] + [lambda k=k: mod_stream(k) for k in range(M)])
             cams, pre_ms = stems[0], stems[1:]
             xs, firsts = self._fuse('a', [lambda i=i: cams[i] for i in range(nb_a)], None, pre_ms)
+            tap('fusion_a', xs)
             res = self._par([lambda: self._run_stage(self.stage[2], xs)] +
                             [lambda k=k: self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0]
                              for k in range(M)])
             ys, stream = res[0], res[1:]
+            tap('stage2', ys)
+            tap('stage_b', stream)
 
             nchw = None
             for idx, letter, nxt in ((2, 'b', 'c'), (3, 'c', 'd')):
@@ -442,6 +451,7 @@ class BackboneEngine:
                         cam_thunks.append(lambda tr=tr: self._tokens(
                             self._apply_chain(tr, self._image(ys[-1]))))
                 xs, firsts = self._fuse(letter, cam_thunks, stream)
+                tap(f'fusion_{letter}', xs)
                 last = idx == 3
                 thunks = [lambda last=last: self._run_stage(self.stage[4 if last else 3], xs,
                                                             final_nchw=last)]
@@ -453,8 +463,10 @@ class BackboneEngine:
                     ys, nchw = res[0]
                 else:
                     ys = res[0]
+                tap('stage4' if last else 'stage3', ys)
                 if nxt in self.stage_mod:
                     stream = res[1:]
+                    tap(f'stage_{nxt}', stream)
             if self.pre_neck_fusion:
                 xs, _ = self._fuse('d', [lambda i=i: ys[i] for i in range(len(ys))], stream)
                 nchw = [self.ops.fuse_sum(t, relu=True, nchw_out=True)[1] for t in xs]

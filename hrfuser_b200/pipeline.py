@@ -81,3 +81,75 @@ class InputPrologue:
             results['pad_fixed_size'] = None
             results['pad_size_divisor'] = self.size_divisor
         return results
+
+
+class RawBackbone:
+    """Raw sensor frames -> the backbone's four feature maps, one CUDA graph per stream.
+
+        rb = RawBackbone(net, [Normalize(..., keys=['img']), Normalize(..., keys=['lidar_img'], ...), ...])
+        outs = rb({'img': uint8 (B,H,W,3) host tensor, 'lidar_img': fp32 (B,H,W,3), ...})
+
+    The first normaliser's first key is the camera stream, the others the extra modalities in
+    order.  The host ships the RAW frames (uint8 camera: a quarter of the fp32 bytes) into
+    static device buffers; `hrf_input_prologue_fwd` (Normalize + Pad + DefaultFormatBundle +
+    collate, reference transforms.py:652-667,719-744, formating.py:211-227) and the engine
+    forward replay as one captured graph.  Like `HRFuserHRFormerBased.forward`, the second call
+    with a given signature on a given stream captures; the maps returned are clones.
+    """
+
+    def __init__(self, net, normalizers, size_divisor=32, pad_val=0):
+        self.net, self.normalizers = net, list(normalizers)
+        self.size_divisor, self.pad_val = size_divisor, pad_val
+        self.keys = [k for n in self.normalizers for k in (n.keys or ['img'])]
+        self.norm_of = {k: n for n in self.normalizers for k in (n.keys or ['img'])}
+        self._graphs = {}
+
+    def _prologue(self, raws):
+        outs = []
+        for k, r in zip(self.keys, raws):
+            n = self.norm_of[k]
+            outs.append(ops.input_prologue(r, n.mean, n.std, to_rgb=n.to_rgb,
+                                           size_divisor=self.size_divisor, pad_val=self.pad_val))
+        return outs
+
+    @torch.no_grad()
+    def __call__(self, results):
+        eng = self.net.engine()
+        frames = [results[k] for k in self.keys]
+        frames = [f.unsqueeze(-1) if f.dim() == 3 else f for f in frames]
+        key = (tuple((tuple(f.shape), f.dtype) for f in frames),
+               torch.cuda.current_stream(eng.device).cuda_stream)
+        ent = self._graphs.get(key)
+        if ent is None or ent == 0:
+            raws = [torch.empty(f.shape, dtype=f.dtype, device=eng.device) for f in frames]
+            for d, f in zip(raws, frames):
+                d.copy_(f, non_blocking=True)
+            if ent is None:                          # first sight: eager
+                self._graphs[key] = 0
+                t = self._prologue(raws)
+                return eng.forward(t[0], t[1:])
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    t = self._prologue(raws)
+                    eng.forward(t[0], t[1:])
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                t = self._prologue(raws)
+                out = eng.forward(t[0], t[1:])
+            ent = self._graphs[key] = (g, raws, out, ops.launch_count() - n0)
+        else:
+            for d, f in zip(ent[1], frames):
+                d.copy_(f, non_blocking=True)
+        ent[0].replay()
+        return [o.clone() for o in ent[2]]
+
+    def launches(self):
+        """hrfuser_b200 kernels per replay of the most recently captured graph"""
+        caps = [e for e in self._graphs.values() if e != 0]
+        return caps[-1][3] if caps else 0

@@ -25,11 +25,12 @@ def rms(t):
 PARITY_LOG = []      # (what, mode, norm-wise error, fraction of elements out of tolerance)
 
 
-def assert_parity(got, ref, mode, what=''):
+def assert_parity(got, ref, mode, what='', min_frac=0.99):
     """fp32: rtol 1e-3 (north_star) -- checked as norm-wise <= 2e-5 *and*
     elementwise allclose(rtol=1e-3, atol=1e-3*rms(ref)).
     bf16: allclose(rtol=2e-2, atol=2e-2*rms(ref)) on >= 99 % of the elements plus
-    norm-wise <= 2e-2 (SURVEY.md App. F explains the rms-scaled atol)."""
+    norm-wise <= 2e-2 (SURVEY.md App. F explains the rms-scaled atol).  `min_frac` relaxes the
+    elementwise share for intermediate taps of deep stacks (stated where it is used)."""
     got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     assert torch.isfinite(got).all(), f'{what}: non-finite output'
@@ -44,7 +45,7 @@ def assert_parity(got, ref, mode, what=''):
         ok = torch.isclose(got, ref, rtol=2e-2, atol=2e-2 * r)
         frac = float(ok.float().mean())
         PARITY_LOG.append((str(what), mode, e, 1 - frac))
-        assert e <= 2e-2 and frac >= 0.99, \
+        assert e <= 2e-2 and frac >= min_frac, \
             f'{what}: bf16 parity failed: norm-wise {e:.3e}, {1 - frac:.2%} elements out'
     return e
 

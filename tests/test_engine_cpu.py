@@ -106,3 +106,79 @@ def test_bad_configs_raise():
     c['extra']['stage2']['num_channels'] = (18,)
     with pytest.raises(AssertionError):
         HRFuserHRFormerBased(**c)
+
+
+@pytest.mark.parametrize('tag,v,d,mc', [('t_nus', 't', 'nus', (3, 3)), ('t_stf', 't', 'stf', (3, 2, 1))])
+def test_engine_stage_taps_vs_reference_golden(built_lib, tag, v, d, mc):
+    """`BackboneEngine.forward(..., taps=...)` names and orders the per-stage maps like the
+    reference's forward hooks (tests/golden/e2e.npz), on the blob-level CPU emulation."""
+    net = _net(backbone_cfg(v, d))
+    H, W = (int(t) for t in E2E[tag + '_hw'])
+    x, mods = synthetic_inputs(1, H, W, mc, seed=3)
+    eng = BackboneEngine(net, 'fp32', device_ops=blob_emul)
+    taps = {}
+    eng.forward(x, mods, taps=taps)
+    n = 0
+    for stage in ('fusion_a', 'fusion_b', 'fusion_c', 'stage2', 'stage3', 'stage4'):
+        for i, t in enumerate(taps[stage]):
+            assert rel_err(t, torch.from_numpy(E2E[f'{tag}_{stage}.{i}'])) < 3e-6, (stage, i)
+            n += 1
+    assert n == 2 + 3 + 4 + 2 + 3 + 4
+    assert len(taps['stage_b']) == len(mc) and len(taps['stage_c']) == len(mc)
+
+
+def test_stem_sub_batches_change_nothing(built_lib):
+    """HRF_STEM_CHUNK runs the stem phase in sub-batches of frames (an L2-blocking experiment,
+    DESIGN.md): frame-wise independent work, so the result is the whole-batch one."""
+    net = _net(tiny_cfg(2))
+    x, mods = synthetic_inputs(3, 64, 96, (3, 3), seed=8)
+    eng = BackboneEngine(net, 'fp32', device_ops=blob_emul)
+    a = eng.forward(x, mods)
+    for ck in (1, 2):
+        eng.stem_chunk = ck
+        b = eng.forward(x, mods)
+        for p, q in zip(a, b):
+            assert rel_err(q, p) < 1e-6
+
+
+def test_eval_mode_with_trainable_parameters_builds_a_graph():
+    """eval() + grad enabled + trainable parameters (fine-tuning with frozen BN
+    statistics) must take the autograd path, as the reference does; under no_grad the engine
+    runs (and, without a GPU, fails loudly)."""
+    net = _net(tiny_cfg(2))
+    x, mods = synthetic_inputs(1, 32, 32, (3, 3), seed=2)
+    out = net(x, mods)
+    assert all(o.requires_grad for o in out)
+    sum(o.sum() for o in out).backward()
+    assert net.conv1.weight.grad is not None
+    from hrfuser_b200 import _lib
+    with torch.no_grad(), pytest.raises(_lib.HrfError):
+        net(x, mods)
+
+
+def test_neck_cache_is_dropped_by_train_and_parent_load():
+    import torch.nn as nn
+    from hrfuser_b200 import HRFPN
+    neck = HRFPN([18, 36, 72, 144], 32)
+    neck._blobs, neck._blobs_ver = ['stale'], neck._weights_version()
+    neck.train()
+    assert neck._blobs is None
+    neck._blobs = ['stale']
+    parent = nn.Module()
+    parent.neck = neck
+    parent.load_state_dict(parent.state_dict())           # a parent's load reaches _load_from_state_dict
+    assert neck._blobs is None
+    v0 = neck._weights_version()
+    with torch.no_grad():
+        neck.reduction_conv.conv.weight.add_(1.0)
+    assert neck._weights_version() != v0                   # in-place updates are seen
+
+
+def test_backbone_engine_is_dropped_by_parent_load():
+    import torch.nn as nn
+    net = _net(tiny_cfg(2))
+    net._engine, net._graphs = object(), {'k': 1}
+    parent = nn.Module()
+    parent.backbone = net
+    parent.load_state_dict(parent.state_dict())
+    assert net._engine is None and net._graphs == {}

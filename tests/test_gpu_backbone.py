@@ -44,8 +44,7 @@ def test_tiny_topology(built_lib, precision):
         if precision == 'fp32':
             assert_parity(g, r, 'fp32', f'out{i}')
         else:
-            # stacked blocks: norm-wise bound end to end
-            assert rel_err(g.cpu(), r) < 3e-2, (i, rel_err(g.cpu(), r))
+            assert_parity(g, r, 'bf16', f'tiny out{i}')       # norm-wise <= 2e-2 and 99 % elementwise
 
 
 def test_t_nus_full_fp32(built_lib):
@@ -60,8 +59,7 @@ def test_t_nus_full_fp32(built_lib):
 def test_t_nus_full_bf16(built_lib):
     got, ref = _run(backbone_cfg('t', 'nus'), (3, 3), 1, 384, 640, 'bf16')
     for i, (g, r) in enumerate(zip(got, ref)):
-        e = rel_err(g.cpu(), r)
-        assert e < 3e-2, f'T-nus bf16 out{i}: norm-wise {e:.3e}'
+        assert_parity(g, r, 'bf16', f'T-nus bf16 out{i}')   # north_star: 2e-2 in the bf16 mode
 
 
 def test_t_stf_4mod_fp32_sparse_and_dropped(built_lib):
@@ -78,10 +76,7 @@ def test_b_nus_all_widths(built_lib, precision):
     high-resolution branches, the generic un-fused path on the wide ones."""
     got, ref = _run(backbone_cfg('b', 'nus'), (3, 3), 1, 64, 96, precision)
     for i, (g, r) in enumerate(zip(got, ref)):
-        if precision == 'fp32':
-            assert_parity(g, r, 'fp32', f'B-nus out{i}')
-        else:
-            assert rel_err(g.cpu(), r) < 3e-2, (i, rel_err(g.cpu(), r))
+        assert_parity(g, r, precision, f'B-nus out{i}')
 
 
 def test_forward_spellings_and_errors(built_lib):
@@ -140,3 +135,103 @@ def test_stream_concurrency_and_graph_replay_are_bit_identical(built_lib, precis
     torch.cuda.synchronize()
     for p, q, r, r2 in zip(a, b, c, c2):
         assert torch.equal(p, q) and torch.equal(p, r) and torch.equal(p, r2)
+
+
+STAGE_TAPS = ('fusion_a', 'stage2', 'stage_b', 'fusion_b', 'stage3', 'stage_c', 'fusion_c', 'stage4')
+
+
+@pytest.mark.parametrize('tag,v,d,mc,H,W', [('t_nus', 't', 'nus', (3, 3), 192, 320),
+                                            ('t_stf', 't', 'stf', (3, 2, 1), 96, 320),
+                                            ('b_nus', 'b', 'nus', (3, 3), 64, 96)])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_per_stage_feature_maps(built_lib, tag, v, d, mc, H, W, precision):
+    """north_star: per-stage backbone feature maps match the reference -- every fusion-block
+    and HRFormer-stage output of the camera stream and of the modality streams, against the
+    oracle's taps (themselves pinned on the reference's hooks: tests/test_oracle_golden.py)."""
+    cfg = backbone_cfg(v, d)
+    net = _build(cfg, precision)
+    x, mods = synthetic_inputs(1, H, W, mc, seed=4)
+    ref_taps = {}
+    with torch.no_grad():
+        O.backbone_forward(net.state_dict(), cfg, x, mods, ref_taps)
+    net.cuda()
+    got_taps = {}
+    net.engine().forward(x.cuda(), [m.cuda() for m in mods], taps=got_taps)
+    torch.cuda.synchronize()
+    n = 0
+    for name in STAGE_TAPS:
+        assert len(got_taps[name]) == len(ref_taps[name]), name
+        for i, (g, r) in enumerate(zip(got_taps[name], ref_taps[name])):
+            # bf16 mode: norm-wise <= 2e-2 on every tap; the elementwise share is 97 % here (the
+            # small low-resolution maps after ~20 stacked bf16 blocks have a heavier error tail:
+            # measured worst case 1.3 % of the elements outside rtol 2e-2) and 99 % on the outputs
+            assert_parity(g, r, precision, f'{tag} {name}.{i}', min_frac=0.97)
+            n += 1
+    M = len(mc)
+    assert n == 2 + 2 + M + 3 + 3 + M + 4 + 4
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_t_stf_full_size(built_lib, precision):
+    """configs[2] at its shipped size: HRFuser-T Seeing Through Fog, 384 x 1248, cam + lidar +
+    radar + gated (3 / 2 / 1 channels)."""
+    got, ref = _run(backbone_cfg('t', 'stf'), (3, 2, 1), 1, 384, 1248, precision)
+    shapes = [(1, 18, 96, 312), (1, 36, 48, 156), (1, 72, 24, 78), (1, 144, 12, 39)]
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert tuple(g.shape) == shapes[i]
+        # bf16 mode: norm-wise <= 2e-2 (measured 8.4e-3 on out0); with three modality streams
+        # accumulating into the camera stream 98.6 % of out0's elements sit inside rtol 2e-2
+        # (T-nus: > 99 %), so the elementwise share asserted here is 98 %
+        assert_parity(g, r, precision, f'T-stf 384x1248 out{i}', min_frac=0.98)
+
+
+def test_b_nus_full_size_bf16(built_lib):
+    """configs[3]'s model at its shipped size: HRFuser-B nuScenes 384 x 640, bf16 mode."""
+    got, ref = _run(backbone_cfg('b', 'nus'), (3, 3), 1, 384, 640, 'bf16')
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert_parity(g, r, 'bf16', f'B-nus 384x640 out{i}')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_public_forward_graph_cache(built_lib, precision):
+    """HRFuserHRFormerBased.forward: first call eager, second call captures a CUDA graph, later
+    calls replay it -- all bit-identical, with device and with pinned host inputs, and the
+    returned maps are the caller's own (not overwritten by the next call)."""
+    net = _build(tiny_cfg(2), precision).cuda()
+    x, mods = synthetic_inputs(2, 64, 96, (3, 3), seed=5, device='cuda')
+    x2, mods2 = synthetic_inputs(2, 64, 96, (3, 3), seed=6)
+    with torch.no_grad():
+        a = net(x, mods)                                    # eager
+        b = net(x, mods)                                    # capture + replay
+        c = net(x, mods)                                    # replay
+        d = net(x2.pin_memory(), [m.pin_memory() for m in mods2])      # host inputs, other data
+        e = net.engine().forward(x2.cuda(), [m.cuda() for m in mods2])
+        torch.cuda.synchronize()
+        assert any(v != 0 for v in net._graphs.values())
+        for p, q, r in zip(a, b, c):
+            assert torch.equal(p, q) and torch.equal(p, r)
+        for p, q in zip(d, e):
+            assert torch.equal(p, q)
+        assert not torch.equal(a[0], d[0])                  # c was not clobbered by the 4th call
+        assert torch.equal(a[0], c[0])
+        net.load_state_dict(_build(tiny_cfg(2), precision, seed=9).state_dict())
+        assert net._graphs == {}                            # a reload drops the captured graphs
+
+
+def test_parent_load_state_dict_invalidates(built_lib):
+    """a checkpoint loaded through a PARENT module never calls the child's
+    load_state_dict; the packed weights must be dropped all the same."""
+    import torch.nn as nn
+    det = nn.Module()
+    det.backbone = _build(tiny_cfg(2), 'fp32', seed=1).cuda()
+    other = nn.Module()
+    other.backbone = _build(tiny_cfg(2), 'fp32', seed=2)
+    x, mods = synthetic_inputs(1, 32, 32, (3, 3), device='cuda')
+    with torch.no_grad():
+        a = det.backbone(x, mods)
+        det.load_state_dict(other.state_dict())
+        b = det.backbone(x, mods)
+        ref = O.backbone_forward(other.backbone.state_dict(), tiny_cfg(2), x.cpu(), [m.cpu() for m in mods])
+    assert not torch.equal(a[0], b[0])
+    for i, (g, r) in enumerate(zip(b, ref)):
+        assert_parity(g, r, 'fp32', f'parent-reloaded out{i}')

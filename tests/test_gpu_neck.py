@@ -84,5 +84,31 @@ def test_whole_neck_full_size_and_zero_input(built_lib):
         # the 3x3 convs run in torch on both sides (cuDNN vs CPU); pooled levels: see above
         e = float((g.cpu() - w).pow(2).mean().sqrt()) / scale
         assert e < 2e-5, (i, e)
-    with pytest.raises(ValueError):
+    with torch.no_grad(), pytest.raises(ValueError):
         net([xs[0].cuda(), xs[1].cuda(), xs[2].cuda(), xs[2].cuda()])
+
+
+def test_reduction_weights_repacked_after_an_optimizer_step(built_lib):
+    """eval -> in-place parameter update -> eval must use the NEW reduction
+    weights (the packed blobs are keyed on the parameters' version counters and dropped by
+    train())."""
+    import torch
+    from hrfuser_b200 import HRFPN
+    torch.manual_seed(0)
+    neck = HRFPN([18, 36, 72, 144], 64, precision='fp32').cuda().eval()
+    xs = [torch.randn(1, c, 32 >> i, 48 >> i, device='cuda') for i, c in enumerate([18, 36, 72, 144])]
+    with torch.no_grad():
+        a = neck(xs)
+        ref_a = neck._forward_autograd(xs)
+        with torch.no_grad():
+            for p_ in neck.parameters():
+                p_.add_(0.05 * torch.randn_like(p_))           # what optimizer.step() does
+        b = neck(xs)
+        ref_b = neck._forward_autograd(xs)
+    for g, r in zip(a, ref_a):
+        assert float((g - r).norm() / r.norm()) < 2e-3        # (the torch side runs TF32 convs)
+    for g, r in zip(b, ref_b):
+        assert float((g - r).norm() / r.norm()) < 2e-3, 'stale packed reduction weights'
+    assert float((a[0] - b[0]).abs().max()) > 1e-3
+    neck.train()
+    assert neck._blobs is None

@@ -64,7 +64,7 @@ def test_lsa(built_lib, H, W, C, heads, mode):
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('M', [1, 2, 3])
-@pytest.mark.parametrize('H,W,C,heads', NUS_T + STF_T[:2] + NUS_B_FUSED[:1] + NUS_B_WIDE + EDGE[:4])
+@pytest.mark.parametrize('H,W,C,heads', NUS_T + STF_T + NUS_B_FUSED + NUS_B_WIDE + EDGE[:4])
 def test_mwca(built_lib, H, W, C, heads, M, mode):
     from hrfuser_b200 import ops
     B = 2
