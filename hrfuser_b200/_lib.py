@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 HRF_F32, HRF_BF16, HRF_U8 = 0, 1, 2
 MAX_FUSE_TERMS = 4
@@ -42,6 +42,11 @@ class DwPwDesc(PwDesc):
 class ConvDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32),
                 ('Cout', C.c_int32), ('stride', C.c_int32), ('dtype', C.c_int32), ('relu', C.c_int32)]
+
+
+class ConvGemmDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32),
+                ('Cout', C.c_int32), ('ksize', C.c_int32), ('stride', C.c_int32), ('relu', C.c_int32)]
 
 
 class StemDesc(C.Structure):
@@ -94,6 +99,12 @@ SIGNATURES = {
     'hrf_conv3x3_blob_floats': (C.c_size_t, [C.POINTER(ConvDesc)]),
     'hrf_conv3x3_pack': (C.c_int, [C.POINTER(ConvDesc), _F, _F, _FP4, C.c_float, _F]),
     'hrf_conv3x3_fwd': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hrf_convgemm_supported': (C.c_int, [C.POINTER(ConvGemmDesc)]),
+    'hrf_convgemm_blob_floats': (C.c_size_t, [C.POINTER(ConvGemmDesc)]),
+    'hrf_convgemm_pack': (C.c_int, [C.POINTER(ConvGemmDesc), _F, _F, _FP4, C.c_float, _F, _F]),
+    'hrf_convgemm_fwd': (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    'hrf_convgemm_grouped_fwd': (C.c_int, [C.POINTER(ConvGemmDesc), C.c_int32, _VPP, _VPP, _VPP, _VPP, C.c_void_p]),
     'hrf_dwpw_blob_floats': (C.c_size_t, [C.POINTER(DwPwDesc)]),
     'hrf_dwpw_pack': (C.c_int, [C.POINTER(DwPwDesc), _F, _FP4, _F, _FP4, C.c_float, _F]),
     'hrf_dwpw_fwd': (C.c_int, [C.POINTER(DwPwDesc), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -123,6 +134,7 @@ SIGNATURES = {
                                     C.c_int32, C.c_void_p]),
     'hrf_input_prologue_fwd': (C.c_int, [C.POINTER(InputDesc), C.c_void_p, _F, _F, C.c_void_p,
                                          C.c_void_p]),
+    'hrf_pool_fwd': (C.c_int, [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     'hrf_nchw_to_nhwc': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,
                                                      C.c_void_p]),
     'hrf_nhwc_to_nchw': (C.c_int, [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p,

@@ -17,6 +17,8 @@
 #include "mixffn_tc.cuh"
 #include "mixffn_v2.cuh"
 #include "conv3x3_tc.cuh"
+#include "conv_gemm_tc.cuh"
+#include "pool.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
 #include "window_attn.cuh"
@@ -538,6 +540,78 @@ int hrf_conv3x3_fwd(const HrfConvDesc* d, const void* x, const float* blob, void
   HRF_REQUIRE(false, HRF_EINVAL, "conv3x3_fwd: dtype");
 }
 
+// ------------------------------------------------------------------ dense conv as TMA + tcgen05 GEMM
+int hrf_convgemm_supported(const HrfConvGemmDesc* d) {
+  HRF_REQUIRE(d != nullptr, HRF_EINVAL, "convgemm: null descriptor");
+  HRF_REQUIRE(d->B > 0 && conv_gemm_supported(d->Cin, d->Cout, d->ksize, d->stride, d->H, d->W), HRF_EUNSUPPORTED,
+              "convgemm: %dx%d conv %d -> %d stride %d is outside what the kernel covers", d->ksize, d->ksize,
+              d->Cin, d->Cout, d->stride);
+  return HRF_OK;
+}
+size_t hrf_convgemm_blob_floats(const HrfConvGemmDesc* d) {
+  if (!d || hrf_convgemm_supported(d) != HRF_OK) return 0;
+  return (size_t)ConvGemmLayout(d->Cin, d->Cout, d->ksize * d->ksize).total;
+}
+int hrf_convgemm_pack(const HrfConvGemmDesc* d, const float* w, const float* bias, const float* const bn[4],
+                      float bn_eps, const float* extra_bias, float* blob) {
+  int rc = hrf_convgemm_supported(d);
+  if (rc) return rc;
+  HRF_REQUIRE(w && blob, HRF_EINVAL, "convgemm_pack: null pointer");
+  const int taps = d->ksize * d->ksize, Cin = d->Cin, Cout = d->Cout;
+  const ConvGemmLayout L(Cin, Cout, taps);
+  std::vector<float> sc, sh;
+  bn_affine(bn, Cout, bn_eps, sc, sh);
+  std::memset(blob, 0, sizeof(float) * L.total);
+  uint16_t* wt = reinterpret_cast<uint16_t*>(blob + L.o_w);
+  for (int n = 0; n < Cout; ++n) {
+    blob[L.o_bias + n] = (bias ? bias[n] : 0.f) * sc[n] + sh[n] + (extra_bias ? extra_bias[n] : 0.f);
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < taps; ++t)
+        wt[((size_t)t * L.NPAD + n) * Cin + c] = f32_to_bf16(w[((size_t)n * Cin + c) * taps + t] * sc[n]);
+  }
+  return HRF_OK;
+}
+int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs, const void* const* resids,
+                             const float* const* blobs, void* const* outs, void* stream) {
+  int rc = hrf_convgemm_supported(d);
+  if (rc) return rc;
+  HRF_REQUIRE(n >= 1 && n <= kMaxProb, HRF_EINVAL, "convgemm_fwd: 1..%d problems per launch, %d given", kMaxProb, n);
+  HRF_REQUIRE(xs && blobs && outs, HRF_EINVAL, "convgemm_fwd: null pointer");
+  ConvGemmParams p{};
+  for (int q = 0; q < n; ++q) {
+    const void* r = resids ? resids[q] : nullptr;
+    HRF_REQUIRE(xs[q] && blobs[q] && outs[q], HRF_EINVAL, "convgemm_fwd: null pointer (problem %d)", q);
+    HRF_REQUIRE(xs[q] != outs[q], HRF_EINVAL, "convgemm_fwd: out must not alias x");
+    HRF_REQUIRE((r != nullptr) == (resids != nullptr && resids[0] != nullptr), HRF_EINVAL,
+                "convgemm_fwd: residuals for all problems or for none");
+    HRF_REQUIRE(((reinterpret_cast<uintptr_t>(xs[q]) | reinterpret_cast<uintptr_t>(outs[q]) |
+                  reinterpret_cast<uintptr_t>(blobs[q]) | reinterpret_cast<uintptr_t>(r)) & 15) == 0,
+                HRF_EINVAL, "convgemm_fwd: pointers must be 16-byte aligned");
+    p.blob[q] = blobs[q]; p.resid[q] = r; p.out[q] = outs[q];
+  }
+  p.n_prob = n;
+  p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.taps = d->ksize * d->ksize; p.relu = d->relu; p.stride = d->stride;
+  p.Ho = (d->H + d->stride - 1) / d->stride;
+  p.Wo = (d->W + d->stride - 1) / d->stride;
+  p.tiles_w = ceil_div(p.Wo, cg::TM_W);
+  p.tiles_h = ceil_div(p.Ho, cg::TM_H);
+  p.n_tiles = p.B * p.tiles_w * p.tiles_h;
+  p.d_tiles_prob = FastDiv(p.n_tiles);
+  p.d_tiles_img = FastDiv(p.tiles_w * p.tiles_h);
+  p.d_tiles_w = FastDiv(p.tiles_w);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ConvGemmLayout(d->Cin, d->Cout, p.taps).NPAD) {
+    case 32: return launch_conv_gemm_n<32>(p, xs, d->H, d->W, d->stride, st);
+    case 64: return launch_conv_gemm_n<64>(p, xs, d->H, d->W, d->stride, st);
+    case 128: return launch_conv_gemm_n<128>(p, xs, d->H, d->W, d->stride, st);
+    default: return launch_conv_gemm_n<256>(p, xs, d->H, d->W, d->stride, st);
+  }
+}
+int hrf_convgemm_fwd(const HrfConvGemmDesc* d, const void* x, const void* resid, const float* blob, void* out,
+                     void* stream) {
+  return hrf_convgemm_grouped_fwd(d, 1, &x, resid ? &resid : nullptr, &blob, &out, stream);
+}
+
 size_t hrf_dwpw_blob_floats(const HrfDwPwDesc* d) {
   if (!d || d->Cin <= 0 || d->Cout <= 0) return 0;
   return (size_t)DwPwLayout(d->Cin, d->Cout).total;
@@ -744,6 +818,15 @@ int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, co
                      int32_t ddt, void* dst, void* stream) {
   HRF_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, HRF_EINVAL, "nchw_to_nhwc: args");
   return launch_layout<true>(B, C, H, W, sdt, src, ddt, dst, (cudaStream_t)stream);
+}
+int hrf_pool_fwd(int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, int32_t is_max, const void* x, void* out,
+                 void* stream) {
+  HRF_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0 && k > 0, HRF_EINVAL, "pool: args");
+  HRF_REQUIRE(C % 8 == 0 && H % k == 0 && W % k == 0, HRF_EUNSUPPORTED,
+              "pool: C=%d must be a multiple of 8 and %dx%d a multiple of the window %d", C, H, W, k);
+  HRF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, HRF_EINVAL,
+              "pool: pointers must be 16-byte aligned");
+  return launch_pool_tokens(x, out, B, H, W, C, k, is_max != 0, (cudaStream_t)stream);
 }
 int hrf_nhwc_to_nchw(int32_t B, int32_t C, int32_t H, int32_t W, int32_t sdt, const void* src,
                      int32_t ddt, void* dst, void* stream) {

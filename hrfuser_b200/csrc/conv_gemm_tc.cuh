@@ -1,0 +1,424 @@
+// Dense 1x1 / 3x3 convolution (+ folded BN, + residual, + ReLU) of the stems, the Bottlenecks,
+// the 256-channel transitions and the HRFPN convs as a warp-specialised, TMA-fed tcgen05
+// implicit GEMM -- bf16 mode (reference hrnet.py:341-371,419-463,
+// resnet.py:263-302, necks/hrfpn.py:87-100).
+//
+//   out[b,h,w,n] = act( sum_tap sum_c x[b, h*s+dy-1, w*s+dx-1, c] * W[tap][n][c] + bias[n] (+ resid[b,h,w,n]) )
+//
+//   M tile   128 output tokens = 8 rows x 16 columns of one image
+//   N        all output channels of the layer, padded to 32 | 64 | 128 | 256 accumulator columns
+//   K loop   taps x (Cin / 64): per step one A tile [128 tokens x 64 channels] and one B tile
+//            [N x 64] in 128-byte-swizzled K-major shared memory, four K = 16 UMMAs
+//
+// Roles (192 threads, one CTA per SM, persistent over the tiles):
+//   warp 0      TMA producer: for every K step one 4-D tensor-tile copy of the activations --
+//               box (64 channels, 16, 8, 1) at (c0, w0 + dx - 1, h0 + dy - 1, b); the unit
+//               zero-fills what lies outside the image, which IS the convolution's zero padding;
+//               a stride-2 convolution reads through a map with element strides (1, 2, 2, 1) --
+//               and one 3-D copy of the weights (64, N, 1) at (c0, 0, tap), into a ring of
+//               STAGES stages (full / empty mbarriers)
+//   warp 1      MMA issuer: waits for a stage, issues the four UMMAs, commits the stage's
+//               `empty` barrier; after the last K step commits the accumulator's `full` barrier.
+//               The accumulator is double-buffered in TMEM (2 x N columns): the MMAs of tile
+//               i + 1 run while the epilogue drains tile i
+//   warps 2-5   epilogue: TMEM -> registers (a thread per token row), + bias, + residual, ReLU,
+//               bf16.  Channel counts that are multiples of 64 go through shared-memory "C
+//               slots" of [128 tokens x 64 channels] in the same 128-byte swizzle: the producer
+//               TMA-loads the residual sub-tile into the slot ahead of time, the epilogue adds
+//               in place (conflict-free 16-byte accesses) and one elected thread TMA-stores the
+//               slot; per-thread global accesses (a 512-byte stride between lanes) ran the
+//               64 -> 256 + residual layer at 97 us against 36 us for cuDNN.  Other widths (the
+//               18 / 36-channel transitions) store straight from registers.
+// No CTA-wide barrier inside the tile loop.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma.cuh"
+
+namespace hrf {
+
+// blob: fp32 bias[NPAD] | bf16 W [taps][NPAD rows][Cin] (K-major rows, zero rows beyond Cout)
+struct ConvGemmLayout {
+  int NPAD, o_bias, o_w, total;   // floats
+  __host__ __device__ ConvGemmLayout(int cin, int cout, int taps) {
+    NPAD = cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+    o_bias = 0;
+    o_w = NPAD;
+    total = o_w + taps * NPAD * cin / 2;
+  }
+};
+
+// Up to kMaxProb problems of ONE shape per launch (the camera stream and the modality streams
+// run the same stem / Bottleneck / transition layers on tensors of the same size, each with its
+// own weights): the persistent CTAs walk the tiles of all of them, so the layer is one launch
+// for (1 + M) streams instead of (1 + M) launches that each take the whole GPU in turn.
+constexpr int kMaxProb = 4;
+struct ConvGemmParams {
+  const float* blob[kMaxProb];
+  const void* resid[kMaxProb];      // [B][Ho][Wo][Cout] bf16 or nullptr (all or none)
+  void* out[kMaxProb];              // [B][Ho][Wo][Cout] bf16
+  int n_prob;
+  int B, Ho, Wo, Cin, Cout, taps, relu, stride;   // relu: bit q = ReLU on problem q
+  int tiles_w, tiles_h, n_tiles;    // n_tiles: per problem
+  FastDiv d_tiles_prob, d_tiles_img, d_tiles_w;
+};
+struct ConvGemmMaps {               // 4 x 4 tensor maps = 2 KB of kernel parameters
+  CUtensorMap x[kMaxProb], w[kMaxProb], c[kMaxProb], r[kMaxProb];
+};
+
+namespace cg {
+constexpr int TM_H = 8, TM_W = 16;                    // the 128-token M tile
+constexpr int A_BYTES = 128 * 128;                    // 128 tokens x 64 channels bf16
+constexpr int NT = 192;
+
+// shared-memory descriptor of a 128-byte-swizzled K-major operand tile (rows of 128 bytes, 8-row
+// groups 1024 bytes apart), K step `ks` (16 elements = 32 bytes) -- sm_100 descriptor version 1,
+// layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, int ks) {
+  uint64_t d = 0;
+  d |= (uint64_t)(((saddr + (uint32_t)ks * 32u) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                             // descriptor version
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(umma::smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(umma::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+}  // namespace cg
+
+template <int NPAD>
+struct ConvGemmCfg {
+  static constexpr int B_BYTES = NPAD * 128;
+  static constexpr int STAGE = cg::A_BYTES + B_BYTES;
+  static constexpr int NSUB = NPAD / 64;                      // 64-channel sub-tiles of the output (0: direct stores)
+  static constexpr int NSLOT = NSUB == 0 ? 0 : (NSUB < 2 ? 2 : NSUB);   // C slots (residual in, result out)
+  static constexpr int C_BYTES = NSLOT * cg::A_BYTES;
+  static constexpr int ROOM = 218 * 1024 - C_BYTES;     // 227 KB - static (bias table, barriers) - slack
+  static constexpr int STAGES = ROOM / STAGE > 8 ? 8 : ROOM / STAGE;
+  static constexpr int SMEM = STAGES * STAGE + C_BYTES + 1024;          // + alignment slack
+  static constexpr int TMEM_COLS = 2 * NPAD < 32 ? 32 : 2 * NPAD;
+  static_assert(SMEM + kMaxProb * NPAD * 4 + 1024 <= 227 * 1024, "dynamic + static shared memory");
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(cg::NT, 1)
+conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ ConvGemmMaps tm) {
+  using namespace umma;
+  using K = ConvGemmCfg<NPAD>;
+  constexpr int STAGES = K::STAGES;
+  extern __shared__ unsigned char sm_raw[];
+  constexpr int NSLOT = K::NSLOT > 0 ? K::NSLOT : 1, NSUB = K::NSUB;
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t c_full[NSLOT], c_empty[NSLOT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[kMaxProb * NPAD];
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
+  // operand tiles need 1024-byte alignment (128-byte swizzle atom = 8 rows x 128 bytes)
+  unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+  const int kc = p.Cin / 64, n_k = p.taps * kc;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);                    // one arrival per epilogue warp
+    }
+    for (int c = 0; c < NSLOT; ++c) {
+      mbar_init(&c_full[c], 1);
+      mbar_init(&c_empty[c], 1);
+    }
+    fence_mbar_init();
+    for (int q = 0; q < p.n_prob; ++q) {
+      tma_prefetch_desc(&tm.x[q]);
+      tma_prefetch_desc(&tm.w[q]);
+      if (NSUB > 0) tma_prefetch_desc(&tm.c[q]);
+    }
+  }
+  const int total_tiles = p.n_tiles * p.n_prob;
+  const bool staged = NSUB > 0 && p.Cout == NPAD;    // whole 64-channel sub-tiles: the C-slot epilogue
+  unsigned char* c_slots = sm + STAGES * K::STAGE;
+  for (int e = tid; e < p.n_prob * NPAD; e += cg::NT) s_bias[e] = __ldg(p.blob[e / NPAD] + (e % NPAD));
+  if (warp == 1) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer ===========================================================================
+    if (elect_one()) {
+      int it = 0, cit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int pr, tl, b, rem, ty, tx;
+        p.d_tiles_prob.divmod(tile, pr, tl);
+        p.d_tiles_img.divmod(tl, b, rem);
+        p.d_tiles_w.divmod(rem, ty, tx);
+        const int h0 = ty * cg::TM_H, w0 = tx * cg::TM_W;
+        for (int k = 0; k < n_k; ++k, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1, 200 + s);
+          const int tap = k / kc, c0 = (k - tap * kc) * 64;
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          unsigned char* a = sm + s * K::STAGE;
+          mbar_expect_tx(&full[s], cg::A_BYTES + K::B_BYTES);
+          cg::tma_load_4d(a, &tm.x[pr], c0, w0 * p.stride + dx, h0 * p.stride + dy, b, &full[s]);
+          tma_load_3d(a + cg::A_BYTES, &tm.w[pr], c0, 0, tap, &full[s]);
+        }
+        if (NSUB > 0 && staged && p.resid[0] != nullptr) {
+          // residual sub-tiles of THIS tile into the C slots (after its K steps: the slots are
+          // released by the previous tile's stores, which must not hold back this tile's MMAs)
+          for (int j = 0; j < NSUB; ++j, ++cit) {
+            const int cs = cit % NSLOT;
+            if (cit >= NSLOT) mbar_wait(&c_empty[cs], ((cit / NSLOT) - 1) & 1, 240 + cs);
+            mbar_expect_tx(&c_full[cs], cg::A_BYTES);
+            cg::tma_load_4d(c_slots + cs * cg::A_BYTES, &tm.r[pr], j * 64, w0, h0, b, &c_full[cs]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ==============================================================================
+    constexpr uint32_t idesc = idesc_bf16(128, NPAD, false, false);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      if (tcount >= 2) mbar_wait(&acc_empty[acc], ((tcount >> 1) - 1) & 1, 210 + acc);
+      tc_fence_after();
+      for (int k = 0; k < n_k; ++k, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1, 220 + s);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a = smem_u32(sm + s * K::STAGE), bq = a + cg::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16(tmem + acc * NPAD, cg::desc_sw128(a, ks), cg::desc_sw128(bq, ks), idesc, (k | ks) != 0);
+          mma_commit(&empty[s]);                      // frees the stage when these MMAs have read it
+          if (k == n_k - 1) mma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue warps ==========================================================================
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;                    // token of the tile
+    const int hh = row >> 4, ww = row & 15;
+    int tcount = 0, cit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      int pr, tl, b, rem, ty, tx;
+      p.d_tiles_prob.divmod(tile, pr, tl);
+      p.d_tiles_img.divmod(tl, b, rem);
+      p.d_tiles_w.divmod(rem, ty, tx);
+      const __nv_bfloat16* resid = static_cast<const __nv_bfloat16*>(p.resid[pr]);
+      __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out[pr]);
+      const float* bias = s_bias + pr * NPAD;
+      const bool relu = (p.relu >> pr) & 1;
+      const int h = ty * cg::TM_H + hh, w = tx * cg::TM_W + ww;
+      const bool live = h < p.Ho && w < p.Wo;
+      const size_t tok = ((size_t)(b * p.Ho + (live ? h : 0)) * p.Wo + (live ? w : 0)) * p.Cout;
+      mbar_wait(&acc_full[acc], (tcount >> 1) & 1, 230 + acc);
+      tc_fence_after();
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * NPAD;
+      if (NSUB > 0 && staged) {
+        // ---- C-slot epilogue: 64-channel sub-tiles through swizzled shared memory + TMA store ----
+        const bool has_r = resid != nullptr;
+#pragma unroll 1
+        for (int j = 0; j < NSUB; ++j, ++cit) {
+          const int cs = cit % NSLOT;
+          unsigned char* slot = c_slots + cs * cg::A_BYTES;
+          float v[64];
+          tmem_ld32(trow + j * 64, v);
+          tmem_ld32(trow + j * 64 + 32, v + 32);
+          if (has_r) mbar_wait(&c_full[cs], (cit / NSLOT) & 1, 250 + cs);          // residual has landed
+          else if (cit >= NSLOT) mbar_wait(&c_empty[cs], ((cit / NSLOT) - 1) & 1, 260 + cs);   // slot drained
+          tmem_ld_wait();
+          unsigned char* rowp = slot + row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4* cp = reinterpret_cast<uint4*>(rowp + ((ch ^ (row & 7)) << 4));
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = v[ch * 8 + e] + bias[j * 64 + ch * 8 + e];
+            if (has_r) {
+              const uint4 r = *cp;
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                a[2 * e] += __uint_as_float(rw[e] << 16);
+                a[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a0 = a[2 * e], a1 = a[2 * e + 1];
+              if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              const __nv_bfloat162 hb = __floats2bfloat162_rn(a0, a1);
+              o[e] = *reinterpret_cast<const uint32_t*>(&hb);
+            }
+            *cp = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async();                                  // generic writes -> the TMA store's reads
+          asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+          if (warp == 2 && elect_one()) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm.c[pr]), "r"(smem_u32(slot)), "r"(j * 64), "r"(tx * cg::TM_W), "r"(ty * cg::TM_H), "r"(b)
+                         : "memory");
+            tma_store_commit();
+            if (cit >= 1) {                                     // the PREVIOUS slot's store has read its data
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              cg::mbar_arrive(&c_empty[(cit - 1) % NSLOT]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NPAD; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_ld_wait();
+        if (live && c0 < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bias[c0 + j];
+          if (((p.Cout * 2) & 15) == 0) {             // 16-byte vector path (channel count % 8 == 0)
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              if (c0 + g8 * 8 < p.Cout) {
+                if (resid) {
+                  const uint4 r = __ldg(reinterpret_cast<const uint4*>(resid + tok + c0 + g8 * 8));
+                  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    v[g8 * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                    v[g8 * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+                  }
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float a0 = v[g8 * 8 + 2 * j], a1 = v[g8 * 8 + 2 * j + 1];
+                  if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  const __nv_bfloat162 hb = __floats2bfloat162_rn(a0, a1);
+                  o[j] = *reinterpret_cast<const uint32_t*>(&hb);
+                }
+                *reinterpret_cast<uint4*>(out + tok + c0 + g8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          } else {                                    // 4-byte path (18 / 36-channel transitions)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + 2 * j < p.Cout) {
+                float a0 = v[2 * j], a1 = v[2 * j + 1];
+                if (resid) {
+                  const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(resid + tok + c0 + 2 * j));
+                  a0 += __uint_as_float(r << 16);
+                  a1 += __uint_as_float(r & 0xffff0000u);
+                }
+                if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(a0, a1);
+                *reinterpret_cast<uint32_t*>(out + tok + c0 + 2 * j) = *reinterpret_cast<const uint32_t*>(&hb);
+              }
+            }
+          }
+        }
+      }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) cg::mbar_arrive(&acc_empty[acc]);
+    }
+    if (NSUB > 0 && staged && warp == 2 && elect_one()) tma_store_wait_all();   // same thread that issued them
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, K::TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static bool conv_gemm_supported(int Cin, int Cout, int k, int stride, int H, int W) {
+  return (k == 1 || k == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && Cin >= 64 && Cout % 2 == 0 &&
+         Cout <= 256 && H > 0 && W > 0 && (k == 3 || stride == 1);
+}
+
+template <int NPAD>
+static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, int Wi, int stride, cudaStream_t stream) {
+  using K = ConvGemmCfg<NPAD>;
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  HRF_REQUIRE(enc != nullptr, HRF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  ConvGemmMaps tm;
+  const bool staged = K::NSUB > 0 && p.Cout == NPAD;
+  for (int q = 0; q < p.n_prob; ++q) {
+    {
+      // activations [B][Hi][Wi][Cin] bf16 as (Cin, Wi, Hi, B); a stride-2 convolution steps over
+      // every second token / row (element strides), so its coordinates stay in INPUT units
+      const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)p.B};
+      const cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)Wi * p.Cin * 2, (cuuint64_t)Hi * Wi * p.Cin * 2};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)(cg::TM_H * stride), 1u};
+      const cuuint32_t est[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+      const CUresult r = enc(&tm.x[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[q]), gdim, gstr, box,
+                             est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: activation tensor map failed (%d)", (int)r);
+    }
+    {
+      const ConvGemmLayout L(p.Cin, p.Cout, p.taps);
+      const cuuint64_t gdim[3] = {(cuuint64_t)p.Cin, (cuuint64_t)NPAD, (cuuint64_t)p.taps};
+      const cuuint64_t gstr[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)NPAD * p.Cin * 2};
+      const cuuint32_t box[3] = {64u, (cuuint32_t)NPAD, 1u};
+      const cuuint32_t est[3] = {1u, 1u, 1u};
+      const CUresult r = enc(&tm.w[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<float*>(p.blob[q] + L.o_w), gdim,
+                             gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: weight tensor map failed (%d)", (int)r);
+    }
+    tm.c[q] = tm.x[q];                                  // placeholders when the direct epilogue runs
+    tm.r[q] = tm.x[q];
+    if (staged) {
+      const cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
+      const cuuint64_t gstr[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.Wo * p.Cout * 2, (cuuint64_t)p.Ho * p.Wo * p.Cout * 2};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)cg::TM_W, (cuuint32_t)cg::TM_H, 1u};
+      const cuuint32_t est[4] = {1u, 1u, 1u, 1u};
+      CUresult r = enc(&tm.c[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out[q], gdim, gstr, box, est,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: output tensor map failed (%d)", (int)r);
+      if (p.resid[q]) {
+        r = enc(&tm.r[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.resid[q]), gdim, gstr, box, est,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: residual tensor map failed (%d)", (int)r);
+      }
+    }
+  }
+  for (int q = p.n_prob; q < kMaxProb; ++q) { tm.x[q] = tm.x[0]; tm.w[q] = tm.w[0]; tm.c[q] = tm.c[0]; tm.r[q] = tm.r[0]; }
+  const int total = p.n_tiles * p.n_prob;
+  const int grid = total < 148 ? total : 148;
+  HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD>, K::SMEM));
+  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
+  count_launch();
+  HRF_CUDA(cudaGetLastError());
+  return HRF_OK;
+}
+
+}  // namespace hrf

@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "mixffn.cuh"
 #include "mixffn_tc.cuh"
+#include "tmap.cuh"
 #include "umma.cuh"
 
 namespace hrf {
@@ -450,22 +451,6 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
 
 
 // ---- host side --------------------------------------------------------------------------------
-// 3-D tiled tensor map over a [B][H][W][C] bf16 token tensor seen as (W*C/2 words, H, B)
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-static PFN_tmapEncodeTiled tmap_encoder() {
-  static PFN_tmapEncodeTiled fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess ||
-        qr != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<PFN_tmapEncodeTiled>(f);
-  }();
-  return fn;
-}
 // true when the token tensor can be described to the TMA unit this way
 static bool tmap_tokens_ok(const void* base, int W, int C) {
   return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 2 == 0 && ((size_t)W * C * 2) % 16 == 0;

@@ -40,7 +40,24 @@ class _Conv:
     broadcast-add and clamp passes cost 3-4x the convolution itself on the
     256-channel stem tensors (profiles/r01_v1_simt_launches.txt)."""
 
-    def __init__(self, conv, bn, relu, dtype, extra_bias=None, use_bias=True):
+    def __init__(self, conv, bn, relu, dtype, extra_bias=None, use_bias=True, engine=None):
+        # bf16 mode on the GPU: the library's warp-specialised TMA / tcgen05 implicit-GEMM kernel
+        # (csrc/conv_gemm_tc.cuh) when it covers the layer -- every stem / Bottleneck / 256-channel
+        # transition conv of the shipped configs; HRF_CONVGEMM=0 keeps cuDNN (A/B runs)
+        k = conv.kernel_size[0]
+        self.tc = (engine is not None and engine.ops is ops and dtype == torch.bfloat16 and
+                   conv.weight.is_cuda and os.environ.get('HRF_CONVGEMM', '1') != '0' and
+                   conv.groups == 1 and conv.kernel_size == (k, k) and conv.padding == (k // 2, k // 2) and
+                   conv.dilation == (1, 1) and conv.stride[0] == conv.stride[1] and
+                   ops.convgemm_supported(conv.in_channels, conv.out_channels, k, conv.stride[0]))
+        self.relu, self.cout = relu, conv.out_channels
+        if self.tc:
+            blob = ops.pack_convgemm(conv, bn, bn.eps if bn is not None else 1e-5, extra_bias)
+            if not use_bias:                        # bias-free branch: its shift rides on another conv's bias
+                npad = 32 if self.cout <= 32 else 64 if self.cout <= 64 else 128 if self.cout <= 128 else 256
+                blob[:npad] = 0
+            self.blob, self.ksize, self.stride1 = engine._blob(blob), k, conv.stride[0]
+            return
         self.w, b = _fold_conv_bn(conv, bn, dtype)
         if extra_bias is not None:
             b = b + extra_bias
@@ -61,6 +78,12 @@ class _Conv:
         self.b32 = b.float() if self.has_bias else None
 
     def __call__(self, x, residual=None):
+        if self.tc:
+            t = x.permute(0, 2, 3, 1)
+            r = residual.permute(0, 2, 3, 1) if residual is not None else None
+            y = ops.conv_gemm(t if t.is_contiguous() else t.contiguous(), self.blob.t, self.cout, self.ksize,
+                              self.stride1, self.relu, r if r is None or r.is_contiguous() else r.contiguous())
+            return y.permute(0, 3, 1, 2)
         y = self._run(x, residual)
         if y.shape[1] != self.cout:
             y = y[:, :self.cout].contiguous(memory_format=torch.channels_last)
@@ -88,11 +111,11 @@ class _Conv:
         return y.relu_() if self.relu else y
 
 
-def _seq(mods, dtype):
+def _seq(mods, dtype, engine=None):
     """nn.Sequential of [conv, bn, (relu)] -> _Conv"""
     mods = list(mods)
     relu = len(mods) > 2 and isinstance(mods[2], nn.ReLU)
-    return _Conv(mods[0], mods[1], relu, dtype)
+    return _Conv(mods[0], mods[1], relu, dtype, engine=engine)
 
 
 class _Bottleneck:
@@ -100,14 +123,17 @@ class _Bottleneck:
     (reference resnet.py:263-302).  The downsample branch runs bias-free and its
     folded BN shift moves into conv3's bias, so the add + ReLU fuse into conv3."""
 
-    def __init__(self, m, dtype):
-        self.c1 = _Conv(m.conv1, m.bn1, True, dtype)
-        self.c2 = _Conv(m.conv2, m.bn2, True, dtype)
+    def __init__(self, m, dtype, engine=None):
+        self.c1 = _Conv(m.conv1, m.bn1, True, dtype, engine=engine)
+        self.c2 = _Conv(m.conv2, m.bn2, True, dtype, engine=engine)
         self.down, extra = None, None
         if m.downsample is not None:
-            _, extra = _fold_conv_bn(m.downsample[0], m.downsample[1], dtype)
-            self.down = _Conv(m.downsample[0], m.downsample[1], False, dtype, use_bias=False)
-        self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra)   # ReLU after the add
+            _, extra = _fold_conv_bn(m.downsample[0], m.downsample[1], torch.float32)
+            self.down = _Conv(m.downsample[0], m.downsample[1], False, dtype, use_bias=False, engine=engine)
+        # ReLU after the add
+        self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra, engine=engine)
+        if not self.c3.tc and extra is not None:
+            self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra.to(dtype))
 
     def __call__(self, x):
         idt = x if self.down is None else self.down(x)
@@ -141,14 +167,14 @@ class BackboneEngine:
         self._host_blobs, self._blob_slots = [], []
         m, dt = module, self.dtype
 
-        self.stem = [self._stem_conv(m.conv1, m.bn1), _Conv(m.conv2, m.bn2, True, dt)] + \
-                    [_Bottleneck(b, dt) for b in m.layer1]
+        self.stem = [self._stem_conv(m.conv1, m.bn1), _Conv(m.conv2, m.bn2, True, dt, engine=self)] + \
+                    [_Bottleneck(b, dt, self) for b in m.layer1]
         self.stem_mod = [[self._stem_conv(m.conv_a[k], m.norm_a[k]),
-                          _Conv(m.conv_b[k], m.norm_b[k], True, dt)] +
-                         [_Bottleneck(b, dt) for b in m.layer_a[k]] for k in range(self.M)]
+                          _Conv(m.conv_b[k], m.norm_b[k], True, dt, engine=self)] +
+                         [_Bottleneck(b, dt, self) for b in m.layer_a[k]] for k in range(self.M)]
         # transition1[i][0]: bare conv on branch 0, full conv-bn-relu on branch 1
-        self.trans1 = [_Conv(m.transition1[0][0], None, False, dt)] + \
-                      [_seq(m.transition1[i][0], dt) for i in range(1, len(m.transition1))]
+        self.trans1 = [_Conv(m.transition1[0][0], None, False, dt, engine=self)] + \
+                      [_seq(m.transition1[i][0], dt, self) for i in range(1, len(m.transition1))]
         self.trans_cam = {2: self._transitions(m.transition2), 3: self._transitions(m.transition3)}
         letters = ['a', 'b', 'c'] + (['d'] if m.pre_neck_fusion else [])
         self.trans_mod = {l: [self._transitions(getattr(m, f'transition_{l}')[k])
@@ -213,7 +239,7 @@ class BackboneEngine:
                conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1) and
                conv.in_channels <= 72 and conv.in_channels % 2 == 0 and conv.out_channels % 2 == 0)
         if not own:
-            return _Conv(conv, bn, relu, self.dtype)
+            return _Conv(conv, bn, relu, self.dtype, engine=self)
         blob = self._blob(ops.pack_conv3x3(conv, bn, bn.eps))
         cout, stride = conv.out_channels, conv.stride[0]
         return lambda x_img: self._image(self.ops.conv3x3(self._tokens(x_img), blob.t, cout, stride, relu))
@@ -358,6 +384,57 @@ class BackboneEngine:
                 xs = res
         return (xs, nchw) if final_nchw else xs
 
+    def _conv_group(self, convs, imgs, residuals=None):
+        """One layer of the (1 + M) streams.  When every conv runs on the conv-GEMM kernel with
+        one layer shape, the streams share ONE launch (hrf_convgemm_grouped_fwd); else each
+        stream runs its own."""
+        c0 = convs[0]
+        same = (len(convs) > 1 and len(convs) <= 4 and all(isinstance(c, _Conv) and c.tc for c in convs) and
+                all((c.cout, c.ksize, c.stride1) == (c0.cout, c0.ksize, c0.stride1) for c in convs) and
+                all(tuple(i.shape) == tuple(imgs[0].shape) for i in imgs))
+        if not same:
+            return [c(i) if residuals is None else c(i, r) for c, i, r in
+                    zip(convs, imgs, residuals or [None] * len(convs))]
+        toks = [self._tokens(i) for i in imgs]
+        res = None if residuals is None else [self._tokens(r) for r in residuals]
+        outs = ops.conv_gemm_grouped(toks, [c.blob.t for c in convs], c0.cout, c0.ksize, c0.stride1,
+                                     [c.relu for c in convs], res)
+        return [self._image(o) for o in outs]
+
+    def _stems_lockstep(self, x, mods):
+        """The camera stem and the modality stems, layer by layer, with one grouped launch per
+        layer; returns (camera tokens per stage-2 branch, modality tokens [k][branch])."""
+        chains = [self.stem] + self.stem_mod
+        ys = self._par([lambda c=c, t=t: c[0](t) for c, t in zip(chains, [x] + list(mods))])
+        ys = self._conv_group([c[1] for c in chains], ys)
+        for j in range(2, len(chains[0])):
+            bs = [c[j] for c in chains]
+            idt = ys if bs[0].down is None else self._conv_group([b.down for b in bs], ys)
+            t = self._conv_group([b.c1 for b in bs], ys)
+            t = self._conv_group([b.c2 for b in bs], t)
+            ys = self._conv_group([b.c3 for b in bs], t, idt)
+        nb_a = len(self.trans1)
+        outs = [self._conv_group([self.trans1[i]] + [self.trans_mod['a'][k][i][0] for k in range(self.M)], ys)
+                for i in range(nb_a)]
+        cams = [self._tokens(outs[i][0]) for i in range(nb_a)]
+        pre_ms = [[self._tokens(outs[i][1 + k]) for i in range(nb_a)] for k in range(self.M)]
+        return cams, pre_ms
+
+    def _can_lockstep(self):
+        if not (self.ops is ops and self.precision == 'bf16' and self.M + 1 <= 4 and
+                os.environ.get('HRF_STEM_LOCKSTEP', '1') != '0'):
+            return False
+        chains = [self.stem] + self.stem_mod
+        if any(len(c) != len(chains[0]) for c in chains):
+            return False
+        for j in range(1, len(chains[0])):
+            layer = [c[j] for c in chains]
+            if j >= 2 and not all(isinstance(b, _Bottleneck) for b in layer):
+                return False
+        return all(tr is not None and len(tr) == 1 and isinstance(tr[0], _Conv)
+                   for k in range(self.M) for tr in self.trans_mod['a'][k]) and \
+            len(self.trans_mod['a'][0]) == len(self.trans1) if self.M else False
+
     def _apply_chain(self, chain, x_img):
         for c in chain:
             x_img = c(x_img)
@@ -430,8 +507,11 @@ class BackboneEngine:
                 return parts[0] if len(parts) == 1 else \
                     [torch.cat([q[i] for q in parts]) for i in range(nb_a)]
 
-            stems = self._par([cam_stream] + [lambda k=k: mod_stream(k) for k in range(M)])
-            cams, pre_ms = stems[0], stems[1:]
+            if self._can_lockstep() and ck == B:
+                cams, pre_ms = self._stems_lockstep(x, mods)
+            else:
+                stems = self._par([cam_stream] + [lambda k=k: mod_stream(k) for k in range(M)])
+                cams, pre_ms = stems[0], stems[1:]
             xs, firsts = self._fuse('a', [lambda i=i: cams[i] for i in range(nb_a)], None, pre_ms)
             tap('fusion_a', xs)
             res = self._par([lambda: self._run_stage(self.stage[2], xs)] +

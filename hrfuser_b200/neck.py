@@ -62,6 +62,7 @@ class HRFPN(nn.Module):
             for _ in range(num_outs))
         self.pooling = F.max_pool2d if pooling_type == 'MAX' else F.avg_pool2d
         self._blobs, self._blobs_ver = None, None
+        self._fpn_blobs, self._fpn_ver = None, None
 
     def init_weights(self):
         """Caffe2Xavier on every Conv2d (mmcv: kaiming_uniform, a=1, fan_in, bias 0)."""
@@ -74,17 +75,18 @@ class HRFPN(nn.Module):
     # ------------------------------------------------------------ packed weights
     def invalidate(self):
         self._blobs = None
+        self._fpn_blobs = None
 
     def train(self, mode=True):
         # an optimizer updates reduction_conv in place between two evaluations: never carry
         # packed weights across a train() phase (the backbone does the same with its engine)
-        self._blobs = None
+        self._blobs = self._fpn_blobs = None
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):
         # reached for every module of the tree when a PARENT (the detector, mmcv's
         # load_checkpoint) loads a checkpoint; Module.load_state_dict of a child is not
-        self._blobs = None
+        self._blobs = self._fpn_blobs = None
         return super()._load_from_state_dict(*a, **k)
 
     def _weights_version(self):
@@ -93,7 +95,7 @@ class HRFPN(nn.Module):
                 None if conv.bias is None else (conv.bias._version, conv.bias.data_ptr()))
 
     def _apply(self, fn, *a, **k):
-        self._blobs = None
+        self._blobs = self._fpn_blobs = None
         return super()._apply(fn, *a, **k)
 
     def _packed(self, device):
@@ -115,8 +117,9 @@ class HRFPN(nn.Module):
         return self._blobs
 
     # ------------------------------------------------------------------ forward
-    def reduce(self, inputs):
-        """`reduction_conv(cat(x0, up(x1), ...))` of hrfpn.py:79-86 -> fp32 NCHW"""
+    def reduce(self, inputs, as_tokens=False):
+        """`reduction_conv(cat(x0, up(x1), ...))` of hrfpn.py:79-86 -> fp32 NCHW (or, with
+        `as_tokens`, the kernels' own [B,H,W,C] tokens in the working precision)"""
         x0 = inputs[0]
         if not x0.is_cuda:
             raise _lib.HrfError('HRFPN: the eval forward runs on the hrfuser_b200 CUDA kernels only '
@@ -133,7 +136,25 @@ class HRFPN(nn.Module):
         ys = [ops.pointwise(ops.nchw_to_nhwc(t.contiguous(), dtype=dt), blob, self.out_channels)
               for t, blob in zip(inputs, blobs)]
         out = ops.fuse_sum(ys[0], ups=ys[1:], relu=False) if len(ys) > 1 else ys[0]
-        return ops.nhwc_to_nchw(out, dtype=torch.float32)
+        return out if as_tokens else ops.nhwc_to_nchw(out, dtype=torch.float32)
+
+    def _back_half_blobs(self, device):
+        """fpn_convs as `hrf_convgemm` blobs (bf16 mode), keyed like the reduction slices"""
+        ver = tuple((c.conv.weight._version, c.conv.weight.data_ptr(),
+                     None if c.conv.bias is None else c.conv.bias._version) for c in self.fpn_convs)
+        if self._fpn_blobs is None or self._fpn_blobs[0].device != device or self._fpn_ver != ver:
+            self._fpn_blobs = [ops.pack_convgemm(c.conv, None).to(device) for c in self.fpn_convs]
+            self._fpn_ver = ver
+        return self._fpn_blobs
+
+    def _tc_back_half(self, x0):
+        """True when pooling + the 3x3 convs run on the library's kernels: bf16 mode, channel
+        count covered by hrf_convgemm_fwd, map divisible by the pyramid's windows."""
+        oc = self.out_channels
+        return (self.precision == 'bf16' and all(c.conv.stride == (1, 1) for c in self.fpn_convs) and
+                ops.convgemm_supported(oc, oc, 3, 1) and oc % 8 == 0 and
+                x0.shape[2] % (1 << (self.num_outs - 1)) == 0 and x0.shape[3] % (1 << (self.num_outs - 1)) == 0 and
+                not any(getattr(c, 'activate', None) is not None for c in self.fpn_convs))
 
     def forward(self, inputs):
         assert len(inputs) == self.num_ins                      # hrfpn.py:78
@@ -143,6 +164,17 @@ class HRFPN(nn.Module):
             # statistics -- must build a graph, as the reference does)
             return self._forward_autograd(inputs)
         # fp32 mode: the cuDNN 3x3 convs must not drop to TF32 (3e-4 off; the engine does the same)
+        if inputs[0].is_cuda and self._tc_back_half(inputs[0]):
+            # bf16 mode: the whole neck on the library's kernels -- the reduced map stays in bf16
+            # tokens, the pyramid levels come from hrf_pool_fwd, the five 3x3 convs from the
+            # TMA / tcgen05 implicit-GEMM kernel (hrf_convgemm_fwd); fp32 NCHW only at the exit
+            with torch.no_grad():
+                tok = self.reduce(list(inputs), as_tokens=True)
+                blobs = self._back_half_blobs(tok.device)
+                mode = 'MAX' if self.pooling is F.max_pool2d else 'AVG'
+                levels = [tok] + [ops.pool_tokens(tok, 2 ** i, mode) for i in range(1, self.num_outs)]
+                return tuple(ops.nhwc_to_nchw(ops.conv_gemm(lv, blobs[i], self.out_channels, 3, 1, False),
+                                              dtype=torch.float32) for i, lv in enumerate(levels))
         with torch.no_grad(), torch.backends.cudnn.flags(enabled=True,
                                                          allow_tf32=self.precision != 'fp32'):
             out = self.reduce(list(inputs))

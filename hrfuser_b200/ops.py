@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnDesc, ConvDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, HRF_U8, InputDesc,
+from ._lib import (AttnDesc, ConvDesc, ConvGemmDesc, DwPwDesc, FfnDesc, FuseDesc, HRF_BF16, HRF_F32, HRF_U8, InputDesc,
                    PwDesc, StemDesc, check)
 
 _DT = {torch.float32: HRF_F32, torch.bfloat16: HRF_BF16}
@@ -159,6 +159,85 @@ def pack_conv3x3(conv, bn, bn_eps=1e-5):
     b = _host(conv.bias) if conv.bias is not None else None
     check(lib.hrf_conv3x3_pack(C.byref(d), _fp(w), _fp(b), _bn4(bn, keep), C.c_float(bn_eps), _fp(blob)))
     return blob
+
+
+def convgemm_supported(cin, cout, ksize, stride):
+    """True when hrf_convgemm_fwd covers a (cin -> cout, ksize, stride) convolution."""
+    lib = _lib.load()
+    d = ConvGemmDesc(1, 8, 16, cin, cout, ksize, stride, 0)
+    return lib.hrf_convgemm_supported(C.byref(d)) == 0
+
+
+def pack_convgemm(conv, bn, bn_eps=1e-5, extra_bias=None):
+    """Dense 1x1 / 3x3 conv + BN folded (+ an extra per-channel bias) -> blob of hrf_convgemm_fwd."""
+    lib = _lib.load()
+    cout, cin, k, _ = conv.weight.shape
+    assert conv.groups == 1 and conv.padding == (k // 2, k // 2) and conv.dilation == (1, 1)
+    d = ConvGemmDesc(1, 8, 16, cin, cout, k, conv.stride[0], 0)
+    n = lib.hrf_convgemm_blob_floats(C.byref(d))
+    if n == 0:
+        raise _lib.HrfError(f'convgemm: {k}x{k} conv {cin} -> {cout} stride {conv.stride[0]} is not covered')
+    blob = torch.empty(n, dtype=torch.float32)
+    keep = []
+    w = _host(conv.weight)
+    b = _host(conv.bias) if conv.bias is not None else None
+    eb = _host(extra_bias) if extra_bias is not None else None
+    check(lib.hrf_convgemm_pack(C.byref(d), _fp(w), _fp(b), _bn4(bn, keep), C.c_float(bn_eps), _fp(eb), _fp(blob)))
+    return blob
+
+
+def conv_gemm(x, blob, cout, ksize, stride=1, relu=False, residual=None):
+    """bf16 tokens [B,H,W,Cin] -> [B,ceil(H/s),ceil(W/s),cout]: conv + folded BN (+ residual) (+ ReLU)
+    on the warp-specialised TMA / tcgen05 implicit-GEMM kernel."""
+    lib = _lib.load()
+    _check_act(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError('conv_gemm runs in the bf16 mode only')
+    B, H, W, Cin = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = x.new_empty(B, Ho, Wo, cout)
+    if residual is not None:
+        if tuple(residual.shape) != tuple(out.shape) or residual.dtype != x.dtype or not residual.is_contiguous():
+            raise ValueError('conv_gemm: residual must be a contiguous tensor of the output shape')
+    d = ConvGemmDesc(B, H, W, Cin, cout, ksize, stride, int(relu))
+    no = B * Ho * Wo
+    with _timed('convgemm', C=Cin, launches=1,
+                bytes=float((B * H * W * Cin + no * cout * (2 if residual is not None else 1)) * 2),
+                flops=float(2 * no * ksize * ksize * Cin * cout)):
+        check(lib.hrf_convgemm_fwd(C.byref(d), x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                   blob.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def conv_gemm_grouped(xs, blobs, cout, ksize, stride=1, relu=False, residuals=None):
+    """`conv_gemm` of ONE layer shape on several tensors (the camera and modality streams), each
+    with its own weights, in one launch (hrf_convgemm_grouped_fwd)."""
+    lib = _lib.load()
+    n = len(xs)
+    for x in xs:
+        _check_act(x)
+        if x.dtype != torch.bfloat16 or tuple(x.shape) != tuple(xs[0].shape):
+            raise ValueError('conv_gemm_grouped: bf16 tensors of one shape')
+    B, H, W, Cin = xs[0].shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    outs = [x.new_empty(B, Ho, Wo, cout) for x in xs]
+    if residuals is not None:
+        for r in residuals:
+            if tuple(r.shape) != tuple(outs[0].shape) or r.dtype != torch.bfloat16 or not r.is_contiguous():
+                raise ValueError('conv_gemm_grouped: residuals must be contiguous tensors of the output shape')
+    mask = sum(1 << q for q, r in enumerate(relu) if r) if isinstance(relu, (list, tuple)) else \
+        ((1 << n) - 1 if relu else 0)
+    d = ConvGemmDesc(B, H, W, Cin, cout, ksize, stride, mask)
+    VP = C.c_void_p * n
+    no = B * Ho * Wo
+    with _timed('convgemm', C=Cin, launches=1,
+                bytes=float(n * (B * H * W * Cin + no * cout * (2 if residuals is not None else 1)) * 2),
+                flops=float(n * 2 * no * ksize * ksize * Cin * cout)):
+        check(lib.hrf_convgemm_grouped_fwd(
+            C.byref(d), n, VP(*[x.data_ptr() for x in xs]),
+            VP(*[r.data_ptr() for r in residuals]) if residuals is not None else None,
+            VP(*[b.data_ptr() for b in blobs]), VP(*[o.data_ptr() for o in outs]), _stream()))
+    return outs
 
 
 def pack_dwpw(conv_dw, bn_dw, conv_pw, bn_pw, bn_eps=1e-5):
@@ -366,6 +445,19 @@ def input_prologue(src, mean, std, to_rgb=False, size_divisor=32, pad_val=0.0, o
     with _timed('input_prologue', C=Cc, launches=1,
                 bytes=float(src.numel() * src.element_size() + out.numel() * 4), flops=float(2 * src.numel())):
         check(lib.hrf_input_prologue_fwd(C.byref(d), src.data_ptr(), m, s, out.data_ptr(), _stream()))
+    return out
+
+
+def pool_tokens(x, k, mode='AVG'):
+    """bf16 tokens [B,H,W,C] -> [B,H/k,W/k,C]: k x k pooling with stride k (HRFPN pyramid)."""
+    lib = _lib.load()
+    _check_act(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError('pool_tokens runs in the bf16 mode only')
+    B, H, W, Cc = x.shape
+    out = x.new_empty(B, H // k, W // k, Cc)
+    with _timed('pool', C=Cc, launches=1, bytes=float((x.numel() + out.numel()) * 2), flops=float(x.numel())):
+        check(lib.hrf_pool_fwd(B, H, W, Cc, k, int(mode == 'MAX'), x.data_ptr(), out.data_ptr(), _stream()))
     return out
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 6
+#define HRF_ABI_VERSION 7
 
 enum { HRF_F32 = 0, HRF_BF16 = 1, HRF_U8 = 2 /* hrf_input_prologue_fwd source only */ };
 enum {
@@ -171,6 +171,41 @@ int hrf_dwpw_pack(const HrfDwPwDesc* d, const float* wdw /*(Cin,1,3,3)*/,
 int hrf_dwpw_fwd(const HrfDwPwDesc* d, const void* x, const float* blob, void* out,
                  void* stream);
 
+/* Dense 1x1 / 3x3 convolution + folded BN (+ residual) (+ ReLU) on channels-last bf16 tokens:
+ * the stem conv2, the Bottlenecks (resnet.py:263-302: conv1 / conv2 / conv3 + identity or
+ * downsample, ReLU after the add), the 256-channel transitions (hrnet.py:419-463,
+ * hrfuser_hrformer_based.py:375-412) and the HRFPN 3x3 convs (necks/hrfpn.py:87-100) --
+ * SURVEY.md 8(f) rank 1 / 2.  One warp-specialised, TMA-fed tcgen05 implicit-GEMM kernel
+ * (csrc/conv_gemm_tc.cuh).  ksize 1 (pad 0, stride 1) or 3 (pad 1, stride 1 | 2);
+ * Cin a multiple of 64, Cout even and <= 256, dtype HRF_BF16. */
+typedef struct HrfConvGemmDesc {
+  int32_t B, H, W, Cin, Cout;   /* H, W: INPUT size; output is ceil(H/stride) x ceil(W/stride) */
+  int32_t ksize;
+  int32_t stride;
+  int32_t relu;                 /* applied after the residual add */
+} HrfConvGemmDesc;
+/* 0 when the kernel covers the problem (else HRF_EUNSUPPORTED: keep the layer on cuDNN) */
+int hrf_convgemm_supported(const HrfConvGemmDesc* d);
+size_t hrf_convgemm_blob_floats(const HrfConvGemmDesc* d);
+/* w: (Cout, Cin, k, k); bias may be NULL; bn = {weight,bias,mean,var} or NULL; extra_bias
+ * (Cout) may be NULL -- the folded shift of a bias-free downsample branch that is added to
+ * conv3's bias so that the add + ReLU fuse into conv3 */
+int hrf_convgemm_pack(const HrfConvGemmDesc* d, const float* w, const float* bias,
+                      const float* const bn[4], float bn_eps, const float* extra_bias,
+                      float* blob_out);
+/* x: [B][H][W][Cin] bf16 tokens; resid: [B][Ho][Wo][Cout] bf16 or NULL; out likewise
+ * (must not alias x).  All 16-byte aligned. */
+int hrf_convgemm_fwd(const HrfConvGemmDesc* d, const void* x, const void* resid,
+                     const float* blob, void* out, void* stream);
+/* The same layer shape on n (1..4) independent tensors, each with its own weights, in ONE
+ * launch: the camera stream and the modality streams of the backbone run identical stem /
+ * Bottleneck / transition layers (hrfuser_hrformer_based.py:533-543).  xs / outs / blobs:
+ * arrays of n device pointers; resids: array of n pointers or NULL.  d->relu is a bit mask
+ * here: bit q = ReLU on problem q. */
+int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs,
+                             const void* const* resids, const float* const* blobs,
+                             void* const* outs, void* stream);
+
 #define HRF_MAX_FUSE_TERMS 4
 typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_j same_j) */
   int32_t B, H, W, C;           /* output branch size */
@@ -287,6 +322,12 @@ typedef struct {
 } HrfInputDesc;
 int hrf_input_prologue_fwd(const HrfInputDesc* d, const void* src, const float* mean,
                            const float* std, float* dst, void* stream);
+
+/* k x k pooling with stride k of bf16 tokens [B][H][W][C] -> [B][H/k][W/k][C]: the HRFPN
+ * pyramid levels (necks/hrfpn.py:88-92, F.avg_pool2d / F.max_pool2d, kernel_size = stride =
+ * 2^i).  C a multiple of 8, H and W multiples of k. */
+int hrf_pool_fwd(int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, int32_t is_max,
+                 const void* x, void* out, void* stream);
 
 /* Layout converters at the boundary of the path. */
 int hrf_nchw_to_nhwc(int32_t B, int32_t C, int32_t H, int32_t W, int32_t src_dtype,

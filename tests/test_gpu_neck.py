@@ -37,7 +37,11 @@ def test_against_reference_golden(built_lib, name, mode):
     before = built_lib.hrf_launch_count()
     with torch.no_grad():
         got = net(xs)
-    assert built_lib.hrf_launch_count() - before == 4 + 4 + 1 + 1      # layouts, pw, fuse_sum, layout
+    if mode == 'bf16' and oc % 64 == 0:
+        # + 4 pooled levels, 5 conv-GEMM launches, 5 exit layouts: the whole neck on the library's kernels
+        assert built_lib.hrf_launch_count() - before == 4 + 4 + 1 + 4 + 5 + 5
+    else:
+        assert built_lib.hrf_launch_count() - before == 4 + 4 + 1 + 1      # layouts, pw, fuse_sum, layout
     assert isinstance(got, tuple) and len(got) == 5
     want = [torch.from_numpy(GOLD[f'{name}.out{i}']) for i in range(5)]
     assert all(g.dtype == torch.float32 for g in got)
@@ -112,3 +116,31 @@ def test_reduction_weights_repacked_after_an_optimizer_step(built_lib):
     assert float((a[0] - b[0]).abs().max()) > 1e-3
     neck.train()
     assert neck._blobs is None
+
+
+@pytest.mark.parametrize('pooling', ['AVG', 'MAX'])
+def test_whole_neck_bf16_on_library_kernels(built_lib, pooling):
+    """bf16 mode, 256 output channels: reduction, pooling pyramid (hrf_pool_fwd) and the five
+    3x3 convs (hrf_convgemm_fwd) all run on the library's kernels; against the oracle."""
+    import torch
+    from hrfuser_b200.neck import HRFPN
+    chans = [18, 36, 72, 144]
+    torch.manual_seed(7)
+    net = HRFPN(in_channels=chans, out_channels=256, pooling_type=pooling, precision='bf16').eval()
+    for p_ in net.parameters():
+        torch.nn.init.normal_(p_, std=0.05)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    xs = [torch.randn(2, c, 96 >> i, 160 >> i) for i, c in enumerate(chans)]
+    with torch.no_grad():
+        want = net._forward_autograd(xs)                  # the reference's formulation, fp32 CPU
+    net = net.cuda()
+    before = built_lib.hrf_launch_count()
+    with torch.no_grad():
+        got = net([x.cuda() for x in xs])
+    assert built_lib.hrf_launch_count() - before == 4 + 4 + 1 + 4 + 5 + 5
+    scale = float(want[0].pow(2).mean().sqrt())
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.dtype == torch.float32 and g.shape == w.shape
+        e = float((g.cpu() - w).pow(2).mean().sqrt()) / scale
+        assert e <= 2e-2, (i, e)
+    assert_parity(got[0], want[0], 'bf16', f'hrfpn bf16 {pooling} out0')

@@ -25,7 +25,8 @@ from hrfuser_b200.engine import BackboneEngine  # noqa: E402
 
 GRIDS = {'nus': [(96, 160), (48, 80), (24, 40), (12, 20)],
          'stf': [(96, 312), (48, 156), (24, 78), (12, 39)]}
-WIDTHS = [(18, 1), (36, 2), (72, 4), (144, 8)]
+WIDTHS = [(18, 1), (36, 2), (72, 4), (144, 8)]                  # HRFuser-T: head_dim 18
+WIDTHS_B = [(78, 2), (156, 4), (312, 8), (624, 16)]             # HRFuser-B: head_dim 39
 
 
 def stub():
@@ -57,7 +58,8 @@ def main():
     ap.add_argument('--wins', default='7', help='window sizes, e.g. 7,14')
     ap.add_argument('--out', default='')
     ap.add_argument('--kinds', default='lsa,mwca,mixffn', help='subset of lsa,mwca,mixffn')
-    ap.add_argument('--widths', default='18,36,72,144', help='channel widths to run')
+    ap.add_argument('--widths', default='', help='channel widths to run (default: all of the variant)')
+    ap.add_argument('--variant', default='t', choices=['t', 'b'], help='HRFuser-T (head_dim 18) or -B (39)')
     ap.add_argument('--mods', default='1,2,3', help='MWCA modality counts')
     a = ap.parse_args()
     dt = torch.bfloat16 if a.precision == 'bf16' else torch.float32
@@ -67,8 +69,8 @@ def main():
     B = a.batch
     for gname, win in [(g, int(w)) for w in a.wins.split(',') for g in a.grids.split(',')]:
         S4 = 4 * win * win                                   # QK^T + PV flops per token and channel
-        for (H, W), (C, heads) in zip(GRIDS[gname], WIDTHS):
-            if str(C) not in a.widths.split(','):
+        for (H, W), (C, heads) in zip(GRIDS[gname], WIDTHS if a.variant == 't' else WIDTHS_B):
+            if a.widths and str(C) not in a.widths.split(','):
                 continue
             n_tok = B * H * W
             nbytes = n_tok * C * dt.itemsize
