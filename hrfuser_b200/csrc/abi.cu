@@ -14,6 +14,7 @@
 #include "mixffn.cuh"
 #include "umma_selftest.cuh"
 #include "window_attn_tc.cuh"
+#include "window_attn_v3.cuh"
 #include "mixffn_tc.cuh"
 #include "mixffn_v2.cuh"
 #include "conv3x3_tc.cuh"
@@ -184,6 +185,11 @@ static int check_attn(const HrfAttnDesc* d) {
   return HRF_OK;
 }
 
+// HRF_ATTN_V3=0 keeps the second-generation kernel for C = 18 (A/B runs)
+static bool attn_v3_enabled() {
+  const char* e = std::getenv("HRF_ATTN_V3");
+  return !(e && e[0] == '0');
+}
 // which implementation serves a window-attention problem
 enum { PATH_TC = 0, PATH_FUSED_SIMT = 1, PATH_GENERIC = 2 };
 static int attn_path(const HrfAttnDesc* d) {
@@ -271,6 +277,65 @@ int hrf_attn_pack(const HrfAttnDesc* d, const float* ln_q_w, const float* ln_q_b
       }
     for (int c = 0; c < C; ++c) bias[3 * NQ + c] = bo ? bo[c] : 0.f;
   }
+  // ---- third-generation sections (window_attn_v3.cuh): LayerNorm affine, softmax scale, log2 e
+  // and the output projection folded into the operand tiles -------------------------------------
+  if (L.o_v3 >= 0) {
+    using A = AttnV3;
+    static_assert(A::SEC_SELF + A::SEC_CROSS == 4784 + 5808, "AttnLayout::o_v3 size");
+    constexpr int Cc = A::C;
+    const double l2e = 1.4426950408889634, sc = (double)scale * l2e;
+    // rows of the three projections over the K index: 0..17 channel (x gamma), 18 bias, 19 beta row
+    double rq[Cc][20], rk[Cc][20], rv[Cc + 1][20];
+    for (int n = 0; n < Cc; ++n) {
+      double bq_b = 0, bk_b = 0;
+      for (int k = 0; k < Cc; ++k) {
+        rq[n][k] = (double)ln_q_w[k] * wq[(size_t)n * Cc + k] * sc;
+        rk[n][k] = (double)ln_kv_w[k] * wk[(size_t)n * Cc + k];
+        bq_b += (double)ln_q_b[k] * wq[(size_t)n * Cc + k];
+        bk_b += (double)ln_kv_b[k] * wk[(size_t)n * Cc + k];
+      }
+      rq[n][18] = (bq ? bq[n] : 0.0) * sc; rq[n][19] = bq_b * sc;
+      rk[n][18] = bk ? bk[n] : 0.0;        rk[n][19] = bk_b;
+      // V' = LN(z) (Wo Wv)^T: one head, so the output projection commutes with the softmax average
+      double b18 = bo ? bo[n] : 0.0, b19 = 0;
+      for (int k = 0; k < Cc; ++k) rv[n][k] = 0;
+      for (int dd = 0; dd < Cc; ++dd) {
+        const double wod = wo[(size_t)n * Cc + dd];
+        double vb = 0;
+        for (int k = 0; k < Cc; ++k) {
+          rv[n][k] += wod * wv[(size_t)dd * Cc + k] * ln_kv_w[k];
+          vb += (double)ln_kv_b[k] * wv[(size_t)dd * Cc + k];
+        }
+        b18 += wod * (bv ? bv[dd] : 0.0);
+        b19 += wod * vb;
+      }
+      rv[n][18] = b18; rv[n][19] = b19;
+    }
+    for (int k = 0; k < 20; ++k) rv[Cc][k] = k == 18 ? 1.0 : 0.0;     // the constant-1 column of V'
+    unsigned char* base = reinterpret_cast<unsigned char*>(blob + L.o_v3);
+    uint16_t* w_self = reinterpret_cast<uint16_t*>(base);
+    uint16_t* w_q = reinterpret_cast<uint16_t*>(base + A::SEC_SELF);
+    uint16_t* w_kv = reinterpret_cast<uint16_t*>(base + A::SEC_SELF + A::W_Q_B);
+    for (int k = 0; k < 20; ++k) {
+      for (int n = 0; n < Cc; ++n) {
+        w_self[umma::tile_off(n, k, 64) / 2] = f32_to_bf16((float)rq[n][k]);
+        w_self[umma::tile_off(18 + n, k, 64) / 2] = f32_to_bf16((float)rk[n][k]);
+        w_q[umma::tile_off(n, k, 32) / 2] = f32_to_bf16((float)rq[n][k]);
+        w_kv[umma::tile_off(n, k, 48) / 2] = f32_to_bf16((float)rk[n][k]);
+      }
+      for (int n = 0; n <= Cc; ++n) {
+        w_self[umma::tile_off(36 + n, k, 64) / 2] = f32_to_bf16((float)rv[n][k]);
+        w_kv[umma::tile_off(18 + n, k, 48) / 2] = f32_to_bf16((float)rv[n][k]);
+      }
+    }
+    float* t_self = reinterpret_cast<float*>(base + A::W_SELF_B);
+    float* t_cross = reinterpret_cast<float*>(base + A::SEC_SELF + A::W_Q_B + A::W_KV_B);
+    for (int t = 0; t < 169; ++t) {
+      const float v = rpb_table ? (float)(rpb_table[(size_t)t] * l2e) : 0.f;      // heads == 1
+      t_self[t] = v;
+      t_cross[t] = v;
+    }
+  }
   return HRF_OK;
 }
 
@@ -298,6 +363,20 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
   HRF_REQUIRE(d->n_kv == 0 || kv, HRF_EINVAL, "attn_fwd: kv list missing");
   cudaStream_t st = (cudaStream_t)stream;
   const int passes = d->n_kv > 0 ? d->n_kv : 1;
+  if (attn_path(d) == PATH_TC && AttnV3::applies(d->C, d->heads, d->win) && passes <= AttnV3::MAXMOD && attn_v3_enabled()) {
+    // C = 18: one launch for the block, every modality inside it
+    AttnV3Params p{};
+    p.x = x; p.out = out; p.n_mod = passes;
+    p.v3_off = AttnLayout(d->C, d->heads, d->win).o_v3;
+    for (int k = 0; k < passes; ++k) {
+      p.z[k] = d->n_kv > 0 ? kv[k] : x;
+      p.blob[k] = blobs[k];
+      HRF_REQUIRE(p.z[k] && p.blob[k], HRF_EINVAL, "attn_fwd: null kv/blob %d", k);
+      HRF_REQUIRE(p.z[k] != out, HRF_EINVAL, "attn_fwd: out must not alias kv %d", k);
+    }
+    p.B = d->B; p.H = d->H; p.W = d->W; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
+    return launch_window_attn_v3(p, d->n_kv > 0, st);
+  }
   for (int k = 0; k < passes; ++k) {
     AttnParams p;
     p.xq = x;

@@ -21,6 +21,9 @@ struct AttnLayout {
   // tiles in the chunk-major layout of umma.cuh (offsets in floats)
   int tc_HDP, tc_KC, tc_NQ, tc_NOUT;
   int o_tc_bias, o_tc_wq, o_tc_wk, o_tc_wv, o_tc_wo;
+  // third-generation kernel (C = 18, one head, window 7: window_attn_v3.cuh): self section
+  // (4784 bytes) then cross section (5808 bytes); -1 when the shape is not covered
+  int o_v3;
   int total;
   // shared-memory strides
   int ldx, ldq;
@@ -41,6 +44,11 @@ struct AttnLayout {
     o_tc_wk = o; o += tc_NQ * tc_KC / 2;
     o_tc_wv = o; o += tc_NQ * tc_KC / 2;
     o_tc_wo = o; o += tc_NOUT * tc_NQ / 2;                   // bf16 [KO/8][NOUT][8], KO == NQ
+    o_v3 = -1;
+    if (C == 18 && heads == 1 && win == 7) {
+      o = round_up(o, 4);
+      o_v3 = o; o += (4784 + 5808) / 4;
+    }
     total = o;
     ldx = stride4odd(Cp);
     ldq = stride4odd(KO);

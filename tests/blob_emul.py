@@ -54,6 +54,10 @@ class AttnLayout:
         names['tc_wo'] = o
         o += KC * NQ // 2
         self.tc = dict(HDP=HDP, KC=KC, NQ=NQ, NOUT=KC)
+        if C == 18 and heads == 1 and win == 7:        # third-generation sections (window_attn_v3.cuh)
+            o = _ru(o, 4)
+            names['v3'] = o
+            o += (4784 + 5808) // 4
         self.total = o
         self.o = names
 

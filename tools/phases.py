@@ -23,6 +23,8 @@ from hrfuser_b200 import _lib, ops  # noqa: E402
 from microbench import GRIDS, WIDTHS, stub  # noqa: E402
 
 NAMES = {
+    'attn_v3': ['LN + prefetch', 'sync', 'proj issue', 'proj wait', 'proj epilogue', 'sync+S issue', 'S wait',
+                'softmax', 'sync+PV issue', 'PV wait', 'out epilogue', '-', '-', '-'],
     'ffn': ['LN prologue', 'sync', 'fc1 issue', 'fc1 wait', 'epilogue 1', 'sync', 'dw conv', 'sync',
             'fc2 issue', 'fc2 wait', 'epilogue 2', '-', '-', '-'],
     'ffn_v2': ['TMA wait + LN', 'sync', 'fc1 issue', 'fc1 wait', 'epilogue 1', 'sync', 'dw conv', 'sync',
@@ -65,7 +67,7 @@ elif a.kind == 'lsa':
     e._upload()
     blobs = [s.t for s in pk['attn']]
     fn = lambda: ops.window_attention(x, None, blobs, heads)
-    names = NAMES['attn']
+    names = NAMES['attn_v3' if Cc == 18 and os.environ.get('HRF_ATTN_V3', '1') != '0' else 'attn']
 else:
     blk, _ = make_block('mwca', Cc, heads, M=2)
     pk = e._fusion_block(blk)
@@ -73,7 +75,7 @@ else:
     blobs = [s.t for s in pk['attn']]
     zs = [torch.randn_like(x) for _ in range(2)]
     fn = lambda: ops.window_attention(x, zs, blobs, heads)
-    names = NAMES['attn']
+    names = NAMES['attn_v3' if Cc == 18 and os.environ.get('HRF_ATTN_V3', '1') != '0' else 'attn']
 for it in range(3):
     fn()
 torch.cuda.synchronize()
