@@ -30,6 +30,18 @@
 //               64 -> 256 + residual layer at 97 us against 36 us for cuDNN.  Other widths (the
 //               18 / 36-channel transitions) store straight from registers.
 // No CTA-wide barrier inside the tile loop.
+//
+// Row-reuse mode (RR: 3x3, stride 1, weights that fit shared memory -- Bottleneck conv2, the
+// 256 -> 18 transition).  The plain implicit GEMM reads every activation tile nine times and
+// the layer's weights once per tile from L2, and those layers ran at L2 -> SM bandwidth, 5x
+// off their MMA time (profiles/r02_timeline.txt: 187 us for the 256 -> 18 transition).  Here
+//   * the weights of the layer [taps][Cin/64][NPAD x 64] are loaded ONCE per CTA (and again when
+//     its tile range crosses into the next problem of a grouped launch);
+//   * a K step is (dx, 64-channel chunk): ONE box of TM_H + 2 = 10 rows x 16 tokens feeds the
+//     three vertical taps -- the A tile of tap dy starts dy rows (dy x 2 KB, a whole number of
+//     swizzle atoms) into the box -- so a tile costs 3 x 10 / 8 = 3.75 activation tile loads
+//     per channel chunk instead of 9;
+//   * CTAs walk contiguous tile ranges (neighbouring tiles share halo rows in L2).
 #pragma once
 #include <cuda.h>
 
@@ -62,6 +74,7 @@ struct ConvGemmParams {
   int n_prob;
   int B, Ho, Wo, Cin, Cout, taps, relu, stride;   // relu: bit q = ReLU on problem q
   int tiles_w, tiles_h, n_tiles;    // n_tiles: per problem
+  int n_stages, tiles_per_cta;      // RR mode: ring depth (runtime), contiguous tile range per CTA
   FastDiv d_tiles_prob, d_tiles_img, d_tiles_w;
 };
 struct ConvGemmMaps {               // 4 x 4 tensor maps = 2 KB of kernel parameters
@@ -71,6 +84,8 @@ struct ConvGemmMaps {               // 4 x 4 tensor maps = 2 KB of kernel parame
 namespace cg {
 constexpr int TM_H = 8, TM_W = 16;                    // the 128-token M tile
 constexpr int A_BYTES = 128 * 128;                    // 128 tokens x 64 channels bf16
+constexpr int A_RR_BYTES = (TM_H + 2) * TM_W * 128;   // row-reuse box: 10 rows x 16 tokens x 64 channels
+constexpr int MAXST = 8;
 constexpr int NT = 192;
 
 // shared-memory descriptor of a 128-byte-swizzled K-major operand tile (rows of 128 bytes, 8-row
@@ -112,15 +127,16 @@ struct ConvGemmCfg {
   static_assert(SMEM + kMaxProb * NPAD * 4 + 1024 <= 227 * 1024, "dynamic + static shared memory");
 };
 
-template <int NPAD>
+template <int NPAD, bool RR>
 __global__ void __launch_bounds__(cg::NT, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ ConvGemmMaps tm) {
   using namespace umma;
   using K = ConvGemmCfg<NPAD>;
-  constexpr int STAGES = K::STAGES;
+  const int STAGES = RR ? p.n_stages : K::STAGES;
+  constexpr int STAGE_B = RR ? cg::A_RR_BYTES : K::STAGE;
   extern __shared__ unsigned char sm_raw[];
   constexpr int NSLOT = K::NSLOT > 0 ? K::NSLOT : 1, NSUB = K::NSUB;
-  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full[cg::MAXST], empty[cg::MAXST], acc_full[2], acc_empty[2], w_full;
   __shared__ __align__(8) uint64_t c_full[NSLOT], c_empty[NSLOT];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[kMaxProb * NPAD];
@@ -129,7 +145,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   // operand tiles need 1024-byte alignment (128-byte swizzle atom = 8 rows x 128 bytes)
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
-  const int kc = p.Cin / 64, n_k = p.taps * kc;
+  const int kc = p.Cin / 64, n_k = RR ? 3 * kc : p.taps * kc;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -144,6 +160,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       mbar_init(&c_full[c], 1);
       mbar_init(&c_empty[c], 1);
     }
+    mbar_init(&w_full, 1);
     fence_mbar_init();
     for (int q = 0; q < p.n_prob; ++q) {
       tma_prefetch_desc(&tm.x[q]);
@@ -153,7 +170,12 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   }
   const int total_tiles = p.n_tiles * p.n_prob;
   const bool staged = NSUB > 0 && p.Cout == NPAD;    // whole 64-channel sub-tiles: the C-slot epilogue
-  unsigned char* c_slots = sm + STAGES * K::STAGE;
+  unsigned char* c_slots = sm + STAGES * STAGE_B;
+  unsigned char* w_res = c_slots + K::C_BYTES;       // RR: the layer's weights, resident
+  // tiles of this CTA: strided over the grid, or (RR) one contiguous range
+  const int t_begin = RR ? blockIdx.x * p.tiles_per_cta : blockIdx.x;
+  const int t_step = RR ? 1 : gridDim.x;
+  const int t_end = RR ? (t_begin + p.tiles_per_cta < total_tiles ? t_begin + p.tiles_per_cta : total_tiles) : total_tiles;
   for (int e = tid; e < p.n_prob * NPAD; e += cg::NT) s_bias[e] = __ldg(p.blob[e / NPAD] + (e % NPAD));
   if (warp == 1) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   tc_fence_before();
@@ -165,22 +187,41 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   if (warp == 0) {
     // ===== TMA producer ===========================================================================
     if (elect_one()) {
-      int it = 0, cit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0, cit = 0, cur_pr = -1;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         int pr, tl, b, rem, ty, tx;
         p.d_tiles_prob.divmod(tile, pr, tl);
         p.d_tiles_img.divmod(tl, b, rem);
         p.d_tiles_w.divmod(rem, ty, tx);
         const int h0 = ty * cg::TM_H, w0 = tx * cg::TM_W;
+        if constexpr (RR) {
+          if (pr != cur_pr) {
+            // (re)load the resident weights; the MMAs of the previous problem's tiles must have
+            // read the old ones: the commit behind the last stage issued covers all of them
+            if (it > 0) mbar_wait(&empty[(it - 1) % STAGES], ((it - 1) / STAGES) & 1, 270);
+            mbar_expect_tx(&w_full, (uint32_t)(9 * kc * K::B_BYTES));
+            for (int t = 0; t < 9 * kc; ++t)
+              tma_load_3d(w_res + t * K::B_BYTES, &tm.w[pr], (t % kc) * 64, 0, t / kc, &w_full);
+            cur_pr = pr;
+          }
+          for (int k = 0; k < n_k; ++k, ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1, 200 + s);
+            const int dxi = k / kc, c0 = (k - dxi * kc) * 64;
+            mbar_expect_tx(&full[s], cg::A_RR_BYTES);
+            cg::tma_load_4d(sm + s * STAGE_B, &tm.x[pr], c0, w0 + dxi - 1, h0 - 1, b, &full[s]);
+          }
+        } else {
         for (int k = 0; k < n_k; ++k, ++it) {
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1, 200 + s);
           const int tap = k / kc, c0 = (k - tap * kc) * 64;
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
-          unsigned char* a = sm + s * K::STAGE;
+          unsigned char* a = sm + s * STAGE_B;
           mbar_expect_tx(&full[s], cg::A_BYTES + K::B_BYTES);
           cg::tma_load_4d(a, &tm.x[pr], c0, w0 * p.stride + dx, h0 * p.stride + dy, b, &full[s]);
           tma_load_3d(a + cg::A_BYTES, &tm.w[pr], c0, 0, tap, &full[s]);
+        }
         }
         if (NSUB > 0 && staged && p.resid[0] != nullptr) {
           // residual sub-tiles of THIS tile into the C slots (after its K steps: the slots are
@@ -197,9 +238,17 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer ==============================================================================
     constexpr uint32_t idesc = idesc_bf16(128, NPAD, false, false);
-    int it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    int it = 0, tcount = 0, cur_pr = -1, wcount = 0;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       const int acc = tcount & 1;
+      if constexpr (RR) {
+        const int pr = p.d_tiles_prob.div(tile);
+        if (pr != cur_pr) {                           // this problem's weights have landed
+          mbar_wait(&w_full, wcount & 1, 280);
+          ++wcount;
+          cur_pr = pr;
+        }
+      }
       if (tcount >= 2) mbar_wait(&acc_empty[acc], ((tcount >> 1) - 1) & 1, 210 + acc);
       tc_fence_after();
       for (int k = 0; k < n_k; ++k, ++it) {
@@ -207,10 +256,23 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         mbar_wait(&full[s], (it / STAGES) & 1, 220 + s);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a = smem_u32(sm + s * K::STAGE), bq = a + cg::A_BYTES;
+          const uint32_t a = smem_u32(sm + s * STAGE_B);
+          if constexpr (RR) {
+            const int dxi = k / kc, c = k - dxi * kc;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16(tmem + acc * NPAD, cg::desc_sw128(a, ks), cg::desc_sw128(bq, ks), idesc, (k | ks) != 0);
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t bq = smem_u32(w_res) + (uint32_t)(((dy * 3 + dxi) * kc + c) * K::B_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16(tmem + acc * NPAD, cg::desc_sw128(a + dy * (cg::TM_W * 128), ks), cg::desc_sw128(bq, ks), idesc,
+                         (k | dy | ks) != 0);
+            }
+          } else {
+            const uint32_t bq = a + cg::A_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16(tmem + acc * NPAD, cg::desc_sw128(a, ks), cg::desc_sw128(bq, ks), idesc, (k | ks) != 0);
+          }
           mma_commit(&empty[s]);                      // frees the stage when these MMAs have read it
           if (k == n_k - 1) mma_commit(&acc_full[acc]);
         }
@@ -223,7 +285,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     const int row = q * 32 + lane;                    // token of the tile
     const int hh = row >> 4, ww = row & 15;
     int tcount = 0, cit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       const int acc = tcount & 1;
       int pr, tl, b, rem, ty, tx;
       p.d_tiles_prob.divmod(tile, pr, tl);
@@ -361,9 +423,20 @@ static bool conv_gemm_supported(int Cin, int Cout, int k, int stride, int H, int
          Cout <= 256 && H > 0 && W > 0 && (k == 3 || stride == 1);
 }
 
+// HRF_CONV_RR=0 keeps the plain implicit GEMM for the 3x3 stride-1 layers (A/B runs)
+static bool conv_rr_enabled() {
+  const char* e = std::getenv("HRF_CONV_RR");
+  return !(e && e[0] == '0');
+}
+
 template <int NPAD>
 static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, int Wi, int stride, cudaStream_t stream) {
   using K = ConvGemmCfg<NPAD>;
+  // row-reuse mode: 3x3, stride 1, the layer's weights + at least two ring stages fit
+  const int wres = 9 * (p.Cin / 64) * K::B_BYTES;
+  const int room = 218 * 1024 - K::C_BYTES - wres;
+  const bool rr = p.taps == 9 && stride == 1 && room >= 2 * cg::A_RR_BYTES && conv_rr_enabled();
+  p.n_stages = rr ? (room / cg::A_RR_BYTES > cg::MAXST ? cg::MAXST : room / cg::A_RR_BYTES) : K::STAGES;
   PFN_tmapEncodeTiled enc = tmap_encoder();
   HRF_REQUIRE(enc != nullptr, HRF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   ConvGemmMaps tm;
@@ -374,7 +447,7 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, i
       // every second token / row (element strides), so its coordinates stay in INPUT units
       const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)p.B};
       const cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)Wi * p.Cin * 2, (cuuint64_t)Hi * Wi * p.Cin * 2};
-      const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)(cg::TM_H * stride), 1u};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)((rr ? cg::TM_H + 2 : cg::TM_H) * stride), 1u};
       const cuuint32_t est[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
       const CUresult r = enc(&tm.x[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[q]), gdim, gstr, box,
                              est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -413,9 +486,20 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, i
   }
   for (int q = p.n_prob; q < kMaxProb; ++q) { tm.x[q] = tm.x[0]; tm.w[q] = tm.w[0]; tm.c[q] = tm.c[0]; tm.r[q] = tm.r[0]; }
   const int total = p.n_tiles * p.n_prob;
-  const int grid = total < 148 ? total : 148;
-  HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD>, K::SMEM));
-  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
+  int grid = total < 148 ? total : 148;
+  if (rr) {
+    p.tiles_per_cta = ceil_div(total, grid);
+    grid = ceil_div(total, p.tiles_per_cta);
+    const size_t smem = (size_t)p.n_stages * cg::A_RR_BYTES + K::C_BYTES + wres + 1024;
+    HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, true>, smem));
+    HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, true>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+    count_launch();
+    HRF_CUDA(cudaGetLastError());
+    return HRF_OK;
+  }
+  p.tiles_per_cta = 0;
+  HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, false>, K::SMEM));
+  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, false>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;

@@ -33,22 +33,17 @@ LAYERS = [  # name, Cin, Cout, k, stride, relu, residual, (H, W) of the INPUT
 
 
 def timed(fn, iters):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        fn()
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    """graph-timed (tools/microbench.py): the ctypes launch path (~20 us) stays out of the number"""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    from microbench import timed as graph_timed
+    return graph_timed(lambda i: fn(), 1, iters)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--iters', type=int, default=30)
+    ap.add_argument('--group', type=int, default=3, help='streams per grouped launch (1 + M)')
     a = ap.parse_args()
     pk = peaks()
     B = a.batch
@@ -64,18 +59,25 @@ def main():
         rs = [torch.randn(B, Ho, Wo, cout, device='cuda').to(torch.bfloat16) for _ in range(n_sets)] if resid else None
         i = [0]
 
+        G = a.group
+
         def ours():
             j = i[0] = (i[0] + 1) % n_sets
-            return ops.conv_gemm(xs[j], blob, cout, k, stride, relu, rs[j] if resid else None)
+            if G == 1:
+                return ops.conv_gemm(xs[j], blob, cout, k, stride, relu, rs[j] if resid else None)
+            sel = [(j + q) % n_sets for q in range(G)]
+            return ops.conv_gemm_grouped([xs[q] for q in sel], [blob] * G, cout, k, stride, [relu] * G,
+                                         [rs[q] for q in sel] if resid else None)
         cv = _Conv(conv.cuda(), bn.cuda(), relu, torch.bfloat16)
 
         def cudnn():
-            j = i[0] = (i[0] + 1) % n_sets
-            return cv(xs[j].permute(0, 3, 1, 2), rs[j].permute(0, 3, 1, 2) if resid else None)
-        t_o, t_c = timed(ours, a.iters), timed(cudnn, a.iters)
+            for _ in range(G):
+                j = i[0] = (i[0] + 1) % n_sets
+                cv(xs[j].permute(0, 3, 1, 2), rs[j].permute(0, 3, 1, 2) if resid else None)
+        t_o, t_c = timed(ours, a.iters) / G, timed(cudnn, a.iters) / G
         byts = (B * H * W * cin + B * Ho * Wo * cout * (2 if resid else 1)) * 2
         flops = 2 * B * Ho * Wo * k * k * cin * cout
-        print(json.dumps(dict(layer=name, B=B, H=H, W=W, cin=cin, cout=cout, k=k, stride=stride,
+        print(json.dumps(dict(layer=name, group=G, B=B, H=H, W=W, cin=cin, cout=cout, k=k, stride=stride,
                               convgemm_ms=round(t_o, 5), cudnn_ms=round(t_c, 5),
                               GBps=round(byts / t_o / 1e6, 1), frac_hbm=round(byts / t_o / 1e6 / pk['hbm_gbs'], 4),
                               TFLOPs=round(flops / t_o / 1e9, 2),
