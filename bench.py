@@ -485,7 +485,7 @@ def run_train(args):
     optimizer step over B frames per GPU.  `torch_syncbn` times the same module with
     torch.nn.SyncBatchNorm in place of the hrf_bn_* kernels."""
     import torch.nn as nn
-    from hrfuser_b200 import HRFuserHRFormerBased, WORKLOADS, backbone_cfg, bn_train, ops
+    from hrfuser_b200 import HRFuserHRFormerBased, WORKLOADS, backbone_cfg, bn_train, ops, train
     from hrfuser_b200 import dist as hdist
     from hrfuser_b200.utils import randomize_parameters, synthetic_inputs
     rank, world, local = hdist.init_from_env()
@@ -506,19 +506,15 @@ def run_train(args):
                 if isinstance(m, bn_train.HrfSyncBatchNorm):
                     m.__class__ = nn.SyncBatchNorm
         net = net.to(dev).train()
-        if world > 1:
+        if world > 1 and torch_bn:
             net = nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
         return net, torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9)
 
     x, mods = synthetic_inputs(B, H, Wd, mod_ch, seed=10 + rank)
     x, mods = x.to(dev), [m.to(dev) for m in mods]
+    loss_fn = lambda out: sum((o * o).mean() for o in out)
 
-    def timed(net, opt):
-        def step():
-            opt.zero_grad(set_to_none=True)
-            out = net(x, mods)
-            sum((o * o).mean() for o in out).backward()
-            opt.step()
+    def time_steps(step):
         for _ in range(Wm):
             step()
         torch.cuda.synchronize()
@@ -533,27 +529,52 @@ def run_train(args):
         hdist.barrier()
         return hdist.max_over_ranks(e0.elapsed_time(e1), dev), ops.launch_count() - n0
 
+    def eager(net, opt, manual_exchange):
+        params = [p for p in net.parameters() if p.requires_grad]
+        group = bn_train.sync_group(None)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss_fn(net(x, mods)).backward()
+            if manual_exchange:
+                train.exchange_gradients(params, group, world)
+            opt.step()
+        return time_steps(step)
+
     sampler = ClockSampler(local).start() if rank == 0 else None
     net, opt = build(False)
-    ms, launches = timed(net, opt)
+    ms_eager, launches_eager = eager(net, opt, True)       # the same step, launched op by op
+    n0 = ops.launch_count()
+    gstep = train.GraphedTrainStep(net, opt, x, mods, loss_fn)
+    launches = (ops.launch_count() - n0) // 4              # 3 warm-up steps + the capture
+    ms, _ = time_steps(gstep)
+    loss = float(gstep.loss)
     clocks = sampler.stop() if sampler else None
-    del net, opt
+    del net, opt, gstep
     torch.cuda.empty_cache()
     net, opt = build(True)
-    ms_t, _ = timed(net, opt)
+    ms_t, _ = eager(net, opt, False)
     if rank == 0:
         print(json.dumps({
             'metric': 'hrfuser_b_syncbn_train_frames_per_s', 'value': world * B * K / (ms / 1e3),
             'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic', 'gpu_launches': launches,
-            'config': {'workload': args.workload, 'mode': 'train (forward + backward + SGD step)',
+            'data': 'synthetic', 'gpu_launches': launches * K, 'hrf_kernel_launches_per_step': launches,
+            'loss_last_step': loss,
+            'config': {'workload': args.workload,
+                       'mode': 'train (forward + backward + gradient exchange + SGD step) replayed as ONE CUDA graph '
+                               '(hrfuser_b200.train.GraphedTrainStep)',
                        'frames_per_gpu_per_step': B, 'input': f'{H}x{Wd}', 'norm': 'SyncBN',
-                       'parallelism': f'DDP x{world}: SyncBN statistics all-reduce (one fp64 all-reduce of 2C+1 '
-                                      'values per BN and pass) + gradient all-reduce, NCCL',
+                       'parallelism': f'data parallel x{world}: SyncBN statistics all-reduce (one fp64 all-reduce of '
+                                      '2C+1 values per BN and pass) + ONE flat-bucket gradient all-reduce, NCCL, '
+                                      'all captured in the graph',
                        'weights': 'random-init (seeded)'},
+            'eager': {'ms_per_step': ms_eager / K, 'frames_per_s': world * B * K / (ms_eager / 1e3),
+                      'hrf_kernel_launches_per_step': launches_eager // K,
+                      'what': 'the same step launched op by op from Python (no graph)'},
             'torch_syncbn': {'ms_per_step': ms_t / K, 'frames_per_s': world * B * K / (ms_t / 1e3),
-                             'what': 'same module and step with torch.nn.SyncBatchNorm'},
+                             'what': 'same module and step with torch.nn.SyncBatchNorm (+ DistributedDataParallel '
+                                     'when N > 1), eager'},
             'clocks': clocks,
         }))
     hdist.barrier()

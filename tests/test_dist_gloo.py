@@ -87,3 +87,37 @@ def test_numa_binding_helper_never_raises_and_formats_ranges():
     assert isinstance(msg, str) and msg
     if msg.startswith('unbound'):
         assert os.sched_getaffinity(0) == before
+
+
+def _grad_worker(rank, world, port, q):
+    """flat-bucket gradient exchange of the graphed training step (train.exchange_gradients)"""
+    from hrfuser_b200 import train
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    hdist.init_from_env('gloo')
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)),
+          torch.nn.Parameter(torch.zeros(2, 2))]
+    ps[0].grad = torch.full((3, 4), float(rank + 1))
+    ps[2].grad = torch.arange(4.).view(2, 2) * (rank + 1)          # ps[1] receives no gradient
+    n = train.exchange_gradients(ps, dist.group.WORLD, world)
+    ok = (n == 16 and ps[1].grad is None and torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and
+          torch.allclose(ps[2].grad, torch.arange(4.).view(2, 2) * 1.5))
+    hdist.barrier()
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok
