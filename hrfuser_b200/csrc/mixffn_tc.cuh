@@ -549,7 +549,7 @@ static bool ffn_tc_supported(const FfnParams& p) {
                                  p.C == 78 || p.C == 156);                               // HRFuser-B
 }
 // chunk groups (CTAs per tile) of the split variants; 0: the CTA finishes the block
-static int ffn_tc_groups(int C) { return C == 72 || C == 78 ? 2 : C == 144 || C == 156 ? 8 : 0; }
+static int ffn_tc_groups(int C) { return C == 72 || C == 78 ? 2 : C == 144 || C == 156 ? 8 : 0; }   // upper bound (workspace size)
 static size_t ffn_tc_workspace_bytes(int B, int H, int W, int C, int hidden) {
   if (hidden != 4 * C) return 0;
   return (size_t)ffn_tc_groups(C) * B * H * W * C * sizeof(float);
@@ -592,8 +592,13 @@ static int launch_mixffn_tc(const FfnParams& p, cudaStream_t stream) {
     case 36: return launch_ffn_tc_c<36, 2>(p, stream);
     case 72: return launch_ffn_tc_c<72, 2>(p, stream);
     case 144: return launch_ffn_tc_c<144, 1>(p, stream);
-    case 78: return launch_ffn_tc_c<78, 2>(p, stream);
-    case 156: return launch_ffn_tc_c<156, 1>(p, stream);
+    case 78:
+      // HRF_B78_SPLIT=1: the split variant (two CTAs per tile + fp32 workspace), for A/B runs
+      if (b78_split()) return launch_ffn_tc_c<78, 2>(p, stream);
+      return launch_ffn_tc_c<78, 4>(p, stream);
+    case 156:
+      if (b78_split()) return launch_ffn_tc_c<156, 1>(p, stream);
+      return launch_ffn_tc_c<156, 2>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_tc: C=%d", p.C);
 }

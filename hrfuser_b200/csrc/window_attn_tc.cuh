@@ -806,6 +806,12 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* ws, int n
   }
 }
 
+// HRF_B78_SPLIT=1: C = 78 on the split variants (several CTAs per tile + fp32 workspace), A/B runs
+static bool b78_split() {
+  const char* e = std::getenv("HRF_B78_SPLIT");
+  return e && e[0] == '1';
+}
+
 template <int C, int HEADS, int HG>
 static int launch_attn_tc_ch(AttnParams p, cudaStream_t stream) {
   constexpr int NG = HEADS / HG;
@@ -869,7 +875,9 @@ static int launch_window_attn_tc(const AttnParams& p, cudaStream_t stream) {
     case 36: return launch_attn_tc_ch<36, 2, 2>(p, stream);
     case 72: return launch_attn_tc_ch<72, 4, 2>(p, stream);
     case 144: return launch_attn_tc_ch<144, 8, 2>(p, stream);
-    case 78: return launch_attn_tc_ch<78, 2, 1>(p, stream);     // head_dim 39 -> padded to 48
+    case 78:                                                     // head_dim 39 -> padded to 48
+      if (b78_split()) return launch_attn_tc_ch<78, 2, 1>(p, stream);
+      return launch_attn_tc_ch<78, 2, 2>(p, stream);
     case 156: return launch_attn_tc_ch<156, 4, 1>(p, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "attn_tc: C=%d", p.C);
