@@ -505,6 +505,8 @@ def run_train(args):
             for m in net.modules():
                 if isinstance(m, bn_train.HrfSyncBatchNorm):
                     m.__class__ = nn.SyncBatchNorm
+                elif isinstance(m, bn_train.HrfLayerNorm):
+                    m.__class__ = nn.LayerNorm
         net = net.to(dev).train()
         if world > 1 and torch_bn:
             net = nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
@@ -573,7 +575,7 @@ def run_train(args):
                       'hrf_kernel_launches_per_step': launches_eager // K,
                       'what': 'the same step launched op by op from Python (no graph)'},
             'torch_syncbn': {'ms_per_step': ms_t / K, 'frames_per_s': world * B * K / (ms_t / 1e3),
-                             'what': 'same module and step with torch.nn.SyncBatchNorm (+ DistributedDataParallel '
+                             'what': 'same module and step with torch.nn.SyncBatchNorm / nn.LayerNorm (+ DistributedDataParallel '
                                      'when N > 1), eager'},
             'clocks': clocks,
         }))

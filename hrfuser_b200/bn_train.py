@@ -97,3 +97,33 @@ def sync_group(process_group=None):
         return None
     group = process_group if process_group is not None else dist.group.WORLD
     return group if dist.get_world_size(group) > 1 else None
+
+
+class _LayerNormTrainFn(torch.autograd.Function):
+    """y = LayerNorm(x) over the last axis on hrf_ln_fwd / hrf_ln_bwd (csrc/ln_train.cuh)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = x.contiguous()
+        y, mean, rstd = ops.ln_fwd(x, weight, bias, eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = ops.ln_bwd(x, dy.contiguous(), mean, rstd, weight, want_dx=ctx.needs_input_grad[0])
+        return dx, dw if ctx.needs_input_grad[1] else None, db if ctx.needs_input_grad[2] else None, None
+
+
+class HrfLayerNorm(nn.LayerNorm):
+    """`nn.LayerNorm` over the channel axis whose CUDA fp32 forward / backward under autograd run
+    on the hrf_ln_* kernels (the training path; the inference engine folds LayerNorm into the
+    attention / MixFFN kernels and never calls this).  Same parameters and state_dict keys."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and len(self.normalized_shape) == 1 and
+                self.elementwise_affine and self.bias is not None and self.normalized_shape[0] <= 1024 and
+                torch.is_grad_enabled()):
+            return _LayerNormTrainFn.apply(x, self.weight, self.bias, self.eps)
+        return super().forward(x)

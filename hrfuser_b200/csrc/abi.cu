@@ -19,6 +19,7 @@
 #include "mixffn_v2.cuh"
 #include "conv3x3_tc.cuh"
 #include "conv_gemm_tc.cuh"
+#include "ln_train.cuh"
 #include "pool.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
@@ -813,6 +814,25 @@ int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const fl
     return launch_bn_reduce<float, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
   return launch_bn_reduce<__nv_bfloat16, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
 }
+// ------------------------------------------------------------------ train-mode LayerNorm
+size_t hrf_ln_bwd_workspace_floats(int32_t rows, int32_t C) {
+  return rows > 0 && C > 0 ? ln_bwd_workspace_floats(rows, C) : 0;
+}
+int hrf_ln_fwd(int32_t rows, int32_t C, float eps, const float* x, const float* gamma, const float* beta,
+               float* y, float* mean, float* rstd, void* stream) {
+  HRF_REQUIRE(rows > 0 && C > 0 && C <= 1024, HRF_EUNSUPPORTED, "ln_fwd: rows=%d C=%d (C <= 1024)", rows, C);
+  HRF_REQUIRE(x && gamma && beta && y && mean && rstd, HRF_EINVAL, "ln_fwd: null pointer");
+  return launch_ln_fwd(x, gamma, beta, y, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+}
+int hrf_ln_bwd(int32_t rows, int32_t C, const float* x, const float* dy, const float* mean, const float* rstd,
+               const float* gamma, float* dx, float* dgamma, float* dbeta, float* workspace,
+               size_t workspace_floats, void* stream) {
+  HRF_REQUIRE(rows > 0 && C > 0 && C <= 1024, HRF_EUNSUPPORTED, "ln_bwd: rows=%d C=%d (C <= 1024)", rows, C);
+  HRF_REQUIRE(x && dy && mean && rstd && gamma && dgamma && dbeta && workspace, HRF_EINVAL, "ln_bwd: null pointer");
+  HRF_REQUIRE(workspace_floats >= ln_bwd_workspace_floats(rows, C), HRF_EINVAL, "ln_bwd: workspace too small");
+  return launch_ln_bwd(x, dy, mean, rstd, gamma, dx, workspace, dgamma, dbeta, rows, C, (cudaStream_t)stream);
+}
+
 int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a, const float* b,
                   const float* c0, int32_t relu, void* out, void* stream) {
   if (int rc = bn_check(d)) return rc;

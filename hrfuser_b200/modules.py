@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .bn_train import HrfBatchNorm2d, HrfSyncBatchNorm
+from .bn_train import HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm
 from .window_maps import relative_position_index, window_geometry
 
 
@@ -34,7 +34,7 @@ def make_norm(cfg, channels):
     elif kind == 'SyncBN':
         m = HrfSyncBatchNorm(channels, **cfg)
     elif kind == 'LN':
-        m = nn.LayerNorm(channels, **cfg)
+        m = HrfLayerNorm(channels, **cfg)
     else:
         raise KeyError(f'unsupported norm type {kind!r}')
     for p in m.parameters():

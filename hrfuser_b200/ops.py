@@ -527,6 +527,37 @@ def _like_x(dy, x):
         raise ValueError('dy must match x (shape, dtype, contiguous)')
 
 
+def ln_fwd(x, weight, bias, eps):
+    """Train-mode LayerNorm over the last axis of a contiguous fp32 CUDA tensor -> (y, mean, rstd)."""
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    with _timed('ln_fwd', C=Cc, bytes=2 * x.numel() * 4, flops=0.0):
+        check(lib.hrf_ln_fwd(rows, Cc, eps, x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                             mean.data_ptr(), rstd.data_ptr(), _stream()))
+    return y, mean, rstd
+
+
+def ln_bwd(x, dy, mean, rstd, weight, want_dx=True):
+    """-> (dx | None, dweight, dbias) of `ln_fwd`."""
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    db = torch.empty_like(dw)
+    n_ws = lib.hrf_ln_bwd_workspace_floats(rows, Cc)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
+    with _timed('ln_bwd', C=Cc, bytes=3 * x.numel() * 4, flops=0.0):
+        check(lib.hrf_ln_bwd(rows, Cc, x.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                             weight.data_ptr(), dx.data_ptr() if want_dx else None, dw.data_ptr(), db.data_ptr(),
+                             ws.data_ptr(), n_ws, _stream()))
+    return dx, dw, db
+
+
 def bn_stats(x):
     """x (B, C, *) contiguous -> fp64 [2C + 1]: per-channel sum(x) | sum(x^2) | element count.
     The SyncBN message: additive across ranks."""

@@ -288,6 +288,22 @@ int hrf_bn_bwd_dx(const HrfBnDesc* d, const void* x, const void* dy, const doubl
 int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a,
                   const float* b, const float* c0, int32_t relu, void* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Train-mode LayerNorm over the channel axis of fp32 token tensors [rows][C]
+ * (nn.LayerNorm(C, eps) of hrformer.py:345-371 / hrfuser_hrformer_based.py:262-313 in the
+ * training configs).  C <= 1024.
+ *   hrf_ln_fwd: y = (x - mean) * rstd * gamma + beta; saves mean / rstd (fp32 [rows]).
+ *   hrf_ln_bwd: dx (may be NULL), dgamma, dbeta (fp32 [C]) from x, dy and the saved statistics;
+ *               deterministic two-stage reduction through `workspace`
+ *               (>= hrf_ln_bwd_workspace_floats(rows, C) floats).
+ * ---------------------------------------------------------------------- */
+size_t hrf_ln_bwd_workspace_floats(int32_t rows, int32_t C);
+int hrf_ln_fwd(int32_t rows, int32_t C, float eps, const float* x, const float* gamma,
+               const float* beta, float* y, float* mean, float* rstd, void* stream);
+int hrf_ln_bwd(int32_t rows, int32_t C, const float* x, const float* dy, const float* mean,
+               const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
+               float* workspace, size_t workspace_floats, void* stream);
+
 /* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
  * through the same descriptor helpers the fused kernels use.  B is [N][K]
  * (b_mn_major = 0, K-major operand) or [K][N] (b_mn_major = 1, MN-major operand).

@@ -319,6 +319,8 @@ def test_gpu_backbone_train_step_matches_torch_batchnorm(built_lib):
         if isinstance(m, bn_train.HrfSyncBatchNorm):
             m.__class__ = nn.BatchNorm2d          # single process: SyncBN == BN
             n_bn += 1
+        elif isinstance(m, bn_train.HrfLayerNorm):
+            m.__class__ = nn.LayerNorm            # ... and torch's LayerNorm
     assert n_bn > 50
     ref64 = copy.deepcopy(ref).double()
     x, mods = synthetic_inputs(4, 128, 128, (3, 3), seed=1)
