@@ -20,6 +20,7 @@
 #include "conv3x3_tc.cuh"
 #include "conv_gemm_tc.cuh"
 #include "ln_train.cuh"
+#include "attn_train.cuh"
 #include "pool.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
@@ -814,6 +815,40 @@ int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const fl
     return launch_bn_reduce<float, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
   return launch_bn_reduce<__nv_bfloat16, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
 }
+// ------------------------------------------------------------------ training-mode attention core
+static int attn_core_check(int nWin, int N, int C, int heads) {
+  HRF_REQUIRE(nWin > 0 && N > 0 && C > 0 && heads > 0 && C % heads == 0, HRF_EINVAL, "attn_core_train: dimensions");
+  HRF_REQUIRE(N <= kAtMaxN && C / heads <= kAtMaxHd, HRF_EUNSUPPORTED,
+              "attn_core_train: N=%d (<= %d) head_dim=%d (<= %d)", N, kAtMaxN, C / heads, kAtMaxHd);
+  return HRF_OK;
+}
+int hrf_attn_core_train_fwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, float scale, const float* q,
+                            const float* k, const float* v, const float* table, const int32_t* rpi, float* o,
+                            float* P, void* stream) {
+  if (int rc = attn_core_check(nWin, N, C, heads)) return rc;
+  HRF_REQUIRE(q && k && v && o && P && ((table == nullptr) == (rpi == nullptr)), HRF_EINVAL, "attn_core_train_fwd: pointers");
+  AttnCoreTrain p{q, k, v, table, rpi, o, P, nWin, N, C, heads, C / heads, scale};
+  return launch_attn_core_train_fwd(p, (cudaStream_t)stream);
+}
+size_t hrf_attn_core_train_ws_floats(int32_t nWin, int32_t N, int32_t heads) {
+  if (nWin <= 0 || N <= 0 || heads <= 0) return 0;
+  return ((size_t)attn_core_chunks(nWin, heads) + 1) * heads * N * N;      // per-CTA partials + their sum
+}
+int hrf_attn_core_train_bwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, float scale, const float* q,
+                            const float* k, const float* v, const float* P, const float* dout, float* dq,
+                            float* dk, float* dv, const int32_t* rpi, int32_t T, float* dtable, float* workspace,
+                            size_t workspace_floats, void* stream) {
+  if (int rc = attn_core_check(nWin, N, C, heads)) return rc;
+  HRF_REQUIRE(q && k && v && P && dout && dq && dk && dv, HRF_EINVAL, "attn_core_train_bwd: null pointer");
+  if (dtable) {
+    HRF_REQUIRE(rpi && workspace && T > 0, HRF_EINVAL, "attn_core_train_bwd: dtable needs rpi, T and a workspace");
+    HRF_REQUIRE(workspace_floats >= hrf_attn_core_train_ws_floats(nWin, N, heads), HRF_EINVAL,
+                "attn_core_train_bwd: workspace too small");
+  }
+  AttnCoreTrainBwd p{q, k, v, P, dout, dq, dk, dv, dtable ? workspace : nullptr, nWin, N, C, heads, C / heads, 0, scale};
+  return launch_attn_core_train_bwd(p, rpi, T, dtable, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ train-mode LayerNorm
 size_t hrf_ln_bwd_workspace_floats(int32_t rows, int32_t C) {
   return rows > 0 && C > 0 ? ln_bwd_workspace_floats(rows, C) : 0;

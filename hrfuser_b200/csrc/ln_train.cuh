@@ -124,12 +124,16 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __restrict__ partial, int n_part, int C,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp per output element: lanes stride over the CTA partials, fixed-order shuffle sum
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= 2 * C) return;
   float a = 0.f;
-  for (int p = 0; p < n_part; ++p) a += partial[(size_t)p * 2 * C + e];
-  if (e < C) dgamma[e] = a;
-  else dbeta[e - C] = a;
+  for (int p = lane; p < n_part; p += 32) a += partial[(size_t)p * 2 * C + e];
+  a = warp_sum(a);
+  if (lane == 0) {
+    if (e < C) dgamma[e] = a;
+    else dbeta[e - C] = a;
+  }
 }
 
 static int ln_grid(int rows) {
@@ -155,7 +159,7 @@ static int launch_ln_bwd_v(const float* x, const float* dy, const float* mean, c
   ln_bwd_kernel<VPT><<<grid, kLnThreads, smem, st>>>(x, dy, mean, rstd, gamma, dx, partial, rows, C);
   count_launch();
   HRF_CUDA(cudaGetLastError());
-  ln_bwd_finalize_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(partial, grid, C, dgamma, dbeta);
+  ln_bwd_finalize_kernel<<<ceil_div(2 * C * 32, 256), 256, 0, st>>>(partial, grid, C, dgamma, dbeta);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .bn_train import HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm
 from .window_maps import relative_position_index, window_geometry
 
@@ -78,8 +79,32 @@ def _image(x, H, W):
 # ----------------------------------------------------------------------------
 # window attention
 # ----------------------------------------------------------------------------
+class _AttnCoreTrainFn(torch.autograd.Function):
+    """softmax(scale q k^T + rel-pos bias) v per (window, head) on hrf_attn_core_train_fwd / _bwd
+    (csrc/attn_train.cuh): q / k / v [nWin, N, C] with heads along C, as the Linear layers emit."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, table, rpi, heads, scale):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, P = ops.attn_core_train_fwd(q, k, v, heads, scale, table, rpi)
+        ctx.save_for_backward(q, k, v, P, rpi)
+        ctx.heads, ctx.scale = heads, scale
+        ctx.T = table.shape[0] if table is not None else 0
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, P, rpi = ctx.saved_tensors
+        want_table = ctx.T > 0 and ctx.needs_input_grad[3]
+        dq, dk, dv, dtable = ops.attn_core_train_bwd(q, k, v, P, do.contiguous(), ctx.heads, ctx.scale,
+                                                     rpi if want_table else None, ctx.T)
+        return dq, dk, dv, dtable, None, None, None
+
+
 class _WindowAttnBase(nn.Module):
     """Shared pieces of WindowMSA / WindowMCA: rpb table + index, softmax core."""
+
+    use_kernels = True      # False: the torch formulation everywhere (bench.py's torch arm, A/B runs)
 
     def _init_common(self, dim, heads, window, with_rpe):
         self.num_heads = heads
@@ -95,6 +120,15 @@ class _WindowAttnBase(nn.Module):
     def _core(self, q, k, v, mask):
         nWin, N, C = q.shape
         h = self.num_heads
+        if (self.use_kernels and q.is_cuda and q.dtype == torch.float32 and mask is None and torch.is_grad_enabled() and
+                not (self.training and self.attn_drop.p > 0) and ops.attn_core_train_supported(N, C // h)):
+            # training path on the GPU: the whole core (and its backward) is one kernel per pass
+            if self.with_rpe and getattr(self, '_rpi32', None) is None or \
+                    self.with_rpe and self._rpi32.device != q.device:
+                self._rpi32 = self.relative_position_index.reshape(-1).to(device=q.device, dtype=torch.int32)
+            o = _AttnCoreTrainFn.apply(q, k, v, self.relative_position_bias_table if self.with_rpe else None,
+                                       self._rpi32 if self.with_rpe else None, h, self.scale)
+            return self.proj_drop(self.out_proj(o))
         split = lambda t: t.view(nWin, N, h, C // h).transpose(1, 2)
         logits = (split(q) * self.scale) @ split(k).transpose(-1, -2)
         if self.with_rpe:

@@ -527,6 +527,45 @@ def _like_x(dy, x):
         raise ValueError('dy must match x (shape, dtype, contiguous)')
 
 
+def attn_core_train_supported(N, hd):
+    return N <= 64 and hd <= 64
+
+
+def attn_core_train_fwd(q, k, v, heads, scale, table=None, rpi=None):
+    """softmax(scale q k^T + table[rpi]) v per (window, head); q / k / v: contiguous fp32 CUDA
+    [nWin, N, C] -> (o [nWin, N, C], P [nWin, heads, N, N])."""
+    lib = _lib.load()
+    nWin, N, Cc = q.shape
+    o = torch.empty_like(q)
+    P = torch.empty(nWin, heads, N, N, dtype=torch.float32, device=q.device)
+    with _timed('attn_core_train_fwd', C=Cc, bytes=4 * q.numel() * 4, flops=4.0 * nWin * N * N * Cc):
+        check(lib.hrf_attn_core_train_fwd(nWin, N, Cc, heads, scale, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                          table.data_ptr() if table is not None else None,
+                                          rpi.data_ptr() if table is not None else None,
+                                          o.data_ptr(), P.data_ptr(), _stream()))
+    return o, P
+
+
+def attn_core_train_bwd(q, k, v, P, dout, heads, scale, rpi=None, T=0):
+    """-> (dq, dk, dv, dtable [T, heads] | None)"""
+    lib = _lib.load()
+    nWin, N, Cc = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    dtable = ws = None
+    n_ws = 0
+    if rpi is not None:
+        dtable = torch.empty(T, heads, dtype=torch.float32, device=q.device)
+        n_ws = lib.hrf_attn_core_train_ws_floats(nWin, N, heads)
+        ws = torch.empty(n_ws, dtype=torch.float32, device=q.device)
+    with _timed('attn_core_train_bwd', C=Cc, bytes=8 * q.numel() * 4, flops=10.0 * nWin * N * N * Cc):
+        check(lib.hrf_attn_core_train_bwd(nWin, N, Cc, heads, scale, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                          P.data_ptr(), dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                          rpi.data_ptr() if rpi is not None else None, T,
+                                          dtable.data_ptr() if dtable is not None else None,
+                                          ws.data_ptr() if ws is not None else None, n_ws, _stream()))
+    return dq, dk, dv, dtable
+
+
 def ln_fwd(x, weight, bias, eps):
     """Train-mode LayerNorm over the last axis of a contiguous fp32 CUDA tensor -> (y, mean, rstd)."""
     lib = _lib.load()

@@ -304,6 +304,27 @@ int hrf_ln_bwd(int32_t rows, int32_t C, const float* x, const float* dy, const f
                const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
                float* workspace, size_t workspace_floats, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Training-mode window-attention core, fp32, forward and backward: the part of WindowMSA /
+ * WindowMCA between the q / k / v projections and the output projection
+ * (hrformer.py:110-131, hrfuser_hrformer_based.py:127-151):
+ *     P = softmax(scale * Q K^T + table[rpi]),   O = P V       per (window, head)
+ * q / k / v / o / their gradients: [nWin][N][C] tokens, head h in columns h*hd..(h+1)*hd
+ * (C = heads * hd; N = Wh*Ww <= 64, hd <= 64).  table: [T][heads] relative-position bias
+ * table with its [N*N] int32 index `rpi`, or both NULL.  P ([nWin][heads][N][N]) is saved by
+ * the forward for the backward.  dtable ([T][heads]) is summed in fixed order through
+ * `workspace` (>= hrf_attn_core_train_ws_floats floats); pass dtable = NULL to skip it.
+ * ---------------------------------------------------------------------- */
+int hrf_attn_core_train_fwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, float scale,
+                            const float* q, const float* k, const float* v, const float* table,
+                            const int32_t* rpi, float* o, float* P, void* stream);
+size_t hrf_attn_core_train_ws_floats(int32_t nWin, int32_t N, int32_t heads);
+int hrf_attn_core_train_bwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, float scale,
+                            const float* q, const float* k, const float* v, const float* P,
+                            const float* dout, float* dq, float* dk, float* dv,
+                            const int32_t* rpi, int32_t T, float* dtable, float* workspace,
+                            size_t workspace_floats, void* stream);
+
 /* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
  * through the same descriptor helpers the fused kernels use.  B is [N][K]
  * (b_mn_major = 0, K-major operand) or [K][N] (b_mn_major = 1, MN-major operand).

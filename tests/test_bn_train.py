@@ -321,6 +321,8 @@ def test_gpu_backbone_train_step_matches_torch_batchnorm(built_lib):
             n_bn += 1
         elif isinstance(m, bn_train.HrfLayerNorm):
             m.__class__ = nn.LayerNorm            # ... and torch's LayerNorm
+        elif hasattr(m, 'use_kernels'):
+            m.use_kernels = False                 # ... and torch's attention core
     assert n_bn > 50
     ref64 = copy.deepcopy(ref).double()
     x, mods = synthetic_inputs(4, 128, 128, (3, 3), seed=1)
