@@ -555,10 +555,10 @@ def run_train(args):
     del net, opt, gstep
     torch.cuda.empty_cache()
     from hrfuser_b200 import modules as hmod
-    hmod._WindowAttnBase.use_kernels = False               # the torch arm: torch ops only
+    hmod._WindowAttnBase.use_kernels = bn_train.HrfDepthwiseConv2d.use_kernels = False   # the torch arm: torch ops only
     net, opt = build(True)
     ms_t, _ = eager(net, opt, False)
-    hmod._WindowAttnBase.use_kernels = True
+    hmod._WindowAttnBase.use_kernels = bn_train.HrfDepthwiseConv2d.use_kernels = True
     if rank == 0:
         print(json.dumps({
             'metric': 'hrfuser_b_syncbn_train_frames_per_s', 'value': world * B * K / (ms / 1e3),
@@ -578,7 +578,7 @@ def run_train(args):
                       'hrf_kernel_launches_per_step': launches_eager // K,
                       'what': 'the same step launched op by op from Python (no graph)'},
             'torch_syncbn': {'ms_per_step': ms_t / K, 'frames_per_s': world * B * K / (ms_t / 1e3),
-                             'what': 'same module and step with torch.nn.SyncBatchNorm / nn.LayerNorm / torch attention core (+ DistributedDataParallel '
+                             'what': 'same module and step with torch.nn.SyncBatchNorm / nn.LayerNorm / torch attention core and depthwise convs (+ DistributedDataParallel '
                                      'when N > 1), eager'},
             'clocks': clocks,
         }))

@@ -127,3 +127,42 @@ class HrfLayerNorm(nn.LayerNorm):
                 torch.is_grad_enabled()):
             return _LayerNormTrainFn.apply(x, self.weight, self.bias, self.eps)
         return super().forward(x)
+
+
+class _DepthwiseConvTrainFn(torch.autograd.Function):
+    """depthwise 3x3 conv (pad 1, stride 1 | 2) on hrf_dwconv_train_* (csrc/dwconv_train.cuh)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        return ops.dwconv_train_fwd(x, weight, bias, stride)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = ops.dwconv_train_bwd(x, g.contiguous(), weight, ctx.stride, want_dx=ctx.needs_input_grad[0],
+                                          want_dw=ctx.needs_input_grad[1],
+                                          want_dbias=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw if ctx.needs_input_grad[1] else None, db, None
+
+
+class HrfDepthwiseConv2d(nn.Conv2d):
+    """`nn.Conv2d(C, C, 3, stride, 1, groups=C)` whose CUDA fp32 forward / backward under autograd
+    run on the hrf_dwconv_train_* kernels; anything else (CPU, other dtypes, no-grad) is torch's."""
+
+    use_kernels = True
+
+    def forward(self, x):
+        if (self.use_kernels and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and
+                x.dim() == 4 and self.weight.is_contiguous()):
+            return _DepthwiseConvTrainFn.apply(x, self.weight, self.bias, self.stride[0])
+        return super().forward(x)
+
+
+def make_conv(cin, cout, k, stride=1, padding=0, groups=1, bias=True):
+    """nn.Conv2d, or its depthwise-3x3 subclass on the library's training kernels"""
+    if groups == cin == cout and k == 3 and padding == 1 and stride in (1, 2):
+        return HrfDepthwiseConv2d(cin, cout, 3, stride, 1, groups=groups, bias=bias)
+    return nn.Conv2d(cin, cout, k, stride, padding, groups=groups, bias=bias)

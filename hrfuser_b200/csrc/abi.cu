@@ -21,6 +21,7 @@
 #include "conv_gemm_tc.cuh"
 #include "ln_train.cuh"
 #include "attn_train.cuh"
+#include "dwconv_train.cuh"
 #include "pool.cuh"
 #include "stem_conv_tc.cuh"
 #include "generic.cuh"
@@ -847,6 +848,52 @@ int hrf_attn_core_train_bwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, f
   }
   AttnCoreTrainBwd p{q, k, v, P, dout, dq, dk, dv, dtable ? workspace : nullptr, nWin, N, C, heads, C / heads, 0, scale};
   return launch_attn_core_train_bwd(p, rpi, T, dtable, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ training-mode depthwise conv
+static int dw_train_check(int B, int C, int H, int W, int stride) {
+  HRF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, HRF_EINVAL, "dwconv_train: dimensions");
+  HRF_REQUIRE(stride == 1 || stride == 2, HRF_EUNSUPPORTED, "dwconv_train: stride %d", stride);
+  HRF_REQUIRE((long long)B * C * H * ((W + 3) / 4) < (1ll << 31), HRF_EUNSUPPORTED, "dwconv_train: tensor too large");
+  return HRF_OK;
+}
+static DwTrainParams dw_train_params(int B, int C, int H, int W, int stride) {
+  DwTrainParams p{};
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+  return p;
+}
+size_t hrf_dwconv_train_ws_floats(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (stride != 1 && stride != 2)) return 0;
+  return dw_train_ws_floats(B, C, (H - 1) / stride + 1, (W - 1) / stride + 1);
+}
+int hrf_dwconv_train_fwd(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* x, const float* w,
+                         const float* bias, float* y, void* stream) {
+  if (int rc = dw_train_check(B, C, H, W, stride)) return rc;
+  HRF_REQUIRE(x && w && y, HRF_EINVAL, "dwconv_train_fwd: null pointer");
+  DwTrainParams p = dw_train_params(B, C, H, W, stride);
+  p.x = x; p.w = w; p.bias = bias; p.out = y;
+  return stride == 1 ? launch_dw_train<1>(0, p, nullptr, nullptr, (cudaStream_t)stream)
+                     : launch_dw_train<2>(0, p, nullptr, nullptr, (cudaStream_t)stream);
+}
+int hrf_dwconv_train_dgrad(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* g, const float* w,
+                           float* dx, void* stream) {
+  if (int rc = dw_train_check(B, C, H, W, stride)) return rc;
+  HRF_REQUIRE(g && w && dx, HRF_EINVAL, "dwconv_train_dgrad: null pointer");
+  DwTrainParams p = dw_train_params(B, C, H, W, stride);
+  p.g = g; p.w = w; p.out = dx;
+  return stride == 1 ? launch_dw_train<1>(1, p, nullptr, nullptr, (cudaStream_t)stream)
+                     : launch_dw_train<2>(1, p, nullptr, nullptr, (cudaStream_t)stream);
+}
+int hrf_dwconv_train_wgrad(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* x, const float* g,
+                           float* dw, float* dbias, float* workspace, size_t workspace_floats, void* stream) {
+  if (int rc = dw_train_check(B, C, H, W, stride)) return rc;
+  HRF_REQUIRE(x && g && dw && workspace, HRF_EINVAL, "dwconv_train_wgrad: null pointer");
+  HRF_REQUIRE(workspace_floats >= hrf_dwconv_train_ws_floats(B, C, H, W, stride), HRF_EINVAL,
+              "dwconv_train_wgrad: workspace too small");
+  DwTrainParams p = dw_train_params(B, C, H, W, stride);
+  p.x = x; p.g = g; p.part = workspace;
+  return stride == 1 ? launch_dw_train<1>(2, p, dw, dbias, (cudaStream_t)stream)
+                     : launch_dw_train<2>(2, p, dw, dbias, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ train-mode LayerNorm

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .bn_train import HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm
+from .bn_train import HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm, make_conv
 from .window_maps import relative_position_index, window_geometry
 
 
@@ -44,7 +44,7 @@ def make_norm(cfg, channels):
 
 
 def conv_bn(cin, cout, k, stride, norm_cfg, relu, groups=1):
-    layers = [nn.Conv2d(cin, cout, k, stride, k // 2, groups=groups, bias=False),
+    layers = [make_conv(cin, cout, k, stride, k // 2, groups=groups, bias=False),
               make_norm(norm_cfg, cout)]
     if relu:
         layers.append(nn.ReLU(inplace=relu == 'inplace'))
@@ -209,7 +209,7 @@ class CrossFFN(nn.Module):
         super().__init__()
         self.layers = nn.Sequential(
             nn.Conv2d(cin, hidden, 1), make_norm(norm_cfg, hidden), nn.GELU(),
-            nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden), make_norm(norm_cfg, hidden),
+            make_conv(hidden, hidden, 3, 1, 1, groups=hidden), make_norm(norm_cfg, hidden),
             nn.GELU(),
             nn.Conv2d(hidden, cout, 1), make_norm(norm_cfg, cout), nn.GELU())
 
@@ -348,7 +348,7 @@ class HRFormerModule(nn.Module):
                     for t in range(i - j):
                         last = t == i - j - 1
                         cout = ch[i] if last else ch[j]
-                        step = [nn.Conv2d(ch[j], ch[j], 3, 2, 1, groups=ch[j], bias=False),
+                        step = [make_conv(ch[j], ch[j], 3, 2, 1, groups=ch[j], bias=False),
                                 make_norm(norm_cfg, ch[j]),
                                 nn.Conv2d(ch[j], cout, 1, bias=False),
                                 make_norm(norm_cfg, cout)]

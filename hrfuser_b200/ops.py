@@ -566,6 +566,39 @@ def attn_core_train_bwd(q, k, v, P, dout, heads, scale, rpi=None, T=0):
     return dq, dk, dv, dtable
 
 
+def dwconv_train_fwd(x, weight, bias, stride):
+    """depthwise 3x3 (pad 1) of a contiguous fp32 CUDA NCHW tensor; weight (C, 1, 3, 3)"""
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    y = torch.empty(B, Cc, (H - 1) // stride + 1, (W - 1) // stride + 1, dtype=torch.float32, device=x.device)
+    with _timed('dwconv_train_fwd', C=Cc, bytes=(x.numel() + y.numel()) * 4, flops=18.0 * y.numel()):
+        check(lib.hrf_dwconv_train_fwd(B, Cc, H, W, stride, x.data_ptr(), weight.data_ptr(),
+                                       bias.data_ptr() if bias is not None else None, y.data_ptr(), _stream()))
+    return y
+
+
+def dwconv_train_bwd(x, g, weight, stride, want_dx=True, want_dw=True, want_dbias=False):
+    """-> (dx | None, dweight (C, 1, 3, 3) | None, dbias | None)"""
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    dx = dw = db = None
+    if want_dx:
+        dx = torch.empty_like(x)
+        with _timed('dwconv_train_dgrad', C=Cc, bytes=(x.numel() + g.numel()) * 4, flops=18.0 * g.numel()):
+            check(lib.hrf_dwconv_train_dgrad(B, Cc, H, W, stride, g.data_ptr(), weight.data_ptr(), dx.data_ptr(),
+                                             _stream()))
+    if want_dw or want_dbias:
+        dw = torch.empty_like(weight)
+        db = torch.empty(Cc, dtype=torch.float32, device=x.device) if want_dbias else None
+        n_ws = lib.hrf_dwconv_train_ws_floats(B, Cc, H, W, stride)
+        ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
+        with _timed('dwconv_train_wgrad', C=Cc, bytes=(x.numel() + g.numel()) * 4, flops=18.0 * g.numel()):
+            check(lib.hrf_dwconv_train_wgrad(B, Cc, H, W, stride, x.data_ptr(), g.data_ptr(), dw.data_ptr(),
+                                             db.data_ptr() if db is not None else None, ws.data_ptr(), n_ws,
+                                             _stream()))
+    return dx, dw, db
+
+
 def ln_fwd(x, weight, bias, eps):
     """Train-mode LayerNorm over the last axis of a contiguous fp32 CUDA tensor -> (y, mean, rstd)."""
     lib = _lib.load()

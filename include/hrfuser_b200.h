@@ -325,6 +325,23 @@ int hrf_attn_core_train_bwd(int32_t nWin, int32_t N, int32_t C, int32_t heads, f
                             const int32_t* rpi, int32_t T, float* dtable, float* workspace,
                             size_t workspace_floats, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Training-mode depthwise 3x3 convolution (padding 1, stride 1 | 2, groups = C), fp32 NCHW:
+ * the depthwise conv of CrossFFN (hrformer.py:273-279) and the stride-2 depthwise convs of the
+ * HRModule exchange (hrformer.py:528-548) in the training configs.  x: [B][C][H][W],
+ * y / g: [B][C][Ho][Wo] with Ho = (H - 1) / stride + 1; w: [C][3][3]; bias may be NULL.
+ * hrf_dwconv_train_wgrad sums per-CTA partials in fixed order through `workspace`
+ * (>= hrf_dwconv_train_ws_floats floats); dbias may be NULL.
+ * ---------------------------------------------------------------------- */
+size_t hrf_dwconv_train_ws_floats(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride);
+int hrf_dwconv_train_fwd(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* x,
+                         const float* w, const float* bias, float* y, void* stream);
+int hrf_dwconv_train_dgrad(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* g,
+                           const float* w, float* dx, void* stream);
+int hrf_dwconv_train_wgrad(int32_t B, int32_t C, int32_t H, int32_t W, int32_t stride, const float* x,
+                           const float* g, float* dw, float* dbias, float* workspace,
+                           size_t workspace_floats, void* stream);
+
 /* Diagnostic: D[128][N] (fp32) = A[128][K] (bf16) x B on the tcgen05 tensor cores,
  * through the same descriptor helpers the fused kernels use.  B is [N][K]
  * (b_mn_major = 0, K-major operand) or [K][N] (b_mn_major = 1, MN-major operand).
