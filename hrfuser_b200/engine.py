@@ -90,6 +90,10 @@ class _Conv:
         return y
 
     def _run(self, x, residual=None):
+        if residual is not None and residual.shape[1] != self.w.shape[0]:
+            # output channels were zero-padded (widths cuDNN has no kernel for): pad the residual alike
+            residual = F.pad(residual, (0, 0, 0, 0, 0, self.w.shape[0] - residual.shape[1])).contiguous(
+                memory_format=torch.channels_last)
         if x.is_cuda and self.relu and self.has_bias:
             if residual is None:
                 return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding,

@@ -55,6 +55,15 @@ def main():
             row['torch_eager_fp32_ms'] = round(time_ms(eager), 4)
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 row['torch_eager_bf16_autocast_ms'] = round(time_ms(eager), 4)
+        # the whole neck (front half + pooling pyramid + five 3x3 convs -> 5 fp32 NCHW maps)
+        for mode in ('fp32', 'bf16'):
+            net = HRFPN(in_channels=chans, out_channels=256, precision=mode).eval().cuda()
+            with torch.no_grad():
+                row[f'whole_ours_{mode}_ms'] = round(time_ms(lambda: net(xs)), 4)
+        with torch.no_grad():
+            row['whole_torch_eager_fp32_ms'] = round(time_ms(lambda: net._forward_autograd(xs)), 4)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                row['whole_torch_eager_bf16_autocast_ms'] = round(time_ms(lambda: net._forward_autograd(xs)), 4)
         n0 = B * grid[0] * grid[1]
         row['concat_tensor_MB_avoided'] = round(n0 * sum(chans) * 4 / 1e6, 1)
         row['gflop_ours'] = round(2 * 256 * sum((n0 >> (2 * i)) * c for i, c in enumerate(chans)) / 1e9, 2)
