@@ -142,6 +142,10 @@ SIGNATURES = {
     'hrf_dwconv_train_fwd': (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 5),
     'hrf_dwconv_train_dgrad': (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 4),
     'hrf_dwconv_train_wgrad': (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
+    'hrf_mixffn_grouped_fwd': (C.c_int, [C.POINTER(FfnDesc), C.c_int32, _VPP, _VPP, _VPP, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]),
+    'hrf_window_attn_grouped_fwd': (C.c_int, [C.POINTER(AttnDesc), C.c_int32, _VPP, _VPP, _VPP, C.c_void_p,
+                                              C.c_size_t, C.c_void_p]),
     'hrf_ln_bwd_workspace_floats': (C.c_size_t, [C.c_int32, C.c_int32]),
     'hrf_ln_fwd': (C.c_int, [C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 7),
     'hrf_ln_bwd': (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]),

@@ -370,6 +370,7 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
     // C = 18: one launch for the block, every modality inside it
     AttnV3Params p{};
     p.x = x; p.out = out; p.n_mod = passes;
+    p.xs[0] = x; p.outs[0] = out; p.n_prob = 1;
     p.v3_off = AttnLayout(d->C, d->heads, d->win).o_v3;
     for (int k = 0; k < passes; ++k) {
       p.z[k] = d->n_kv > 0 ? kv[k] : x;
@@ -401,6 +402,34 @@ int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* 
         rc = d->dtype == HRF_F32 ? launch_window_attn_generic<float>(p, st)
                                  : launch_window_attn_generic<__nv_bfloat16>(p, st);
     }
+    if (rc) return rc;
+  }
+  return HRF_OK;
+}
+
+// Self-attention (n_kv == 0) of several tensors of ONE shape, each with its own blob, in one launch
+// where the kernel supports it (C = 18: window_attn_v3); otherwise one launch per tensor.
+int hrf_window_attn_grouped_fwd(const HrfAttnDesc* d, int32_t n, const void* const* xs,
+                                const float* const* blobs, void* const* outs, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  int rc = check_attn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(d->n_kv == 0, HRF_EINVAL, "attn_grouped_fwd: self-attention only (n_kv = %d)", d->n_kv);
+  HRF_REQUIRE(n >= 1 && xs && blobs && outs, HRF_EINVAL, "attn_grouped_fwd: arguments");
+  for (int q = 0; q < n; ++q) {
+    HRF_REQUIRE(xs[q] && blobs[q] && outs[q] && xs[q] != outs[q], HRF_EINVAL, "attn_grouped_fwd: pointers of problem %d", q);
+  }
+  if (n <= AttnV3::MAXMOD && attn_path(d) == PATH_TC && AttnV3::applies(d->C, d->heads, d->win) && attn_v3_enabled()) {
+    AttnV3Params p{};
+    p.n_mod = 1; p.n_prob = n;
+    p.v3_off = AttnLayout(d->C, d->heads, d->win).o_v3;
+    for (int q = 0; q < n; ++q) { p.xs[q] = xs[q]; p.outs[q] = outs[q]; p.blob[q] = blobs[q]; }
+    p.x = xs[0]; p.out = outs[0];
+    p.B = d->B; p.H = d->H; p.W = d->W; p.pad_mask = d->with_pad_mask; p.eps = d->ln_eps;
+    return launch_window_attn_v3(p, false, (cudaStream_t)stream);
+  }
+  for (int q = 0; q < n; ++q) {
+    rc = hrf_window_attn_fwd(d, xs[q], nullptr, &blobs[q], outs[q], workspace, workspace_bytes, stream);
     if (rc) return rc;
   }
   return HRF_OK;
@@ -550,6 +579,33 @@ int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* 
   }
   return d->dtype == HRF_F32 ? launch_mixffn_generic<float>(p, st)
                              : launch_mixffn_generic<__nv_bfloat16>(p, st);
+}
+
+// MixFFN of several tensors of ONE shape, each with its own blob, in one launch where the kernel
+// supports it (C = 18: mixffn_v2); otherwise one launch per tensor.
+int hrf_mixffn_grouped_fwd(const HrfFfnDesc* d, int32_t n, const void* const* xs, const float* const* blobs,
+                           void* const* outs, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_ffn(d);
+  if (rc) return rc;
+  HRF_REQUIRE(n >= 1 && xs && blobs && outs, HRF_EINVAL, "ffn_grouped_fwd: arguments");
+  bool v2 = n <= kFfnMaxProb && ffn_path(d) == PATH_TC;
+  for (int q = 0; q < n; ++q) {
+    HRF_REQUIRE(xs[q] && blobs[q] && outs[q] && xs[q] != outs[q], HRF_EINVAL, "ffn_grouped_fwd: pointers of problem %d", q);
+    FfnParams pq{xs[q], blobs[q], outs[q], nullptr, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
+    v2 = v2 && ffn_v2_supported(pq);
+  }
+  if (v2) {
+    FfnParams p{xs[0], blobs[0], outs[0], nullptr, d->B, d->H, d->W, d->C, d->hidden, d->ln_eps, FastDiv(), FastDiv()};
+    FfnV2Problems pb;
+    pb.n = n;
+    for (int q = 0; q < n; ++q) { pb.x[q] = xs[q]; pb.blob[q] = blobs[q]; pb.out[q] = outs[q]; }
+    return launch_mixffn_v2(p, (cudaStream_t)stream, &pb);
+  }
+  for (int q = 0; q < n; ++q) {
+    rc = hrf_mixffn_fwd(d, xs[q], blobs[q], outs[q], workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return HRF_OK;
 }
 
 // ------------------------------------------------------------------ exchange

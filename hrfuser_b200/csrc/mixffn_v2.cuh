@@ -126,10 +126,25 @@ __device__ __forceinline__ uint32_t pack_f16x2(float x, float y) {
   return r;
 }
 
-template <int C, int TH, int TW, int NT>
+// Several PROBLEMS of one shape per launch (the camera's branch 0 and the modality streams run the
+// same MixFFN on tensors of the same size, each with its own weights): the images of all
+// problems form one tile space, every CTA walks ONE contiguous range of it (so it crosses from
+// one problem into the next at most once or twice and reloads the 11.6 KB of weights there), and
+// the launch, the setup and -- above all -- the partly filled last round are paid once:
+// 3 x 640 tiles over 296 resident CTAs are 7 rounds instead of 3 x 3.
+constexpr int kFfnMaxProb = 3;
+struct FfnV2Group {
+  const float* blob[kFfnMaxProb];
+  int n_prob, tiles_per_cta;      // tiles_per_cta > 0: contiguous ranges; 0: tiles strided over the grid (one problem)
+};
+template <int NP>
+struct FfnV2Maps {                 // NP = 1: the single-problem launch keeps its two maps (and its speed)
+  CUtensorMap x[NP], o[NP];
+};
+
+template <int C, int TH, int TW, int NT, int NP>
 __global__ void __launch_bounds__(NT, FfnV2<C, TH, TW, NT>::CTAS_PER_SM)
-mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
-                 const __grid_constant__ CUtensorMap tm_o) {
+mixffn_v2_kernel(FfnParams p, FfnV2Group gp, const __grid_constant__ FfnV2Maps<NP> tm) {
   using namespace umma;
   using K = FfnV2<C, TH, TW, NT>;
   constexpr int KC = K::KC, NOUT = K::NOUT, N1 = K::N1, NCH = K::NCH, NW = K::NW;
@@ -141,15 +156,29 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
   pdl_launch_dependents();
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const FfnLayout L(C, K::HID);
-  const float* blob = p.blob;
   const int tiles_x = ceil_div(p.W, TW), tiles_y = ceil_div(p.H, TH);
-  const int n_tiles = p.B * tiles_x * tiles_y;
-  auto tile_coords = [&](int tile, int& b, int& ty0, int& tx0) {
-    int rem;
-    p.d_tiles_xy.divmod(tile, b, rem);
+  const int total_tiles = gp.n_prob * p.B * tiles_x * tiles_y;
+  const bool contig = gp.tiles_per_cta > 0;
+  const int t_begin = contig ? blockIdx.x * gp.tiles_per_cta : blockIdx.x;
+  const int t_step = contig ? 1 : gridDim.x;
+  const int n_tiles = !contig ? total_tiles                       // end of this CTA's tile walk
+                              : (t_begin + gp.tiles_per_cta < total_tiles ? t_begin + gp.tiles_per_cta : total_tiles);
+  // tile -> (problem, image of the problem, first row, first column)
+  auto tile_coords = [&](int tile, int& pr, int& b, int& ty0, int& tx0) {
+    int rem, bg;
+    p.d_tiles_xy.divmod(tile, bg, rem);
     p.d_tiles_x.divmod(rem, ty0, tx0);
+    pr = NP == 1 ? 0 : (bg >= p.B) + (bg >= 2 * p.B);
+    b = bg - pr * p.B;
     ty0 *= TH;
     tx0 *= TW;
+  };
+  auto load_weights = [&](int pr) {                    // one thread: the problem's W1 | W2 | conv tables
+    const float* blob = gp.blob[pr];
+    mbar_expect_tx(&wbar, K::W1_B + K::W2_B + K::CV_B);
+    bulk_g2s(sm + K::o_w1, blob + L.o_v2_w1, K::W1_B, &wbar);
+    bulk_g2s(sm + K::o_w2, blob + L.o_v2_w2, K::W2_B, &wbar);
+    bulk_g2s(sm + K::o_cv, blob + L.o_v2_cv, K::CV_B, &wbar);
   };
 
   // ---- one-time setup ---------------------------------------------------------------------
@@ -163,17 +192,14 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
     mbar_init(&bar2, 1);
     fence_mbar_init();
     pdl_wait();                                        // x is the predecessor's output
-    if ((int)blockIdx.x < n_tiles) {
-      int b, ty0, tx0;
-      tile_coords(blockIdx.x, b, ty0, tx0);
+    if (t_begin < n_tiles) {
+      int pr, b, ty0, tx0;
+      tile_coords(t_begin, pr, b, ty0, tx0);
       mbar_expect_tx(&full[0], K::HH * K::RAW_ROW);
-      tma_load_3d(sm + K::o_raw, &tm_x, (tx0 - K::PADL) * (C / 2), ty0 - 1, b, &full[0]);
+      tma_load_3d(sm + K::o_raw, &tm.x[pr], (tx0 - K::PADL) * (C / 2), ty0 - 1, b, &full[0]);
+      load_weights(pr);
+      tma_prefetch_desc(&tm.o[pr]);
     }
-    mbar_expect_tx(&wbar, K::W1_B + K::W2_B + K::CV_B);
-    bulk_g2s(sm + K::o_w1, blob + L.o_v2_w1, K::W1_B, &wbar);
-    bulk_g2s(sm + K::o_w2, blob + L.o_v2_w2, K::W2_B, &wbar);
-    bulk_g2s(sm + K::o_cv, blob + L.o_v2_cv, K::CV_B, &wbar);
-    tma_prefetch_desc(&tm_o);
   }
   {
     // H2: zero, its tenth chunk (hidden channels 72..79 of the chunk, the K padding) holds the
@@ -193,23 +219,26 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
   const uint32_t a_w1 = smem_u32(sm + K::o_w1), a_w2 = smem_u32(sm + K::o_w2);
   const uint32_t a_xn = smem_u32(sm + K::o_xn), a_h2 = smem_u32(sm + K::o_h2);
   pdl_wait();
-  uint32_t ph1 = 0, ph2 = 0;
-  bool w_ready = false;
+  uint32_t ph1 = 0, ph2 = 0, wph = 0;
+  int cur_pr = -1;
 
   HRF_PROF(14)
   int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (int tile = t_begin; tile < n_tiles; tile += t_step, ++it) {
     HRF_PROF_TILE
     const int s = it & 1;
-    int b, ty0, tx0;
-    tile_coords(tile, b, ty0, tx0);
+    int pr, b, ty0, tx0;
+    tile_coords(tile, pr, b, ty0, tx0);
     const unsigned char* raw = sm + K::o_raw + s * K::RAW_B;
+    // the range crossed into the next problem: its weights (every read of the old ones lies
+    // before the previous tile's last barrier)
+    if (tid == 0 && cur_pr >= 0 && pr != cur_pr) load_weights(pr);
     // the other stage was last read by the previous tile's epilogue 2 (a barrier ago): refill it
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
-      int nb, nty0, ntx0;
-      tile_coords(tile + gridDim.x, nb, nty0, ntx0);
+    if (tid == 0 && tile + t_step < n_tiles) {
+      int npr, nb, nty0, ntx0;
+      tile_coords(tile + t_step, npr, nb, nty0, ntx0);
       mbar_expect_tx(&full[s ^ 1], K::HH * K::RAW_ROW);
-      tma_load_3d(sm + K::o_raw + (s ^ 1) * K::RAW_B, &tm_x, (ntx0 - K::PADL) * (C / 2), nty0 - 1, nb, &full[s ^ 1]);
+      tma_load_3d(sm + K::o_raw + (s ^ 1) * K::RAW_B, &tm.x[npr], (ntx0 - K::PADL) * (C / 2), nty0 - 1, nb, &full[s ^ 1]);
     }
     mbar_wait(&full[s], (it >> 1) & 1, 100 + s);
 
@@ -264,9 +293,10 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
       }
     }
     HRF_PROF(0)
-    if (!w_ready) {
-      mbar_wait(&wbar, 0, 102);
-      w_ready = true;
+    if (pr != cur_pr) {                                // first tile / first tile of the next problem
+      mbar_wait(&wbar, wph, 102);
+      wph ^= 1;
+      cur_pr = pr;
     }
 
 #pragma unroll 1
@@ -436,7 +466,7 @@ mixffn_v2_kernel(FfnParams p, const __grid_constant__ CUtensorMap tm_x,
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      tma_store_3d(&tm_o, tx0 * (C / 2), ty0, b, sm + K::o_out);
+      tma_store_3d(&tm.o[pr], tx0 * (C / 2), ty0, b, sm + K::o_out);
       tma_store_commit();
     }
     HRF_PROF(11)
@@ -481,31 +511,64 @@ static bool ffn_v2_supported(const FfnParams& p) {
          tmap_tokens_ok(p.out, p.W, p.C) && p.W * p.C / 2 >= 1;
 }
 
-template <int C, int TH, int TW, int NT>
-static int launch_ffn_v2_t(FfnParams p, cudaStream_t stream) {
+// one problem: (p.x, p.blob, p.out); several: n_prob entries of xs / blobs / outs
+struct FfnV2Problems {
+  int n = 1;
+  const void* x[kFfnMaxProb];
+  const float* blob[kFfnMaxProb];
+  void* out[kFfnMaxProb];
+};
+
+template <int C, int TH, int TW, int NT, int NP>
+static int launch_ffn_v2_np(FfnParams p, const FfnV2Problems& pb, cudaStream_t stream) {
   using K = FfnV2<C, TH, TW, NT>;
   const int tiles_x = ceil_div(p.W, TW), tiles_y = ceil_div(p.H, TH);
-  const int n_tiles = p.B * tiles_x * tiles_y;
+  const int n_tiles = pb.n * p.B * tiles_x * tiles_y;
   p.d_tiles_x = FastDiv(tiles_x);
   p.d_tiles_xy = FastDiv(tiles_x * tiles_y);
-  CUtensorMap tm_x, tm_o;
-  int rc = make_tmap_tokens(&tm_x, p.x, p.B, p.H, p.W, C, K::BOXW, K::HH);
-  if (rc) return rc;
-  rc = make_tmap_tokens(&tm_o, p.out, p.B, p.H, p.W, C, TW, TH);
-  if (rc) return rc;
+  FfnV2Maps<NP> tm;
+  FfnV2Group gp{};
+  gp.n_prob = pb.n;
+  for (int q = 0; q < kFfnMaxProb; ++q) gp.blob[q] = pb.blob[q < pb.n ? q : 0];
+  for (int q = 0; q < NP; ++q) {
+    const int s = q < pb.n ? q : 0;
+    int rc = make_tmap_tokens(&tm.x[q], pb.x[s], p.B, p.H, p.W, C, K::BOXW, K::HH);
+    if (rc) return rc;
+    rc = make_tmap_tokens(&tm.o[q], pb.out[s], p.B, p.H, p.W, C, TW, TH);
+    if (rc) return rc;
+    HRF_REQUIRE((reinterpret_cast<uintptr_t>(pb.blob[s]) & 15) == 0, HRF_EINVAL, "mixffn_v2: blob must be 16-byte aligned");
+  }
   static const int env_per_sm = [] { const char* e = std::getenv("HRF_FFN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const int per_sm = env_per_sm > 0 && env_per_sm < K::CTAS_PER_SM ? env_per_sm : K::CTAS_PER_SM;
   const int cap = 148 * per_sm;
-  const int grid = n_tiles < cap ? n_tiles : cap;
-  HRF_REQUIRE((reinterpret_cast<uintptr_t>(p.blob) & 15) == 0, HRF_EINVAL, "mixffn_v2: blob must be 16-byte aligned");
-  HRF_CUDA(ensure_smem((const void*)mixffn_v2_kernel<C, TH, TW, NT>, K::SMEM));
-  HRF_CUDA(launch_pdl(mixffn_v2_kernel<C, TH, TW, NT>, dim3(grid), dim3(NT), K::SMEM, stream, p, tm_x, tm_o));
+  // HRF_BALANCED_GRID=1 (experiment): ceil(tiles / rounds) CTAs that all walk `rounds` tiles instead of
+  // one full resident wave -- the same step time (2.799 vs 2.802 ms: the slots it frees for the other
+  // streams' kernels buy nothing), and a slower kernel on its own (the last, partly filled round of
+  // a full wave runs uncontended: MixFFN 19.8 vs 23.0 us), so the full wave is the default
+  static const bool balanced = [] { const char* e = std::getenv("HRF_BALANCED_GRID"); return e && e[0] == '1'; }();
+  const int rounds = ceil_div(n_tiles, cap);
+  int grid = !balanced ? (n_tiles < cap ? n_tiles : cap) : ceil_div(n_tiles, rounds);
+  if (pb.n > 1) {                                      // several problems: contiguous ranges (weights reload at a crossing)
+    gp.tiles_per_cta = ceil_div(n_tiles, grid);
+    grid = ceil_div(n_tiles, gp.tiles_per_cta);
+  }
+  HRF_CUDA(ensure_smem((const void*)mixffn_v2_kernel<C, TH, TW, NT, NP>, K::SMEM));
+  HRF_CUDA(launch_pdl(mixffn_v2_kernel<C, TH, TW, NT, NP>, dim3(grid), dim3(NT), K::SMEM, stream, p, gp, tm));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
 }
 
-static int launch_mixffn_v2(const FfnParams& p, cudaStream_t stream) {
+template <int C, int TH, int TW, int NT>
+static int launch_ffn_v2_t(FfnParams p, const FfnV2Problems& pb, cudaStream_t stream) {
+  return pb.n == 1 ? launch_ffn_v2_np<C, TH, TW, NT, 1>(p, pb, stream)
+                   : launch_ffn_v2_np<C, TH, TW, NT, kFfnMaxProb>(p, pb, stream);
+}
+
+static int launch_mixffn_v2(const FfnParams& p, cudaStream_t stream, const FfnV2Problems* group = nullptr) {
+  FfnV2Problems pb;
+  if (group) pb = *group;
+  else { pb.n = 1; pb.x[0] = p.x; pb.blob[0] = p.blob; pb.out[0] = p.out; }
   // HRF_FFN_TILE selects the variant (experiments; tools/gpu_r2_ffn2.sh).  Default: 12 x 16 tile,
   // 576 threads (two CTAs = 36 warps per SM at 56 registers; depthwise units of 3 x 1 outputs):
   // 21.7 us at 96 x 160 x 8 against 23.5 us for 288 threads / 3 x 2 units and 27.0 us for the
@@ -513,13 +576,13 @@ static int launch_mixffn_v2(const FfnParams& p, cudaStream_t stream) {
   static const int shape = [] { const char* e = std::getenv("HRF_FFN_TILE"); return e ? atoi(e) : 0; }();
   switch (p.C) {
     case 18:
-      if (shape == 1) return launch_ffn_v2_t<18, 6, 16, 288>(p, stream);
-      if (shape == 2) return launch_ffn_v2_t<18, 9, 16, 288>(p, stream);
-      if (shape == 3) return launch_ffn_v2_t<18, 12, 16, 288>(p, stream);
-      if (shape == 4) return launch_ffn_v2_t<18, 12, 16, 384>(p, stream);
-      if (shape == 5) return launch_ffn_v2_t<18, 9, 16, 576>(p, stream);
-      if (shape == 6) return launch_ffn_v2_t<18, 9, 16, 448>(p, stream);
-      return launch_ffn_v2_t<18, 12, 16, 576>(p, stream);
+      if (shape == 1) return launch_ffn_v2_t<18, 6, 16, 288>(p, pb, stream);
+      if (shape == 2) return launch_ffn_v2_t<18, 9, 16, 288>(p, pb, stream);
+      if (shape == 3) return launch_ffn_v2_t<18, 12, 16, 288>(p, pb, stream);
+      if (shape == 4) return launch_ffn_v2_t<18, 12, 16, 384>(p, pb, stream);
+      if (shape == 5) return launch_ffn_v2_t<18, 9, 16, 576>(p, pb, stream);
+      if (shape == 6) return launch_ffn_v2_t<18, 9, 16, 448>(p, pb, stream);
+      return launch_ffn_v2_t<18, 12, 16, 576>(p, pb, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_v2: C=%d", p.C);
 }

@@ -60,16 +60,22 @@ struct AttnV3 {
   static bool applies(int C_, int heads, int win) { return C_ == 18 && heads == 1 && win == 7; }
 };
 
+// Self-attention may run several PROBLEMS of one shape in one launch (the camera's branch 0 and
+// the modality streams walk the same HRFormer blocks on tensors of the same size, each with its
+// own weights: grouped, they share the launch, the setup and the tail: 3 x 13.7 us -> ~27 us).
 struct AttnV3Params {
-  const void* x;                        // camera / query tokens, also the residual
-  const void* z[AttnV3::MAXMOD];        // key / value tokens per modality (cross)
-  const float* blob[AttnV3::MAXMOD];    // packed blob per modality (self: blob[0])
+  const void* x;                        // cross: camera / query tokens, also the residual
+  const void* z[AttnV3::MAXMOD];        // cross: key / value tokens per modality
+  const float* blob[AttnV3::MAXMOD];    // packed blob per modality (cross) / per problem (self)
+  const void* xs[AttnV3::MAXMOD];       // self: tokens of every problem
+  void* outs[AttnV3::MAXMOD];           // self: output of every problem
+  int n_prob;                           // self: problems in this launch (cross: 1)
   int v3_off;                           // float offset of the v3 section inside a blob
   void* out;
   int n_mod;                            // 1 for self-attention
   int B, H, W, pad_mask;
   float eps;
-  FastDiv d_win_img, d_win_row;
+  FastDiv d_win_img, d_win_row, d_tiles;   // d_tiles: tiles per problem (global tile -> problem)
 };
 
 namespace v3 {
@@ -147,14 +153,16 @@ __global__ void __launch_bounds__(128, CROSS ? 4 : 5) window_attn_v3_kernel(cons
   constexpr int o_q = (CROSS ? 2 : 1) * A::XT, o_k = o_q + A::QT, o_w = o_q + A::REGION;
   constexpr int o_kvsrc = CROSS ? o_zn : o_xn;       // tile K / V' are projected from; V' then overwrites it
   const int n_mod = CROSS ? p.n_mod : 1;
+  const int n_prob = CROSS ? 1 : p.n_prob;
+  const int n_w = CROSS ? n_mod : n_prob;          // weight sections resident in shared memory
 
   // ---- one-time setup: weights + tables by bulk copies, zero columns, TMEM ---------------------
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_init(&wbar, 1);
     fence_mbar_init();
-    mbar_expect_tx(&wbar, (uint32_t)(n_mod * SEC));
-    for (int m = 0; m < n_mod; ++m)
+    mbar_expect_tx(&wbar, (uint32_t)(n_w * SEC));
+    for (int m = 0; m < n_w; ++m)
       bulk_g2s(sm + o_w + m * SEC,
                reinterpret_cast<const unsigned char*>(p.blob[m] + p.v3_off) + (CROSS ? A::SEC_SELF : 0), SEC, &wbar);
   }
@@ -183,8 +191,9 @@ __global__ void __launch_bounds__(128, CROSS ? 4 : 5) window_attn_v3_kernel(cons
   const bool use_mask = p.pad_mask && pad_h > 0 && pad_w > 0;
   const int n_windows = p.B * nWh * nWw;
   const int n_tiles = (n_windows + 1) / 2;
-  const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(p.x);
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+  const int total_tiles = n_tiles * n_prob;          // global tile = problem * n_tiles + tile
+  auto x_of = [&](int pr) { return static_cast<const __nv_bfloat16*>(CROSS ? p.x : p.xs[pr]); };
+  auto out_of = [&](int pr) { return static_cast<__nv_bfloat16*>(CROSS ? p.out : p.outs[pr]); };
 
   // relative-position bias of (query slot i, key slot j): table[rp_base - (jh * 13 + jw)]
   const int ic = i < S ? i : S - 1;
@@ -202,15 +211,21 @@ __global__ void __launch_bounds__(128, CROSS ? 4 : 5) window_attn_v3_kernel(cons
 
   uint32_t xr[9], zr[9];
   pdl_wait();                                        // everything above read only the weight blobs
-  int tok = row_token(blockIdx.x);
-  if (tok >= 0) {
-    load_row_raw<C>(xq + (size_t)tok * C, xr);
-    if (CROSS) load_row_raw<C>(static_cast<const __nv_bfloat16*>(p.z[0]) + (size_t)tok * C, zr);
+  int tok = -1;
+  if ((int)blockIdx.x < total_tiles) {
+    const int pr0 = n_prob > 1 ? p.d_tiles.div(blockIdx.x) : 0;
+    tok = row_token(blockIdx.x - pr0 * n_tiles);
+    if (tok >= 0) {
+      load_row_raw<C>(x_of(pr0) + (size_t)tok * C, xr);
+      if (CROSS) load_row_raw<C>(static_cast<const __nv_bfloat16*>(p.z[0]) + (size_t)tok * C, zr);
+    }
   }
 
   HRF_PROF(14)
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
     HRF_PROF_TILE
+    const int pr = n_prob > 1 ? p.d_tiles.div(gt) : 0, tile = gt - pr * n_tiles;
+    __nv_bfloat16* out = out_of(pr);
     const int wdx = tile * 2 + g;
     {
       const unsigned bal = __ballot_sync(0xffffffffu, tok >= 0);
@@ -231,8 +246,9 @@ __global__ void __launch_bounds__(128, CROSS ? 4 : 5) window_attn_v3_kernel(cons
 
 #pragma unroll 1
     for (int m = 0; m < n_mod; ++m) {
-      const unsigned char* wsec = sm + o_w + m * SEC;
-      const uint32_t a_wm = a_w + m * SEC;
+      const int wi = CROSS ? m : pr;                 // weight section: modality (cross) / problem (self)
+      const unsigned char* wsec = sm + o_w + wi * SEC;
+      const uint32_t a_wm = a_w + wi * SEC;
       uint32_t zcur[9];                              // this modality's raw rows (the "+ z" residual)
       if (CROSS) {
 #pragma unroll
@@ -407,10 +423,14 @@ __global__ void __launch_bounds__(128, CROSS ? 4 : 5) window_attn_v3_kernel(cons
       if (m + 1 < n_mod) {                           // cross: the next modality's rows of this tile
         if (CROSS && tok >= 0) load_row_raw<C>(static_cast<const __nv_bfloat16*>(p.z[CROSS ? m + 1 : 0]) + (size_t)tok * C, zr);
       } else {                                       // the next tile's rows
-        tok_next = row_token(tile + gridDim.x);
-        if (tok_next >= 0) {
-          load_row_raw<C>(xq + (size_t)tok_next * C, xnext);
-          if (CROSS) load_row_raw<C>(static_cast<const __nv_bfloat16*>(p.z[0]) + (size_t)tok_next * C, zr);
+        const int gn = gt + gridDim.x;
+        if (gn < total_tiles) {
+          const int prn = n_prob > 1 ? p.d_tiles.div(gn) : 0;
+          tok_next = row_token(gn - prn * n_tiles);
+          if (tok_next >= 0) {
+            load_row_raw<C>(x_of(prn) + (size_t)tok_next * C, xnext);
+            if (CROSS) load_row_raw<C>(static_cast<const __nv_bfloat16*>(p.z[0]) + (size_t)tok_next * C, zr);
+          }
         }
       }
       HRF_PROF(8)
@@ -474,22 +494,30 @@ static int launch_window_attn_v3(AttnV3Params p, bool cross, cudaStream_t stream
   p.d_win_row = FastDiv(ceil_div(p.W, 7));
   p.d_win_img = FastDiv(ceil_div(p.H, 7) * ceil_div(p.W, 7));
   const int n_windows = p.B * ceil_div(p.H, 7) * ceil_div(p.W, 7);
-  const int n_tiles = (n_windows + 1) / 2;
-  const int smem = A::smem_bytes(cross, p.n_mod);
+  if (cross) p.n_prob = 1;
+  p.d_tiles = FastDiv((n_windows + 1) / 2);
+  const int n_tiles = ((n_windows + 1) / 2) * p.n_prob;
+  const int smem = A::smem_bytes(cross, cross ? p.n_mod : p.n_prob);
   static const int env_per_sm = [] { const char* e = std::getenv("HRF_ATTN_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 0; }();
   const int by_smem = (227 * 1024) / (smem + 1024 + 64), by_tmem = 512 / A::tmem_cols(cross);
   int per_sm = by_smem < by_tmem ? by_smem : by_tmem;
   if (per_sm > (cross ? 4 : 5)) per_sm = cross ? 4 : 5;          // __launch_bounds__ register budget
   if (env_per_sm > 0 && env_per_sm < per_sm) per_sm = env_per_sm;
   const int cap = 148 * (per_sm > 0 ? per_sm : 1);
-  const int grid = n_tiles < cap ? n_tiles : cap;
-  for (int m = 0; m < p.n_mod; ++m)
+  // HRF_BALANCED_GRID=1 (experiment): ceil(tiles / rounds) CTAs that all walk `rounds` tiles instead of
+  // one full resident wave -- the same step time (2.799 vs 2.802 ms: the slots it frees for the other
+  // streams' kernels buy nothing), and a slower kernel on its own (the last, partly filled round of
+  // a full wave runs uncontended: MixFFN 19.8 vs 23.0 us), so the full wave is the default
+  static const bool balanced = [] { const char* e = std::getenv("HRF_BALANCED_GRID"); return e && e[0] == '1'; }();
+  const int rounds = ceil_div(n_tiles, cap);
+  const int grid = !balanced ? (n_tiles < cap ? n_tiles : cap) : ceil_div(n_tiles, rounds);
+  for (int m = 0; m < (cross ? p.n_mod : p.n_prob); ++m)
     HRF_REQUIRE((reinterpret_cast<uintptr_t>(p.blob[m] + p.v3_off) & 15) == 0, HRF_EINVAL, "attn_v3: blob must be 16-byte aligned");
   if (cross) {
     HRF_CUDA(ensure_smem((const void*)window_attn_v3_kernel<true>, A::smem_bytes(true, A::MAXMOD)));
     HRF_CUDA(launch_pdl(window_attn_v3_kernel<true>, dim3(grid), dim3(128), (size_t)smem, stream, p));
   } else {
-    HRF_CUDA(ensure_smem((const void*)window_attn_v3_kernel<false>, A::smem_bytes(false, 1)));
+    HRF_CUDA(ensure_smem((const void*)window_attn_v3_kernel<false>, A::smem_bytes(false, A::MAXMOD)));
     HRF_CUDA(launch_pdl(window_attn_v3_kernel<false>, dim3(grid), dim3(128), (size_t)smem, stream, p));
   }
   count_launch();

@@ -372,10 +372,55 @@ class BackboneEngine:
             same_t.append(t)
         return self.ops.fuse_sum(ys[i], up_t, same_t, relu=True, nchw_out=want_nchw)
 
-    def _run_stage(self, mods, xs, final_nchw=False):
+    # -- the modality streams in lockstep with the camera's branch 0 -----------------------------
+    # In stages 2 and 3 the camera's branch 0 and every modality stream walk the same number of
+    # HRFormer blocks on tensors of one shape (each with its own weights).  Stepping through them
+    # together turns (1 + M) attention and (1 + M) MixFFN launches per block into ONE of each
+    # (hrf_window_attn_grouped_fwd / hrf_mixffn_grouped_fwd): launch, setup and the partly filled
+    # last round of the persistent grids are paid once (3 x 640 MixFFN tiles over 296 resident
+    # CTAs: 7 rounds instead of 3 x 3).  HRF_LOCKSTEP=0 runs the streams on their own.
+    @staticmethod
+    def _groupable(blocks, xs):
+        b0, x0 = blocks[0], xs[0]
+        key = lambda b: (b['heads'], b['win'], b['eps'], b['pad_mask'], b['ffn']['hidden'], b['ffn']['eps'], len(b['attn']))
+        return (len(blocks) > 1 and x0.dtype == torch.bfloat16 and x0.shape[-1] == 18 and
+                all(key(b) == key(b0) for b in blocks) and all(tuple(x.shape) == tuple(x0.shape) for x in xs))
+
+    def _run_block_group(self, blocks, xs):
+        if not self._groupable(blocks, xs):
+            return [self._run_block(b, x) for b, x in zip(blocks, xs)]
+        b0 = blocks[0]
+        ys = self.ops.window_attention_grouped(xs, [b['attn'][0].t for b in blocks], b0['heads'], b0['win'],
+                                               b0['pad_mask'], b0['eps'])
+        return self.ops.mixffn_grouped(ys, [b['ffn']['blob'].t for b in blocks], b0['ffn']['hidden'], b0['ffn']['eps'])
+
+    def _run_branch_lockstep(self, blocks, x, comp):
+        """branch 0 of a camera module; `comp` = the modality chains ({'blocks', 'x', 'i'}) that step along"""
+        for blk in blocks:
+            live = [c for c in comp if c['i'] < len(c['blocks'])]
+            outs = self._run_block_group([blk] + [c['blocks'][c['i']] for c in live], [x] + [c['x'] for c in live])
+            x = outs[0]
+            for c, o in zip(live, outs[1:]):
+                c['x'], c['i'] = o, c['i'] + 1
+        return x
+
+    def _can_lockstep_stage(self, mods, comp_stages):
+        return (self.ops is ops and hasattr(self.ops, 'window_attention_grouped') and self.precision == 'bf16' and
+                os.environ.get('HRF_LOCKSTEP', '1') != '0' and len(comp_stages) > 0 and
+                all(rows is None and len(br) == 1 for st in comp_stages for br, rows in st))
+
+    def _run_stage(self, mods, xs, final_nchw=False, comp_stages=None, comp_xs=None):
+        """comp_stages / comp_xs: modality stages (single-branch modules) and their inputs to run in
+        lockstep with branch 0; returns (xs, [modality outputs]) then"""
         nchw = None
+        comp = None
+        if comp_stages is not None:
+            comp = [dict(blocks=[b for br, _ in st for b in br[0]], x=x, i=0) for st, x in zip(comp_stages, comp_xs)]
         for mi, (branches, rows) in enumerate(mods):
-            ys = self._par([lambda br=br, x=x: self._run_branch(br, x) for br, x in zip(branches, xs)])
+            thunks = [lambda br=br, x=x: self._run_branch(br, x) for br, x in zip(branches, xs)]
+            if comp is not None:
+                thunks[0] = lambda br=branches[0], x=xs[0]: self._run_branch_lockstep(br, x, comp)
+            ys = self._par(thunks)
             if rows is None:
                 xs = ys
                 continue
@@ -386,6 +431,11 @@ class BackboneEngine:
                 xs, nchw = [r[0] for r in res], [r[1] for r in res]
             else:
                 xs = res
+        if comp is not None:
+            for c in comp:                             # blocks beyond the camera's (none in the shipped configs)
+                while c['i'] < len(c['blocks']):
+                    c['x'], c['i'] = self._run_block(c['blocks'][c['i']], c['x']), c['i'] + 1
+            return ((xs, nchw) if final_nchw else xs), [c['x'] for c in comp]
         return (xs, nchw) if final_nchw else xs
 
     def _conv_group(self, convs, imgs, residuals=None):
@@ -518,10 +568,13 @@ class BackboneEngine:
                 cams, pre_ms = stems[0], stems[1:]
             xs, firsts = self._fuse('a', [lambda i=i: cams[i] for i in range(nb_a)], None, pre_ms)
             tap('fusion_a', xs)
-            res = self._par([lambda: self._run_stage(self.stage[2], xs)] +
-                            [lambda k=k: self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0]
-                             for k in range(M)])
-            ys, stream = res[0], res[1:]
+            if self._can_lockstep_stage(self.stage[2], self.stage_mod['b']):
+                ys, stream = self._run_stage(self.stage[2], xs, comp_stages=self.stage_mod['b'], comp_xs=firsts)
+            else:
+                res = self._par([lambda: self._run_stage(self.stage[2], xs)] +
+                                [lambda k=k: self._run_stage(self.stage_mod['b'][k], [firsts[k]])[0]
+                                 for k in range(M)])
+                ys, stream = res[0], res[1:]
             tap('stage2', ys)
             tap('stage_b', stream)
 
@@ -537,12 +590,17 @@ class BackboneEngine:
                 xs, firsts = self._fuse(letter, cam_thunks, stream)
                 tap(f'fusion_{letter}', xs)
                 last = idx == 3
-                thunks = [lambda last=last: self._run_stage(self.stage[4 if last else 3], xs,
-                                                            final_nchw=last)]
-                if nxt in self.stage_mod:
-                    thunks += [lambda k=k: self._run_stage(self.stage_mod[nxt][k], [firsts[k]])[0]
-                               for k in range(M)]
-                res = self._par(thunks)
+                cam_stage = self.stage[4 if last else 3]
+                if nxt in self.stage_mod and self._can_lockstep_stage(cam_stage, self.stage_mod[nxt]):
+                    r0, rest = self._run_stage(cam_stage, xs, final_nchw=last, comp_stages=self.stage_mod[nxt],
+                                               comp_xs=firsts)
+                    res = [r0] + list(rest)
+                else:
+                    thunks = [lambda last=last: self._run_stage(cam_stage, xs, final_nchw=last)]
+                    if nxt in self.stage_mod:
+                        thunks += [lambda k=k: self._run_stage(self.stage_mod[nxt][k], [firsts[k]])[0]
+                                   for k in range(M)]
+                    res = self._par(thunks)
                 if last:
                     ys, nchw = res[0]
                 else:

@@ -310,6 +310,28 @@ def window_attention(x, kv, blobs, heads, win=7, with_pad_mask=False, eps=1e-6, 
     return out
 
 
+def window_attention_grouped(xs, blobs, heads, win=7, with_pad_mask=False, eps=1e-6):
+    """LSA (out = x + Attn(LN x)) of several tensors of one shape, each with its own blob -- the
+    camera's branch 0 and the modality streams -- through hrf_window_attn_grouped_fwd (one launch
+    where the kernel covers it)."""
+    lib = _lib.load()
+    for x in xs:
+        _check_act(x)
+        assert x.shape == xs[0].shape and x.dtype == xs[0].dtype
+    assert len(blobs) == len(xs)
+    B, H, W, Cc = xs[0].shape
+    outs = [torch.empty_like(x) for x in xs]
+    d = attn_desc(B, H, W, Cc, heads, 0, xs[0].dtype, win, with_pad_mask, eps)
+    n, S, s, q = B * H * W, win * win, xs[0].element_size(), len(xs)
+    with _timed('lsa', C=Cc, launches=1, bytes=float(q * n * 2 * Cc * s), flops=float(q * n * (8 * Cc * Cc + 4 * S * Cc)),
+                problems=q):
+        ws_bytes = lib.hrf_attn_workspace_bytes(C.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs[0].device) if ws_bytes else None
+        check(lib.hrf_window_attn_grouped_fwd(C.byref(d), q, _ptr_array(xs), _ptr_array(blobs), _ptr_array(outs),
+                                              ws.data_ptr() if ws_bytes else None, ws_bytes, _stream()))
+    return outs
+
+
 def mixffn(x, blob, hidden, eps=1e-6, out=None):
     lib = _lib.load()
     _check_act(x)
@@ -324,6 +346,26 @@ def mixffn(x, blob, hidden, eps=1e-6, out=None):
         check(lib.hrf_mixffn_fwd(C.byref(d), x.data_ptr(), blob.data_ptr(), out.data_ptr(),
                                  ws.data_ptr() if ws_bytes else None, ws_bytes, _stream()))
     return out
+
+
+def mixffn_grouped(xs, blobs, hidden, eps=1e-6):
+    """MixFFN block of several tensors of one shape, each with its own blob, through
+    hrf_mixffn_grouped_fwd (one launch where the kernel covers it)."""
+    lib = _lib.load()
+    for x in xs:
+        _check_act(x)
+        assert x.shape == xs[0].shape and x.dtype == xs[0].dtype
+    B, H, W, Cc = xs[0].shape
+    outs = [torch.empty_like(x) for x in xs]
+    d = FfnDesc(B, H, W, Cc, hidden, _dtype_code(xs[0]), eps)
+    n, q = B * H * W, len(xs)
+    with _timed('mixffn', C=Cc, launches=1, bytes=float(q * n * 2 * Cc * xs[0].element_size()),
+                flops=float(q * n * (4 * Cc * hidden + 18 * hidden)), problems=q):
+        ws_bytes = lib.hrf_ffn_workspace_bytes(C.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs[0].device) if ws_bytes else None
+        check(lib.hrf_mixffn_grouped_fwd(C.byref(d), q, _ptr_array(xs), _ptr_array(blobs), _ptr_array(outs),
+                                         ws.data_ptr() if ws_bytes else None, ws_bytes, _stream()))
+    return outs
 
 
 def pointwise(x, blob, cout, relu=False):

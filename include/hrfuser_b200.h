@@ -102,6 +102,13 @@ size_t hrf_attn_workspace_bytes(const HrfAttnDesc* d);
 int hrf_window_attn_fwd(const HrfAttnDesc* d, const void* x, const void* const* kv,
                         const float* const* blobs, void* out, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Self-attention (n_kv == 0) of n tensors of ONE shape, each with its own packed blob (the
+ * camera's branch 0 and the modality streams walk the same HRFormer blocks in the same stages):
+ * ONE launch where the kernel covers it (C = 18), one per tensor otherwise.  outs[q] must not
+ * alias xs[q].  The workspace rule of hrf_window_attn_fwd applies (shared by the tensors). */
+int hrf_window_attn_grouped_fwd(const HrfAttnDesc* d, int32_t n, const void* const* xs,
+                                const float* const* blobs, void* const* outs, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * MixFFN (CrossFFN, hrformer.py:267-295) fused with the LayerNorm in front and
@@ -127,6 +134,11 @@ int hrf_ffn_pack(const HrfFfnDesc* d, const float* ln_w, const float* ln_b,
 size_t hrf_ffn_workspace_bytes(const HrfFfnDesc* d);
 int hrf_mixffn_fwd(const HrfFfnDesc* d, const void* x, const float* blob, void* out,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* The same block on n tensors of ONE shape, each with its own packed blob (the camera's branch 0 and
+ * the modality streams): ONE launch where the kernel covers it (C = 18), one per tensor otherwise. */
+int hrf_mixffn_grouped_fwd(const HrfFfnDesc* d, int32_t n, const void* const* xs,
+                           const float* const* blobs, void* const* outs, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Multi-resolution exchange (HRModule.forward hrnet.py:184-207 with the fuse

@@ -297,3 +297,42 @@ def test_conv3x3(built_lib, cin, cout, stride, H, W, relu, mode):
     torch.cuda.synchronize()
     assert got.dtype == DT[mode] and tuple(got.shape) == tuple(ref.shape)
     assert_parity(got, ref, mode, f'conv3x3 {cin}->{cout} s{stride} {H}x{W}')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('H,W,C,heads', [NUS_T[0], STF_T[0], NUS_T[1], EDGE[2], (13, 9, 18, 1)])
+@pytest.mark.parametrize('n', [1, 2, 3])
+def test_grouped_lsa_and_mixffn(built_lib, H, W, C, heads, n, mode):
+    """hrf_window_attn_grouped_fwd / hrf_mixffn_grouped_fwd: the camera's branch 0 and the modality
+    streams in one launch -- n tensors of one shape, each with its own weights; every problem must
+    equal its single-tensor call's reference (one launch for C = 18 in bf16 mode)."""
+    from hrfuser_b200 import ops
+    B = 3
+    xs, attn_blobs, ffn_packs, sds = [], [], [], []
+    e = _engine_stub()
+    for q in range(n):
+        blk, sd = make_block('lsa', C, heads, seed=10 * q + H + C)
+        packed = e._hrformer_block(blk)
+        attn_blobs.append(packed['attn'][0])
+        ffn_packs.append(packed['ffn'])
+        sds.append(sd)
+        xs.append(tokens(B, H, W, C, seed=q + 1).to(DT[mode]))
+    e._upload()
+    xc = [x.cuda() for x in xs]
+    n0 = ops.launch_count()
+    got_a = ops.window_attention_grouped(xc, [b.t for b in attn_blobs], heads)
+    n1 = ops.launch_count()
+    got_f = ops.mixffn_grouped(xc, [f['blob'].t for f in ffn_packs], ffn_packs[0]['hidden'], ffn_packs[0]['eps'])
+    n2 = ops.launch_count()
+    torch.cuda.synchronize()
+    if mode == 'bf16' and C == 18:
+        assert n1 - n0 == 1                            # one launch for the whole group
+        if (W * C * 2) % 16 == 0:                      # (MixFFN: rows the TMA unit can address)
+            assert n2 - n1 == 1
+    for q in range(n):
+        with torch.no_grad():
+            ref_a = _ref_lsa(xs[q].float(), sds[q], heads, H, W)
+            t = xs[q].float().view(B, H * W, C)
+            ref_f = (t + O.cross_ffn(O.layer_norm(t, sds[q], 'blk.norm2'), sds[q], 'blk.ffn', H, W)).view_as(xs[q])
+        assert_parity(got_a[q], ref_a, mode, f'grouped lsa {q}/{n} {H}x{W} C{C}')
+        assert_parity(got_f[q], ref_f, mode, f'grouped mixffn {q}/{n} {H}x{W} C{C}')
