@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 HRF_F32, HRF_BF16, HRF_U8 = 0, 1, 2
 MAX_FUSE_TERMS = 4

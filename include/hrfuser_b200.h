@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 7
+#define HRF_ABI_VERSION 8
 
 enum { HRF_F32 = 0, HRF_BF16 = 1, HRF_U8 = 2 /* hrf_input_prologue_fwd source only */ };
 enum {
