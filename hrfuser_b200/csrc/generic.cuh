@@ -139,10 +139,11 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
   const bool a_ok = m0 + a_row < p.M, b_ok = n0 + b_n < p.N;
   const float* a_src = p.A + (size_t)(a_ok ? m0 + a_row : 0) * p.lda;
   const float* b_src = p.Wt + (b_ok ? n0 + b_n : 0);
-#pragma unroll 1
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int buf = kb & 1, k0 = kb * KB;
-    float a[32], b[32];
+  // the global loads of block kb + 1 are requested before block kb is converted / issued, so their
+  // latency hides behind the conversion, the barrier and the MMAs (it was exposed once per block)
+  float a[32], b[32];
+  auto load_block = [&](int kb) {
+    const int k0 = kb * KB;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {                // K % 4 == 0 (checked by the launcher)
       const int k = k0 + a_k + j;
@@ -155,6 +156,11 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
       const int k = k0 + b_k + j;
       b[j] = (b_ok && k < p.K) ? __ldg(b_src + (size_t)k * p.N) : 0.f;
     }
+  };
+  load_block(0);
+#pragma unroll 1
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
     if (kb >= 2) {                                   // the MMAs of block kb-2 read this stage
       cta_wait(&bars[buf], ph[buf]);
       ph[buf] ^= 1;
@@ -178,6 +184,8 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
         mma_bf16(tmem, desc_kmajor(aA, 128, s2), desc_kmajor(aB, NT, s2), id, kb > 0 || s2 > 0);
       mma_commit(&bars[buf]);
     }
+    // (behind the fence: fence.proxy.async's MEMBAR would wait for loads requested in front of it)
+    if (kb + 1 < nkb) load_block(kb + 1);
   }
   {                                                  // the last commit covers every MMA
     const int buf = (nkb - 1) & 1;
@@ -197,6 +205,36 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
     tmem_ld8(trow + cc * 8, y);
     tmem_ld_wait();
     if (m < p.M) {
+      const int nb = n0 + cc * 8;
+      if (nb + 8 <= p.N && p.ldo % 8 == 0 && p.N % 8 == 0) {
+        // eight consecutive outputs of a row as 16- / 32-byte vectors (scalar stores 512 bytes apart
+        // between lanes cost a sector per element)
+        const size_t off = (size_t)m * p.ldo + nb;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = y[j] + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
+          if (p.act == 1) v[j] = fmaxf(v[j], 0.f);
+          else if (p.act == 2) v[j] = gelu_erf(v[j]);
+        }
+        if constexpr (std::is_same<TO, float>::value) {
+          if (r1) { const float4 a = *reinterpret_cast<const float4*>(r1 + off), b = *reinterpret_cast<const float4*>(r1 + off + 4);
+                    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w; }
+          if (r2) { const float4 a = *reinterpret_cast<const float4*>(r2 + off), b = *reinterpret_cast<const float4*>(r2 + off + 4);
+                    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w; }
+          *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(out + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          float t[8];
+          if (r1) { load_row_bf16<8>(r1 + off, t);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += t[j]; }
+          if (r2) { load_row_bf16<8>(r2 + off, t);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += t[j]; }
+          store_row_bf16<8>(out + off, v);
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = n0 + cc * 8 + j;
@@ -209,6 +247,7 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(GemmParams p) {
           if (r2) v += Elem<TO>::ld(r2 + off);
           Elem<TO>::st(out + off, v);
         }
+      }
       }
     }
   }
@@ -303,16 +342,22 @@ __global__ void __launch_bounds__(128) attn_core_kernel(CoreParams p) {
 }
 
 // ---- depthwise 3x3 (stride 1, pad 1) + bias + GELU on fp32 (n_tok, CH) ------------------------
+// A thread owns four consecutive channels of a token (CH % 4 == 0: float4 loads of the nine taps and
+// of their weights), 32-bit index arithmetic.  FAST: the tanh-form GELU of the bf16 mode (the
+// fused kernels' `gelu_as`); the fp32 mode keeps erf.  (The element-per-thread version with 64-bit
+// `/ %` ran at 0.56 TB/s: 135 us for the 24 x 40 x 8 x 1248 hidden tensor of HRFuser-B.)
+template <bool FAST>
 __global__ void __launch_bounds__(256) dw3x3_gelu_kernel(const float* x, const float* __restrict__ wd,
                                                          const float* __restrict__ bd, float* out,
                                                          int B, int H, int W, int CH) {
-  const size_t total = (size_t)B * H * W * CH;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % CH);
-    const size_t t = e / CH;
-    const int w = (int)(t % W), h = (int)((t / W) % H), b = (int)(t / ((size_t)W * H));
-    float s = __ldg(bd + c);
+  const int cq = CH >> 2;
+  const unsigned total = (unsigned)B * H * W * cq;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned t = e / cq;
+    const int c = (int)(e - t * cq) * 4;
+    const unsigned hb = t / W;
+    const int w = (int)(t - hb * W), b = (int)(hb / H), h = (int)(hb - (unsigned)b * H);
+    float4 s = __ldg(reinterpret_cast<const float4*>(bd + c));
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
       const int y = h + dy;
@@ -321,11 +366,15 @@ __global__ void __launch_bounds__(256) dw3x3_gelu_kernel(const float* x, const f
       for (int dx = -1; dx <= 1; ++dx) {
         const int xx = w + dx;
         if (xx < 0 || xx >= W) continue;
-        s = fmaf(__ldg(x + ((size_t)(b * H + y) * W + xx) * CH + c),
-                 __ldg(wd + (size_t)((dy + 1) * 3 + dx + 1) * CH + c), s);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(b * H + y) * W + xx) * CH + c));
+        const float4 k = __ldg(reinterpret_cast<const float4*>(wd + (size_t)((dy + 1) * 3 + dx + 1) * CH + c));
+        s.x = fmaf(v.x, k.x, s.x); s.y = fmaf(v.y, k.y, s.y); s.z = fmaf(v.z, k.z, s.z); s.w = fmaf(v.w, k.w, s.w);
       }
     }
-    out[e] = gelu_erf(s);
+    float4 o;
+    if (FAST) { o.x = gelu_as(s.x); o.y = gelu_as(s.y); o.z = gelu_as(s.z); o.w = gelu_as(s.w); }
+    else { o.x = gelu_erf(s.x); o.y = gelu_erf(s.y); o.z = gelu_erf(s.z); o.w = gelu_erf(s.w); }
+    *reinterpret_cast<float4*>(out + (size_t)t * CH + c) = o;
   }
 }
 
@@ -622,9 +671,11 @@ static int launch_mixffn_generic(const FfnParams& p, cudaStream_t st) {
   constexpr bool tc = std::is_same<T, __nv_bfloat16>::value;   // bf16 mode: tensor-core GEMMs
   GemmParams g1{xn, blob + L.o_w1, blob + L.o_b1, nullptr, nullptr, h1, n, Hd, C, C, Hd, 2};
   if ((rc = launch_gemm<float>(g1, st, tc))) return rc;
-  const size_t total = (size_t)n * Hd;
+  HRF_REQUIRE(Hd % 4 == 0 && (size_t)n * (Hd / 4) < (1ull << 31), HRF_EUNSUPPORTED, "mixffn (generic path): hidden=%d", Hd);
+  const size_t total = (size_t)n * (Hd / 4);
   const int dgrid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  dw3x3_gelu_kernel<<<dgrid, 256, 0, st>>>(h1, blob + L.o_wd, blob + L.o_bd, h2, p.B, p.H, p.W, Hd);
+  if (tc) dw3x3_gelu_kernel<true><<<dgrid, 256, 0, st>>>(h1, blob + L.o_wd, blob + L.o_bd, h2, p.B, p.H, p.W, Hd);
+  else dw3x3_gelu_kernel<false><<<dgrid, 256, 0, st>>>(h1, blob + L.o_wd, blob + L.o_bd, h2, p.B, p.H, p.W, Hd);
   count_launch();
   HRF_CUDA(cudaGetLastError());
   // out = x + GELU(h2 W2^T + b2)
