@@ -408,19 +408,22 @@ def run_ours(args):
             tfs = g['flops'] / g['total_ms'] / 1e9
             bound = 'hbm' if ai < ridge else 'tensor'
             kernels[f'{kind}_c{Cc}'] = dict(
-                calls=g['calls'], total_ms=round(g['total_ms'], 4), avg_ms=round(g['avg_ms'], 5),
+                calls=g['calls'], tensors=g['problems'], total_ms=round(g['total_ms'], 4), avg_ms=round(g['avg_ms'], 5),
                 share_of_hrf_kernels=round(g['total_ms'] / ours_ms, 4), bound=bound,
                 achieved_gbs=round(gbs, 2), achieved_tflops=round(tfs, 3),
                 frac=round(gbs / pk['hbm_gbs'] if bound == 'hbm' else tfs / pk['bf16_tflops'], 5))
         top_key, top = next(iter(kernels.items()))
         (kind, Cc), g = max(summ.items(), key=lambda kv: kv[1]['total_ms'])
-        per_launch_bytes = g['bytes'] / g['calls']
+        # grouped launches (the camera's branch 0 + the modality streams in one call) are counted per
+        # PROBLEM: bytes per tensor, and the graph-timed call below is a one-tensor call
+        per_launch_bytes = g['bytes'] / g['problems']
         roof = dict(kernel=top_key, bound=top['bound'],
                     achieved=top['achieved_gbs'] if top['bound'] == 'hbm' else top['achieved_tflops'],
                     peak=pk['hbm_gbs'] if top['bound'] == 'hbm' else pk['bf16_tflops'],
                     unit='GB/s' if top['bound'] == 'hbm' else 'TFLOP/s', frac=top['frac'],
                     traffic=None, peak_source=pk['source'],
-                    algorithmic_bytes_per_call=per_launch_bytes, avg_call_ms=top['avg_ms'],
+                    algorithmic_bytes_per_call=per_launch_bytes, avg_call_ms=round(g['total_ms'] / g['problems'], 5),
+                    launches_per_step=g['calls'], tensors_per_step=g['problems'],
                     share_of_step=round(g['total_ms'] / eager_ms, 4),
                     hrf_kernels_share_of_step=round(ours_ms / eager_ms, 4),
                     eager_step_ms=round(eager_ms, 3),
@@ -444,13 +447,15 @@ def run_ours(args):
             if top['bound'] == 'hbm':
                 roof['achieved'] = round(per_launch_bytes / g_ms / 1e6, 2)
             else:
-                roof['achieved'] = round(g['flops'] / g['calls'] / g_ms / 1e9, 3)
+                roof['achieved'] = round(g['flops'] / g['problems'] / g_ms / 1e9, 3)
             roof['frac'] = round(roof['achieved'] / roof['peak'], 5)
             roof['note'] = ('avg_call_ms / achieved / frac: the dominant kernel replayed 20x back to back in one CUDA '
                             'graph, CUDA events around 5 replays (input L2-resident, as inside the step where its '
                             'producer has just written it); *_events: the same call bracketed by two event records '
                             'in a serial un-graphed step (includes its launch latency); share_of_step and the '
-                            '`kernels` table use the event times')
+                            '`kernels` table use the event times; per TENSOR: in the step the camera and modality '
+                            'streams share grouped launches (tensors_per_step / launches_per_step), '
+                            'algorithmic_bytes_per_call and avg_call_ms are for one tensor')
 
     # ---- gather per-rank frame counts (the path's only collective) ------------
     frames = torch.tensor([float(B * K)], device=dev)

@@ -62,8 +62,9 @@ class Recorder:
         """-> {(kind, C): dict(calls, total_ms, avg_ms, bytes, flops)} after a sync"""
         out = {}
         for kind, meta, a, b in self.calls:
-            g = out.setdefault((kind, meta['C']), dict(calls=0, total_ms=0.0, bytes=0.0, flops=0.0))
+            g = out.setdefault((kind, meta['C']), dict(calls=0, problems=0, total_ms=0.0, bytes=0.0, flops=0.0))
             g['calls'] += 1
+            g['problems'] += meta.get('problems', 1)     # grouped launches: tensors per call
             g['total_ms'] += a.elapsed_time(b)
             g['bytes'] += meta['bytes']
             g['flops'] += meta['flops']
