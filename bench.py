@@ -277,9 +277,12 @@ def run_ours(args):
     dev_sets = [[t.to(dev) for t in hs] for hs in host_sets]
 
     # ---- one CUDA graph per input set -------------------------------------------
-    # HRF_STEPS_IN_FLIGHT=n > 1 (experiment): n independent steps replay concurrently on n
-    # streams (private memory pools); the default 1 runs the steps back to back.
-    n_fly = max(1, int(os.environ.get('HRF_STEPS_IN_FLIGHT', '1')))
+    # Two independent steps replay concurrently on two streams (private memory pools), as a serving
+    # process drives the backbone (and as the e2e leg's three caller streams do): a step's stem phase
+    # -- one persistent conv kernel in flight at a time -- overlaps the previous step's stage tail.
+    # `value` is K steps over the time they take this way; `serial` in the line is the same K steps
+    # back to back on one stream (HRF_STEPS_IN_FLIGHT=1 makes that the headline).
+    n_fly = max(1, int(os.environ.get('HRF_STEPS_IN_FLIGHT', '2')))
     graphs, pool = [], None
     for ds in dev_sets:
         g = GraphedForward(engine, ds[0], ds[1:], pool=None if n_fly > 1 else pool)
@@ -289,8 +292,8 @@ def run_ours(args):
     fly_streams = [torch.cuda.Stream() for _ in range(n_fly)] if n_fly > 1 else None
     torch.cuda.synchronize()
 
-    def run_steps(n):
-        if fly_streams is None:
+    def run_steps(n, serial=False):
+        if fly_streams is None or serial:
             for i in range(n):
                 graphs[i % R]()
             return
@@ -319,6 +322,17 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     dev_ms = hdist.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop() if sampler else None
+    serial_ms = dev_ms
+    if fly_streams is not None:                  # the same K steps back to back on one stream
+        run_steps(Wm, serial=True)
+        torch.cuda.synchronize()
+        hdist.barrier()
+        e0.record()
+        run_steps(K, serial=True)
+        e1.record()
+        torch.cuda.synchronize()
+        hdist.barrier()
+        serial_ms = hdist.max_over_ranks(e0.elapsed_time(e1), dev)
 
     # ---- (b) end to end through the public API: pinned host inputs -> forward -> D2H ---------
     # `net(x_host, mods_host)`: the forward copies the pinned host tensors straight into the
@@ -480,7 +494,11 @@ def run_ours(args):
                        'parallelism': f'scene-batch shards x{world}, no data-path collective',
                        'l2': f'inputs rotate over {R} sets ({R * bytes_in / 1e6:.0f} MB > 126 MB L2); '
                              'one CUDA graph per set',
-                       'timing': 'CUDA events around K graph replays, max over ranks'},
+                       'steps_in_flight': n_fly,
+                       'timing': f'CUDA events around K graph replays ({n_fly} independent steps in flight on '
+                                 f'{n_fly} streams), max over ranks'},
+            'serial': {'value': total_frames / (serial_ms / 1e3), 'ms_per_step': serial_ms / K,
+                       'what': 'the same K steps back to back on one stream'},
             'e2e': {'value': total_frames / (e2e_ms / 1e3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': bytes_in, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': e2e_ms / K, 'host_affinity_rank0': numa,
