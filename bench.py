@@ -502,6 +502,8 @@ def run_ours(args):
             'e2e': {'value': total_frames / (e2e_ms / 1e3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': bytes_in, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': e2e_ms / K, 'host_affinity_rank0': numa,
+                    'h2d_gb_per_s': round(bytes_in / (e2e_ms / K) / 1e6, 2),
+                    'd2h_gb_per_s': round(d2h_bytes / (e2e_ms / K) / 1e6, 2),
                     'how': f'through HRFuserHRFormerBased.forward(x_host, mods_host) on {n_slots} '
                            'caller streams (the forward keeps one captured graph per signature and '
                            'stream): pinned fp32 host inputs -> H2D -> forward -> D2H of the 4 fp32 '
