@@ -142,6 +142,11 @@ struct FfnV2Maps {                 // NP = 1: the single-problem launch keeps it
   CUtensorMap x[NP], o[NP];
 };
 
+#ifndef HRF_FFN_GELU1_HALF
+#define HRF_FFN_GELU1_HALF 1
+#endif
+__device__ __forceinline__ constexpr bool v2_gelu1_half() { return HRF_FFN_GELU1_HALF != 0; }
+
 template <int C, int TH, int TW, int NT, int NP>
 __global__ void __launch_bounds__(NT, FfnV2<C, TH, TW, NT>::CTAS_PER_SM)
 mixffn_v2_kernel(FfnParams p, FfnV2Group gp, const __grid_constant__ FfnV2Maps<NP> tm) {
@@ -339,8 +344,14 @@ mixffn_v2_kernel(FfnParams p, FfnV2Group gp, const __grid_constant__ FfnV2Maps<N
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 g = gelu_hx2(make_float2(a[hf * 8 + 2 * e], a[hf * 8 + 2 * e + 1]));
-              w[e] = pack_f16x2(g.x, g.y);
+              if (v2_gelu1_half()) {
+                // round the fc1 output to fp16 first and evaluate GELU packed (one MUFU.TANH.F16x2 per
+                // pair, no separate pack): H1 is stored as fp16 anyway
+                w[e] = h2_as_u32(gelu_hx_h2(u32_as_h2(pack_f16x2(a[hf * 8 + 2 * e], a[hf * 8 + 2 * e + 1]))));
+              } else {
+                const float2 g = gelu_hx2(make_float2(a[hf * 8 + 2 * e], a[hf * 8 + 2 * e + 1]));
+                w[e] = pack_f16x2(g.x, g.y);
+              }
             }
             *reinterpret_cast<uint4*>(sm + K::o_h1 + ((size_t)(grp * 2 + hf) * K::NHALO + t) * 16) =
                 make_uint4(w[0], w[1], w[2], w[3]);
