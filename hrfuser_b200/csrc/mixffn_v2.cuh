@@ -580,20 +580,12 @@ static int launch_mixffn_v2(const FfnParams& p, cudaStream_t stream, const FfnV2
   FfnV2Problems pb;
   if (group) pb = *group;
   else { pb.n = 1; pb.x[0] = p.x; pb.blob[0] = p.blob; pb.out[0] = p.out; }
-  // HRF_FFN_TILE selects the variant (experiments; tools/gpu_r2_ffn2.sh).  Default: 12 x 16 tile,
-  // 576 threads (two CTAs = 36 warps per SM at 56 registers; depthwise units of 3 x 1 outputs):
-  // 21.7 us at 96 x 160 x 8 against 23.5 us for 288 threads / 3 x 2 units and 27.0 us for the
-  // first-generation kernel.
-  static const int shape = [] { const char* e = std::getenv("HRF_FFN_TILE"); return e ? atoi(e) : 0; }();
+  // 12 x 16 tile, 576 threads (two CTAs = 36 warps per SM at 56 registers; depthwise units of 3 x 1
+  // outputs): 21.7 us at 96 x 160 x 8 by CUDA events against 23.5 us for 288 threads / 3 x 2 units and
+  // 27.0 us for the first-generation kernel.  The other tile shapes that were measured (6 x 16, 9 x 16,
+  // 12 x 16 at 288 / 384 / 448 threads; 12 x 18) are in the git history.
   switch (p.C) {
-    case 18:
-      if (shape == 1) return launch_ffn_v2_t<18, 6, 16, 288>(p, pb, stream);
-      if (shape == 2) return launch_ffn_v2_t<18, 9, 16, 288>(p, pb, stream);
-      if (shape == 3) return launch_ffn_v2_t<18, 12, 16, 288>(p, pb, stream);
-      if (shape == 4) return launch_ffn_v2_t<18, 12, 16, 384>(p, pb, stream);
-      if (shape == 5) return launch_ffn_v2_t<18, 9, 16, 576>(p, pb, stream);
-      if (shape == 6) return launch_ffn_v2_t<18, 9, 16, 448>(p, pb, stream);
-      return launch_ffn_v2_t<18, 12, 16, 576>(p, pb, stream);
+    case 18: return launch_ffn_v2_t<18, 12, 16, 576>(p, pb, stream);
   }
   HRF_REQUIRE(false, HRF_EUNSUPPORTED, "mixffn_v2: C=%d", p.C);
 }
