@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t pack_f16x2(float x, float y) {
 // one problem into the next at most once or twice and reloads the 11.6 KB of weights there), and
 // the launch, the setup and -- above all -- the partly filled last round are paid once:
 // 3 x 640 tiles over 296 resident CTAs are 7 rounds instead of 3 x 3.
-constexpr int kFfnMaxProb = 3;
+constexpr int kFfnMaxProb = 4;      // camera + up to three modality streams (T-stf)
 struct FfnV2Group {
   const float* blob[kFfnMaxProb];
   int n_prob, tiles_per_cta;      // tiles_per_cta > 0: contiguous ranges; 0: tiles strided over the grid (one problem)
@@ -173,7 +173,7 @@ mixffn_v2_kernel(FfnParams p, FfnV2Group gp, const __grid_constant__ FfnV2Maps<N
     int rem, bg;
     p.d_tiles_xy.divmod(tile, bg, rem);
     p.d_tiles_x.divmod(rem, ty0, tx0);
-    pr = NP == 1 ? 0 : (bg >= p.B) + (bg >= 2 * p.B);
+    pr = NP == 1 ? 0 : (bg >= p.B) + (bg >= 2 * p.B) + (bg >= 3 * p.B);
     b = bg - pr * p.B;
     ty0 *= TH;
     tx0 *= TW;

@@ -301,7 +301,7 @@ def test_conv3x3(built_lib, cin, cout, stride, H, W, relu, mode):
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('H,W,C,heads', [NUS_T[0], STF_T[0], NUS_T[1], EDGE[2], (13, 9, 18, 1)])
-@pytest.mark.parametrize('n', [1, 2, 3])
+@pytest.mark.parametrize('n', [1, 2, 3, 4])
 def test_grouped_lsa_and_mixffn(built_lib, H, W, C, heads, n, mode):
     """hrf_window_attn_grouped_fwd / hrf_mixffn_grouped_fwd: the camera's branch 0 and the modality
     streams in one launch -- n tensors of one shape, each with its own weights; every problem must
