@@ -5,7 +5,8 @@
 //
 // What changed against window_attn_tc.cuh (which stays for the multi-head widths):
 //   * three tensor-core round trips per window pair instead of four, and 64 TMEM columns
-//     instead of 128 (LSA), so 6 CTAs are resident per SM instead of 4:
+//     instead of 128 (LSA), so 5 CTAs are resident per SM instead of 4 (the register budget: at 6,
+//     80 registers, nvcc spills the prefetched row right behind its load and LayerNorm stalls on it):
 //       - with ONE head the output projection commutes with the softmax average:
 //           out_i = sum_j P_ij (v_j Wo^T) / sum_j P_ij + bo,
 //         so V' = LN(z) (Wo Wv)^T is projected alongside Q and K (weights multiplied on the
