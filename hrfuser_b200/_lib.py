@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HRF_LIB: alternative build of the same ABI (debug / instrumented), tools only
 LIB_PATH = os.environ.get('HRF_LIB') or os.path.join(HERE, 'libhrfuser_b200.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 HRF_F32, HRF_BF16, HRF_U8 = 0, 1, 2
 MAX_FUSE_TERMS = 4
@@ -124,10 +124,11 @@ SIGNATURES = {
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_bn_bwd_stats': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_size_t, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'hrf_bn_bwd_dx': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     'hrf_bn_affine': (C.c_int, [C.POINTER(BnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hrf_selftest_umma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

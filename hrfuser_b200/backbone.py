@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from .modules import (HRFormerBlock, HRFormerModule, HRFuserFusionBlock, Bottleneck,
                       make_bottleneck_layer, make_norm, make_transition)
+from .bn_train import norm_act
 
 
 class HRFuserHRFormerBased(nn.Module):
@@ -284,12 +285,12 @@ class HRFuserHRFormerBased(nn.Module):
         """Training path (torch ops, autograd).  Same wiring as the engine; see
         the reference forward hrfuser_hrformer_based.py:522-627."""
         M = self.num_fused_modalities
-        x = self.relu(self.bn1(self.conv1(x)))
-        x = self.layer1(self.relu(self.bn2(self.conv2(x))))
+        x = norm_act(self.bn1, self.relu, self.conv1(x))
+        x = self.layer1(norm_act(self.bn2, self.relu, self.conv2(x)))
         stream = []
         for k in range(M):
-            m = self.relu(self.norm_a[k](self.conv_a[k](mods[k])))
-            stream.append(self.layer_a[k](self.relu(self.norm_b[k](self.conv_b[k](m)))))
+            m = norm_act(self.norm_a[k], self.relu, self.conv_a[k](mods[k]))
+            stream.append(self.layer_a[k](norm_act(self.norm_b[k], self.relu, self.conv_b[k](m))))
 
         def fuse(letter, cams):
             trans, fusion = getattr(self, f'transition_{letter}'), getattr(self, f'fusion_{letter}')

@@ -19,6 +19,7 @@ CPU execution model, used by the CPU tests) go through torch's implementation.
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 
@@ -32,39 +33,44 @@ def _all_reduce_sum(t, group):
 class _BatchNormTrainFn(torch.autograd.Function):
     """y = BN_train(x).  Forward: hrf_bn_stats -> [all-reduce] -> hrf_bn_normalize (which also
     saves mean / invstd and updates the running statistics); backward: hrf_bn_bwd_stats ->
-    [all-reduce] -> hrf_bn_bwd_dx.  No per-channel math on the host side."""
+    [all-reduce] -> hrf_bn_bwd_dx.  No per-channel math on the host side.
+    `act` fuses the ReLU / GELU module that follows the norm layer: y = act(BN_train(x)); the
+    backward recomputes the pre-activation from x, so only x is saved."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, act=0):
         x = x.contiguous()
         stats = _all_reduce_sum(ops.bn_stats(x), group)      # [sum x | sum x^2 | count], fp64
         y, mean, invstd = ops.bn_normalize(x, stats, weight, bias, eps, momentum, running_mean,
-                                           running_var)
-        ctx.save_for_backward(x, weight, mean, invstd, stats)
-        ctx.group = group
+                                           running_var, act=act)
+        ctx.save_for_backward(x, weight, bias, mean, invstd, stats)
+        ctx.group, ctx.act = group, act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean, invstd, stats = ctx.saved_tensors
+        x, weight, bias, mean, invstd, stats = ctx.saved_tensors
         dy = dy.contiguous()
         C = x.shape[1]
         # parameter gradients are rank-local (DDP averages them), as in torch's SyncBatchNorm
-        sums, dweight, dbias = ops.bn_bwd_stats(x, dy, mean, invstd, want_param_grads=True)
+        sums, dweight, dbias = ops.bn_bwd_stats(x, dy, mean, invstd, want_param_grads=True,
+                                                weight=weight, bias=bias, act=ctx.act)
         dx = None
         if ctx.needs_input_grad[0]:
             _all_reduce_sum(sums, ctx.group)
-            dx = ops.bn_bwd_dx(x, dy, sums, stats[2 * C:], weight, mean, invstd)
+            dx = ops.bn_bwd_dx(x, dy, sums, stats[2 * C:], weight, mean, invstd, bias=bias,
+                               act=ctx.act)
         return (dx, dweight if weight is not None and ctx.needs_input_grad[1] else None,
-                dbias if ctx.needs_input_grad[2] else None, None, None, None, None, None)
+                dbias if bias is not None and ctx.needs_input_grad[2] else None,
+                None, None, None, None, None, None)
 
 
-def _train_forward(mod, x, group):
+def _train_forward(mod, x, group, act=0):
     if mod.momentum is None:
         raise NotImplementedError('cumulative moving average (momentum=None) is not supported')
     track = mod.track_running_stats and mod.running_mean is not None
     y = _BatchNormTrainFn.apply(x, mod.weight, mod.bias, mod.running_mean if track else None,
-                                mod.running_var if track else None, mod.eps, mod.momentum, group)
+                                mod.running_var if track else None, mod.eps, mod.momentum, group, act)
     if track:
         mod.num_batches_tracked.add_(1)
     return y
@@ -73,22 +79,65 @@ def _train_forward(mod, x, group):
 class HrfBatchNorm2d(nn.BatchNorm2d):
     """`nn.BatchNorm2d` whose CUDA training forward / backward run on hrf_bn_* kernels."""
 
-    def forward(self, x):
+    def forward(self, x, act=0):
         if x.is_cuda and (self.training or not self.track_running_stats):
             self._check_input_dim(x)
-            return _train_forward(self, x, None)
-        return super().forward(x)
+            return _train_forward(self, x, None, act)
+        return _apply_act(super().forward(x), act)
 
 
 class HrfSyncBatchNorm(nn.SyncBatchNorm):
     """`nn.SyncBatchNorm` with one fp64 all-reduce of (sum, sum of squares, count) per forward
     and one of (sum dy, sum dy * xhat) per backward, around the hrf_bn_* kernels."""
 
-    def forward(self, x):
+    def forward(self, x, act=0):
         if x.is_cuda and (self.training or not self.track_running_stats):
             self._check_input_dim(x)
-            return _train_forward(self, x, sync_group(self.process_group))
-        return super().forward(x)
+            return _train_forward(self, x, sync_group(self.process_group), act)
+        return _apply_act(super().forward(x), act)
+
+
+def _apply_act(y, act):
+    return F.relu(y) if act == ops.BN_ACT_RELU else F.gelu(y) if act == ops.BN_ACT_GELU else y
+
+
+def act_code(m):
+    """BN_ACT_* of an activation module the BN kernels can fuse, else None"""
+    if isinstance(m, nn.ReLU):
+        return ops.BN_ACT_RELU
+    if isinstance(m, nn.GELU) and getattr(m, 'approximate', 'none') == 'none':
+        return ops.BN_ACT_GELU
+    return None
+
+
+def norm_act(norm, act, x):
+    """act(norm(x)), in the norm layer's own kernels when it is an Hrf(Sync)BatchNorm2d on CUDA"""
+    code = act_code(act) if isinstance(norm, (HrfBatchNorm2d, HrfSyncBatchNorm)) and x.is_cuda else None
+    if code is not None and NormActSequential.fuse_act:
+        return norm(x, act=code)
+    return act(norm(x))
+
+
+class NormActSequential(nn.Sequential):
+    """nn.Sequential (same child names, same state_dict) that hands an activation module to the
+    Hrf(Sync)BatchNorm2d right before it, whose kernels apply it and its derivative in their
+    own passes (`fuse_act = False` restores the child-by-child walk)."""
+    fuse_act = True
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            code = act_code(nxt) if self.fuse_act and isinstance(m, (HrfBatchNorm2d, HrfSyncBatchNorm)) else None
+            if code is not None and x.is_cuda:
+                x = m(x, act=code)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
 
 
 def sync_group(process_group=None):

@@ -859,18 +859,24 @@ int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* sums, void* ws, size
   HRF_REQUIRE(x && sums && ws, HRF_EINVAL, "bn_stats: null pointer");
   HRF_REQUIRE(ws_bytes >= bn_workspace_bytes(d->B, d->C, d->HW), HRF_EINVAL, "bn_stats: workspace too small");
   if (d->dtype == HRF_F32)
-    return launch_bn_reduce<float, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, sums, nullptr, nullptr, ws, (cudaStream_t)stream);
-  return launch_bn_reduce<__nv_bfloat16, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, sums, nullptr, nullptr, ws, (cudaStream_t)stream);
+    return launch_bn_reduce<float, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sums, nullptr, nullptr, ws, (cudaStream_t)stream);
+  return launch_bn_reduce<__nv_bfloat16, false>(d->B, d->C, d->HW, x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sums, nullptr, nullptr, ws, (cudaStream_t)stream);
+}
+static int bn_act_check(int32_t act) {
+  HRF_REQUIRE(act >= BN_ACT_NONE && act <= BN_ACT_GELU, HRF_EINVAL, "bn: act %d (0 none, 1 ReLU, 2 GELU)", act);
+  return HRF_OK;
 }
 int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const float* mean,
-                     const float* invstd, double* sums, float* dweight, float* dbias, void* ws,
-                     size_t ws_bytes, void* stream) {
+                     const float* invstd, const float* weight, const float* bias, int32_t act,
+                     double* sums, float* dweight, float* dbias, void* ws, size_t ws_bytes,
+                     void* stream) {
   if (int rc = bn_check(d)) return rc;
+  if (int rc = bn_act_check(act)) return rc;
   HRF_REQUIRE(x && dy && mean && invstd && sums && ws, HRF_EINVAL, "bn_bwd_stats: null pointer");
   HRF_REQUIRE(ws_bytes >= bn_workspace_bytes(d->B, d->C, d->HW), HRF_EINVAL, "bn_bwd_stats: workspace too small");
   if (d->dtype == HRF_F32)
-    return launch_bn_reduce<float, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
-  return launch_bn_reduce<__nv_bfloat16, true>(d->B, d->C, d->HW, x, dy, mean, invstd, sums, dweight, dbias, ws, (cudaStream_t)stream);
+    return launch_bn_reduce<float, true>(d->B, d->C, d->HW, x, dy, mean, invstd, weight, bias, act, sums, dweight, dbias, ws, (cudaStream_t)stream);
+  return launch_bn_reduce<__nv_bfloat16, true>(d->B, d->C, d->HW, x, dy, mean, invstd, weight, bias, act, sums, dweight, dbias, ws, (cudaStream_t)stream);
 }
 // ------------------------------------------------------------------ training-mode attention core
 static int attn_core_check(int nWin, int N, int C, int heads) {
@@ -981,14 +987,15 @@ int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float
   k.b = b;
   k.c0 = c0;
   if (d->dtype == HRF_F32)
-    return launch_bn_affine<float, COEF_GIVEN>(d->B, d->C, d->HW, x, dy, k, relu, out, (cudaStream_t)stream);
-  return launch_bn_affine<__nv_bfloat16, COEF_GIVEN>(d->B, d->C, d->HW, x, dy, k, relu, out, (cudaStream_t)stream);
+    return launch_bn_affine<float, COEF_GIVEN>(d->B, d->C, d->HW, x, dy, k, relu ? BN_ACT_RELU : BN_ACT_NONE, out, (cudaStream_t)stream);
+  return launch_bn_affine<__nv_bfloat16, COEF_GIVEN>(d->B, d->C, d->HW, x, dy, k, relu ? BN_ACT_RELU : BN_ACT_NONE, out, (cudaStream_t)stream);
 }
 int hrf_bn_normalize(const HrfBnDesc* d, const void* x, const double* stats, const float* weight,
                      const float* bias, float eps, float momentum, float* running_mean,
-                     float* running_var, float* save_mean, float* save_invstd, int32_t relu,
+                     float* running_var, float* save_mean, float* save_invstd, int32_t act,
                      void* y, void* stream) {
   if (int rc = bn_check(d)) return rc;
+  if (int rc = bn_act_check(act)) return rc;
   HRF_REQUIRE(x && stats && save_mean && save_invstd && y, HRF_EINVAL, "bn_normalize: null pointer");
   HRF_REQUIRE(!running_mean == !running_var, HRF_EINVAL, "bn_normalize: running_mean and running_var go together");
   HRF_REQUIRE(eps >= 0.f, HRF_EINVAL, "bn_normalize: eps");
@@ -1003,23 +1010,25 @@ int hrf_bn_normalize(const HrfBnDesc* d, const void* x, const double* stats, con
   k.save_mean = save_mean;
   k.save_invstd = save_invstd;
   if (d->dtype == HRF_F32)
-    return launch_bn_affine<float, COEF_FWD>(d->B, d->C, d->HW, x, nullptr, k, relu, y, (cudaStream_t)stream);
-  return launch_bn_affine<__nv_bfloat16, COEF_FWD>(d->B, d->C, d->HW, x, nullptr, k, relu, y, (cudaStream_t)stream);
+    return launch_bn_affine<float, COEF_FWD>(d->B, d->C, d->HW, x, nullptr, k, act, y, (cudaStream_t)stream);
+  return launch_bn_affine<__nv_bfloat16, COEF_FWD>(d->B, d->C, d->HW, x, nullptr, k, act, y, (cudaStream_t)stream);
 }
 int hrf_bn_bwd_dx(const HrfBnDesc* d, const void* x, const void* dy, const double* sums,
-                  const double* count, const float* weight, const float* mean, const float* invstd,
-                  void* dx, void* stream) {
+                  const double* count, const float* weight, const float* bias, int32_t act,
+                  const float* mean, const float* invstd, void* dx, void* stream) {
   if (int rc = bn_check(d)) return rc;
+  if (int rc = bn_act_check(act)) return rc;
   HRF_REQUIRE(x && dy && sums && count && mean && invstd && dx, HRF_EINVAL, "bn_bwd_dx: null pointer");
   BnCoef k{};
   k.sums = sums;
   k.count = count;
   k.weight = weight;
+  k.bias = bias;
   k.mean = mean;
   k.invstd = invstd;
   if (d->dtype == HRF_F32)
-    return launch_bn_affine<float, COEF_BWD>(d->B, d->C, d->HW, x, dy, k, 0, dx, (cudaStream_t)stream);
-  return launch_bn_affine<__nv_bfloat16, COEF_BWD>(d->B, d->C, d->HW, x, dy, k, 0, dx, (cudaStream_t)stream);
+    return launch_bn_affine<float, COEF_BWD>(d->B, d->C, d->HW, x, dy, k, act, dx, (cudaStream_t)stream);
+  return launch_bn_affine<__nv_bfloat16, COEF_BWD>(d->B, d->C, d->HW, x, dy, k, act, dx, (cudaStream_t)stream);
 }
 
 int hrf_selftest_umma(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t b_mn_major,

@@ -18,6 +18,12 @@
 //        (COEF_FWD also saves mean / invstd and updates the running statistics), so that a BN
 //        forward is 3 launches and nothing else on the host, a backward 3 more
 //
+// Fused activation (`act`: ReLU or exact GELU, the nn.ReLU / nn.GELU that follows the norm layer
+// at hrformer.py:267-282, hrnet.py:338-358, resnet.py:161-206): the forward applies it to the
+// normalised value in the same pass; the backward recomputes z = w * xhat + b from x and the
+// saved statistics and multiplies dy by act'(z) on the fly in both of its passes, so neither
+// the pre-activation tensor nor a separate activation pass ever exists in HBM.
+//
 // All three are pure streaming kernels: 16-byte loads, four in flight per thread, no reuse.
 // Deterministic: no atomics; the partial order is fixed by (b, chunk).
 #pragma once
@@ -27,6 +33,20 @@ namespace hrf {
 
 constexpr int kBnThreads = 256;
 constexpr int kBnVecPerThread = 4;
+
+enum { BN_ACT_NONE = 0, BN_ACT_RELU = 1, BN_ACT_GELU = 2 };
+__device__ __forceinline__ float bn_act(float z, int act) {
+  if (act == BN_ACT_RELU) return fmaxf(z, 0.f);
+  if (act == BN_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  return z;
+}
+// d act(z) / dz
+__device__ __forceinline__ float bn_act_grad(float z, int act) {
+  if (act == BN_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == BN_ACT_GELU)
+    return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.39894228040143268f * __expf(-0.5f * z * z);
+  return 1.f;
+}
 
 template <typename T>
 __device__ __forceinline__ float bn_to_float(T v) { return (float)v; }
@@ -79,7 +99,8 @@ __device__ __forceinline__ float2 bn_block_sum2(float a, float b, float2* red /*
 template <typename T, int VEC, bool BWD>
 __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
-                 const float* __restrict__ invstd, float2* __restrict__ part, int C, int HW,
+                 const float* __restrict__ invstd, const float* __restrict__ weight,
+                 const float* __restrict__ bias, int act, float2* __restrict__ part, int C, int HW,
                  FastDiv chunks_div) {
   constexpr int NV = kBnVecPerThread;
   constexpr int CH = kBnThreads * NV * VEC;
@@ -120,6 +141,7 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     if (threadIdx.x == 0) part[((size_t)b * chunks + chunk) * C + c] = make_float2(m, m2);
   } else {
     const float mu = __ldg(mean + c), is = __ldg(invstd + c);
+    const float za = (weight ? __ldg(weight + c) : 1.f) * is, zb = bias ? __ldg(bias + c) : 0.f;
     float g[NV][VEC];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -135,8 +157,10 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
       if (o < n) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          s0 += g[i][j];
-          s1 = fmaf(g[i][j], (v[i][j] - mu) * is, s1);
+          const float xc = v[i][j] - mu;
+          const float ge = act ? g[i][j] * bn_act_grad(fmaf(za, xc, zb), act) : g[i][j];
+          s0 += ge;
+          s1 = fmaf(ge, xc * is, s1);
         }
       }
     }
@@ -237,7 +261,7 @@ struct BnCoef {
 template <typename T, int VEC, bool TWO, int MODE>
 __global__ void __launch_bounds__(kBnThreads)
 bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef k,
-                 T* __restrict__ out, int C, int HW, FastDiv chunks_div, int relu) {
+                 T* __restrict__ out, int C, int HW, FastDiv chunks_div, int act) {
   static_assert(MODE != COEF_BWD || TWO, "the backward reads x and dy");
   static_assert(MODE != COEF_FWD || !TWO, "the forward reads x only");
   constexpr int NV = kBnVecPerThread;
@@ -260,13 +284,13 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef
   }
   // out = ka * (TWO ? dy : x - km) + kb * (x - km) + kc: centring x before the multiply keeps
   // the result exact to fp32 rounding when |mean| >> std
-  float ka, kb = 0.f, kc, km = 0.f;
+  float ka, kb = 0.f, kc, km = 0.f, kz = 0.f;
   if constexpr (MODE == COEF_GIVEN) {
     ka = __ldg(k.a + c);
     kc = __ldg(k.c0 + c);
     if constexpr (TWO) kb = __ldg(k.b + c);
   } else {
-    __shared__ float coef[4];
+    __shared__ float coef[5];
     if (threadIdx.x == 0) {
       const double w = k.weight ? (double)__ldg(k.weight + c) : 1.0;
       if constexpr (MODE == COEF_FWD) {
@@ -298,6 +322,7 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef
         coef[1] = (float)(-gs * invstd * mdyx);
         coef[2] = (float)(-gs * mdy);
         coef[3] = (float)mean;
+        coef[4] = k.bias ? __ldg(k.bias + c) : 0.f;     // z = gs * (x - mean) + bias
       }
     }
     __syncthreads();
@@ -305,6 +330,7 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef
     kb = coef[1];
     kc = coef[2];
     km = coef[3];
+    if constexpr (MODE == COEF_BWD) kz = coef[4];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -314,9 +340,14 @@ bn_affine_kernel(const T* __restrict__ x, const T* __restrict__ dy, const BnCoef
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const float xc = v[i][j] - km;
-        if constexpr (TWO) r[j] = fmaf(ka, g[i][j], fmaf(kb, xc, kc));
-        else r[j] = fmaf(ka, xc, kc);
-        if (relu) r[j] = fmaxf(r[j], 0.f);
+        if constexpr (MODE == COEF_BWD) {
+          const float ge = act ? g[i][j] * bn_act_grad(fmaf(ka, xc, kz), act) : g[i][j];
+          r[j] = fmaf(ka, ge, fmaf(kb, xc, kc));
+        } else {
+          if constexpr (TWO) r[j] = fmaf(ka, g[i][j], fmaf(kb, xc, kc));
+          else r[j] = fmaf(ka, xc, kc);
+          if (act) r[j] = bn_act(r[j], act);
+        }
       }
       bn_store<T, VEC>(out + base + o, r);
     }
@@ -347,18 +378,18 @@ static size_t bn_workspace_bytes(int B, int C, int HW) {
 
 template <typename T, bool BWD>
 static int launch_bn_reduce(int B, int C, int HW, const void* x, const void* dy, const float* mean,
-                            const float* invstd, double* sums, float* dweight, float* dbias, void* ws,
-                            cudaStream_t stream) {
+                            const float* invstd, const float* weight, const float* bias, int act,
+                            double* sums, float* dweight, float* dbias, void* ws, cudaStream_t stream) {
   const BnGeom g = bn_geom<T>(B, C, HW, x, dy, nullptr);
   HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
   const FastDiv cd(g.chunks);
   float2* part = reinterpret_cast<float2*>(ws);
   if (g.vec > 1)
     bn_reduce_kernel<T, 16 / (int)sizeof(T), BWD><<<(unsigned)g.blocks, kBnThreads, 0, stream>>>(
-        (const T*)x, (const T*)dy, mean, invstd, part, C, HW, cd);
+        (const T*)x, (const T*)dy, mean, invstd, weight, bias, act, part, C, HW, cd);
   else
     bn_reduce_kernel<T, 1, BWD><<<(unsigned)g.blocks, kBnThreads, 0, stream>>>(
-        (const T*)x, (const T*)dy, mean, invstd, part, C, HW, cd);
+        (const T*)x, (const T*)dy, mean, invstd, weight, bias, act, part, C, HW, cd);
   HRF_CUDA(cudaGetLastError());
   bn_finalize_kernel<BWD><<<ceil_div(C, 4), 128, 0, stream>>>(part, sums, C, HW, B * g.chunks,
                                                                g.chunks, g.chunk_elems, dweight, dbias);
@@ -369,7 +400,7 @@ static int launch_bn_reduce(int B, int C, int HW, const void* x, const void* dy,
 
 template <typename T, int MODE>
 static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy, const BnCoef& k,
-                            int relu, void* out, cudaStream_t stream) {
+                            int act, void* out, cudaStream_t stream) {
   const BnGeom g = bn_geom<T>(B, C, HW, x, dy, out);
   HRF_REQUIRE(g.blocks < (1ll << 31), HRF_EUNSUPPORTED, "bn: %lld blocks", g.blocks);
   const FastDiv cd(g.chunks);
@@ -381,9 +412,9 @@ static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy,
   if constexpr (MODE != COEF_FWD) {
     if (dy) {
       if (g.vec > 1)
-        bn_affine_kernel<T, V16, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, relu);
+        bn_affine_kernel<T, V16, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, act);
       else
-        bn_affine_kernel<T, 1, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, relu);
+        bn_affine_kernel<T, 1, true, MODE><<<grid, kBnThreads, 0, stream>>>(xp, dp, k, op, C, HW, cd, act);
       count_launch();
       HRF_CUDA(cudaGetLastError());
       return HRF_OK;
@@ -391,9 +422,9 @@ static int launch_bn_affine(int B, int C, int HW, const void* x, const void* dy,
   }
   if constexpr (MODE != COEF_BWD) {
     if (g.vec > 1)
-      bn_affine_kernel<T, V16, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, relu);
+      bn_affine_kernel<T, V16, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, act);
     else
-      bn_affine_kernel<T, 1, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, relu);
+      bn_affine_kernel<T, 1, false, MODE><<<grid, kBnThreads, 0, stream>>>(xp, nullptr, k, op, C, HW, cd, act);
     count_launch();
     HRF_CUDA(cudaGetLastError());
   }

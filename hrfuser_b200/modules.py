@@ -18,7 +18,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .bn_train import HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm, make_conv
+from .bn_train import (HrfBatchNorm2d, HrfLayerNorm, HrfSyncBatchNorm, NormActSequential, make_conv,
+                       norm_act)
 from .window_maps import relative_position_index, window_geometry
 
 
@@ -48,7 +49,7 @@ def conv_bn(cin, cout, k, stride, norm_cfg, relu, groups=1):
               make_norm(norm_cfg, cout)]
     if relu:
         layers.append(nn.ReLU(inplace=relu == 'inplace'))
-    return nn.Sequential(*layers)
+    return NormActSequential(*layers)
 
 
 class DropPath(nn.Module):
@@ -207,7 +208,7 @@ class CrossFFN(nn.Module):
 
     def __init__(self, cin, hidden, cout, norm_cfg):
         super().__init__()
-        self.layers = nn.Sequential(
+        self.layers = NormActSequential(
             nn.Conv2d(cin, hidden, 1), make_norm(norm_cfg, hidden), nn.GELU(),
             make_conv(hidden, hidden, 3, 1, 1, groups=hidden), make_norm(norm_cfg, hidden),
             nn.GELU(),
@@ -290,8 +291,8 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
+        y = norm_act(self.bn1, self.relu, self.conv1(x))
+        y = norm_act(self.bn2, self.relu, self.conv2(y))
         y = self.bn3(self.conv3(y))
         return self.relu(y + (x if self.downsample is None else self.downsample(x)))
 
@@ -354,7 +355,7 @@ class HRFormerModule(nn.Module):
                                 make_norm(norm_cfg, cout)]
                         if not last:
                             step.append(nn.ReLU(False))
-                        chain.append(nn.Sequential(*step))
+                        chain.append(NormActSequential(*step))
                     row.append(nn.Sequential(*chain))
             rows.append(nn.ModuleList(row))
         return nn.ModuleList(rows)

@@ -686,10 +686,15 @@ def bn_stats(x):
     return stats
 
 
+BN_ACT_NONE, BN_ACT_RELU, BN_ACT_GELU = 0, 1, 2
+
+
 def bn_normalize(x, stats, weight, bias, eps, momentum=0.0, running_mean=None, running_var=None,
-                 relu=False):
-    """y = BN(x) from the (all-reduced) `bn_stats` message; -> (y, mean, invstd); updates the
-    running statistics in place when given."""
+                 relu=False, act=BN_ACT_NONE):
+    """y = act(BN(x)) from the (all-reduced) `bn_stats` message; -> (y, mean, invstd); updates the
+    running statistics in place when given.  act: BN_ACT_NONE | BN_ACT_RELU | BN_ACT_GELU
+    (`relu=True` is BN_ACT_RELU)."""
+    act = BN_ACT_RELU if relu and not act else int(act)
     lib = _lib.load()
     d = _bn_desc(x)
     y = torch.empty_like(x)
@@ -700,13 +705,15 @@ def bn_normalize(x, stats, weight, bias, eps, momentum=0.0, running_mean=None, r
                                    _f32c(bias, 'bias'), float(eps), float(momentum),
                                    _f32c(running_mean, 'running_mean'),
                                    _f32c(running_var, 'running_var'), mean.data_ptr(),
-                                   invstd.data_ptr(), int(relu), y.data_ptr(), _stream()))
+                                   invstd.data_ptr(), act, y.data_ptr(), _stream()))
     return y, mean, invstd
 
 
-def bn_bwd_stats(x, dy, mean, invstd, want_param_grads=False):
+def bn_bwd_stats(x, dy, mean, invstd, want_param_grads=False, weight=None, bias=None, act=BN_ACT_NONE):
     """-> fp64 [2C]: per-channel sum(dy) | sum(dy * (x - mean) * invstd), and with
-    `want_param_grads` the fp32 (dweight, dbias) copies of the same (rank-local) numbers."""
+    `want_param_grads` the fp32 (dweight, dbias) copies of the same (rank-local) numbers.
+    With `act`, dy is the gradient of act(BN(x)) and is multiplied by act'(z) on the fly
+    (z recomputed from x, the statistics and weight / bias)."""
     lib = _lib.load()
     d = _bn_desc(x)
     _like_x(dy, x)
@@ -715,24 +722,26 @@ def bn_bwd_stats(x, dy, mean, invstd, want_param_grads=False):
     grads = torch.empty(2, d.C, dtype=torch.float32, device=x.device) if want_param_grads else None
     with _timed('bn_bwd_stats', C=d.C, bytes=2 * x.numel() * x.element_size(), flops=0.0):
         check(lib.hrf_bn_bwd_stats(C.byref(d), x.data_ptr(), dy.data_ptr(), _f32c(mean, 'mean'),
-                                   _f32c(invstd, 'invstd'), sums.data_ptr(),
+                                   _f32c(invstd, 'invstd'), _f32c(weight, 'weight'),
+                                   _f32c(bias, 'bias'), int(act), sums.data_ptr(),
                                    grads[0].data_ptr() if want_param_grads else None,
                                    grads[1].data_ptr() if want_param_grads else None,
                                    ws.data_ptr(), ws.numel(), _stream()))
     return (sums, grads[0], grads[1]) if want_param_grads else sums
 
 
-def bn_bwd_dx(x, dy, sums, count, weight, mean, invstd):
-    """dx of train-mode BN from the (all-reduced) `bn_bwd_stats` sums; `count` is the fp64
-    device scalar the forward message carried (stats[2C:])."""
+def bn_bwd_dx(x, dy, sums, count, weight, mean, invstd, bias=None, act=BN_ACT_NONE):
+    """dx of train-mode BN (followed by `act`) from the (all-reduced) `bn_bwd_stats` sums;
+    `count` is the fp64 device scalar the forward message carried (stats[2C:])."""
     lib = _lib.load()
     d = _bn_desc(x)
     _like_x(dy, x)
     dx = torch.empty_like(x)
     with _timed('bn_bwd_affine', C=d.C, bytes=3 * x.numel() * x.element_size(), flops=0.0):
         check(lib.hrf_bn_bwd_dx(C.byref(d), x.data_ptr(), dy.data_ptr(), sums.data_ptr(),
-                                count.data_ptr(), _f32c(weight, 'weight'), _f32c(mean, 'mean'),
-                                _f32c(invstd, 'invstd'), dx.data_ptr(), _stream()))
+                                count.data_ptr(), _f32c(weight, 'weight'), _f32c(bias, 'bias'),
+                                int(act), _f32c(mean, 'mean'), _f32c(invstd, 'invstd'),
+                                dx.data_ptr(), _stream()))
     return dx
 
 

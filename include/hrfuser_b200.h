@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HRF_ABI_VERSION 8
+#define HRF_ABI_VERSION 9
 
 enum { HRF_F32 = 0, HRF_BF16 = 1, HRF_U8 = 2 /* hrf_input_prologue_fwd source only */ };
 enum {
@@ -277,6 +277,12 @@ int hrf_bias_act_fwd(int64_t n_tokens, int32_t C, int32_t dtype, int32_t relu, v
  *                      weight / bias may be NULL (1 / 0).
  *   hrf_bn_bwd_dx:     dx = weight*invstd*(dy - sum_dy/n - xhat * sum_dy_xhat/n) from the
  *                      (reduced) sums; count points at the forward's stats[2C].
+ * Fused activation: `act` = HRF_BN_ACT_NONE | _RELU | _GELU (exact, erf) is the nn.ReLU /
+ * nn.GELU module that follows the norm layer (hrformer.py:267-282 MlpDWBN, hrnet.py:338-358,
+ * resnet.py:161-206).  hrf_bn_normalize returns act(BN(x)); the two backward calls take dy
+ * with respect to THAT output and multiply it by act'(z), z = weight * xhat + bias recomputed
+ * from x and the saved statistics (pass the same weight / bias / act to both); with act = 0
+ * weight / bias are not read by hrf_bn_bwd_stats.
  *   hrf_bn_affine:     out = a[c]*x + c0[c]  (dy == NULL)  or  a[c]*dy + b[c]*x + c0[c],
  *                      caller-supplied fp32 [C] coefficients.
  * out / y / dx may alias their inputs. */
@@ -284,19 +290,21 @@ typedef struct {
   int32_t B, C, HW;
   int32_t dtype;
 } HrfBnDesc;
+enum { HRF_BN_ACT_NONE = 0, HRF_BN_ACT_RELU = 1, HRF_BN_ACT_GELU = 2 };
 size_t hrf_bn_workspace_bytes(const HrfBnDesc* d);
 int hrf_bn_stats(const HrfBnDesc* d, const void* x, double* stats, void* workspace,
                  size_t workspace_bytes, void* stream);
 int hrf_bn_normalize(const HrfBnDesc* d, const void* x, const double* stats, const float* weight,
                      const float* bias, float eps, float momentum, float* running_mean,
-                     float* running_var, float* save_mean, float* save_invstd, int32_t relu,
+                     float* running_var, float* save_mean, float* save_invstd, int32_t act,
                      void* y, void* stream);
 int hrf_bn_bwd_stats(const HrfBnDesc* d, const void* x, const void* dy, const float* mean,
-                     const float* invstd, double* sums, float* dweight, float* dbias,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     const float* invstd, const float* weight, const float* bias, int32_t act,
+                     double* sums, float* dweight, float* dbias, void* workspace,
+                     size_t workspace_bytes, void* stream);
 int hrf_bn_bwd_dx(const HrfBnDesc* d, const void* x, const void* dy, const double* sums,
-                  const double* count, const float* weight, const float* mean,
-                  const float* invstd, void* dx, void* stream);
+                  const double* count, const float* weight, const float* bias, int32_t act,
+                  const float* mean, const float* invstd, void* dx, void* stream);
 int hrf_bn_affine(const HrfBnDesc* d, const void* x, const void* dy, const float* a,
                   const float* b, const float* c0, int32_t relu, void* out, void* stream);
 

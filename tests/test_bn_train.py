@@ -27,8 +27,27 @@ def _emul_stats(x):
     return torch.cat([xd.sum((0, 2)), (xd * xd).sum((0, 2)), n])
 
 
+def _act(z, act):
+    return z.relu() if act == 1 else torch.nn.functional.gelu(z) if act == 2 else z
+
+
+def _act_grad(z, act):
+    if act == 1:
+        return (z > 0).to(z.dtype)
+    if act == 2:
+        return 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
+    return torch.ones_like(z)
+
+
+def _emul_z(x, mean, invstd, weight, bias):
+    sh = (1, -1) + (1,) * (x.dim() - 2)
+    a = (weight.double() if weight is not None else 1.0) * invstd.double()
+    b = bias.double() if bias is not None else torch.zeros_like(mean, dtype=torch.float64)
+    return (x.double() - mean.double().view(sh)) * (a * torch.ones_like(b)).view(sh) + b.view(sh)
+
+
 def _emul_normalize(x, stats, weight, bias, eps, momentum=0.0, running_mean=None, running_var=None,
-                    relu=False):
+                    relu=False, act=0):
     C = x.shape[1]
     n = stats[2 * C]
     mean = stats[:C] / n
@@ -41,10 +60,12 @@ def _emul_normalize(x, stats, weight, bias, eps, momentum=0.0, running_mean=None
         running_var.mul_(1 - momentum).add_((momentum * var * n / (n - 1).clamp_min(1)).float())
     sh = (1, -1) + (1,) * (x.dim() - 2)
     y = ((x.double() - mean.view(sh)) * a.view(sh) + c0.view(sh)).to(x.dtype)
-    return (y.relu() if relu else y), mean.float(), invstd.float()
+    return _act(y, 1 if relu and not act else act), mean.float(), invstd.float()
 
 
-def _emul_bwd_stats(x, dy, mean, invstd, want_param_grads=False):
+def _emul_bwd_stats(x, dy, mean, invstd, want_param_grads=False, weight=None, bias=None, act=0):
+    if act:
+        dy = dy.double() * _act_grad(_emul_z(x, mean, invstd, weight, bias), act)
     xd, gd = x.double().flatten(2), dy.double().flatten(2)
     xhat = (xd - mean.double()[None, :, None]) * invstd.double()[None, :, None]
     sums = torch.cat([gd.sum((0, 2)), (gd * xhat).sum((0, 2))])
@@ -52,8 +73,10 @@ def _emul_bwd_stats(x, dy, mean, invstd, want_param_grads=False):
     return (sums, sums[C:].float(), sums[:C].float()) if want_param_grads else sums
 
 
-def _emul_bwd_dx(x, dy, sums, count, weight, mean, invstd):
+def _emul_bwd_dx(x, dy, sums, count, weight, mean, invstd, bias=None, act=0):
     C = x.shape[1]
+    if act:
+        dy = (dy.double() * _act_grad(_emul_z(x, mean, invstd, weight, bias), act)).to(dy.dtype)
     mdy, mdyx = sums[:C] / count, sums[C:] / count
     g = (weight.double() if weight is not None else 1.0) * invstd.double()
     kb = -g * invstd.double() * mdyx
@@ -90,6 +113,18 @@ def _torch_bn_reference(x, w, b, dy, eps=1e-5):
     return y.detach(), xr.grad, bn.weight.grad, bn.bias.grad, bn.running_mean, bn.running_var
 
 
+def _torch_bn_act_reference(x, w, b, dy, act, eps=1e-5):
+    """nn.BatchNorm2d followed by nn.ReLU / nn.GELU under torch autograd"""
+    bn = nn.BatchNorm2d(x.shape[1], eps=eps).to(x.device, x.dtype).train()
+    with torch.no_grad():
+        bn.weight.copy_(w)
+        bn.bias.copy_(b)
+    xr = x.clone().requires_grad_(True)
+    y = (nn.ReLU() if act == 1 else nn.GELU())(bn(xr))
+    y.backward(dy)
+    return y.detach(), xr.grad, bn.weight.grad, bn.bias.grad
+
+
 def _case(B, C, H, W, seed=0, device='cpu', offset=0.0):
     g = torch.Generator().manual_seed(seed)
     x = (torch.randn(B, C, H, W, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g))
@@ -112,6 +147,37 @@ def test_cpu_tensors_use_torch_batchnorm():
     m = make_norm(dict(type='BN'), 6).train()
     ref = nn.BatchNorm2d(6).train()
     assert torch.equal(m(x), ref(x))
+
+
+@pytest.mark.parametrize('act', [1, 2])
+def test_function_fused_activation_host_logic(emulated_kernels, act):
+    """y = act(BN(x)); the backward gets dy of THAT output and only x is saved"""
+    x, w, b, dy = _case(4, 10, 6, 9, seed=4)
+    y_ref, dx_ref, dw_ref, db_ref = _torch_bn_act_reference(x, w, b, dy, act)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = bn_train._BatchNormTrainFn.apply(xr, wr, br, None, None, 1e-5, 0.1, None, act)
+    y.backward(dy)
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(xr.grad, dx_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(wr.grad, dw_ref, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(br.grad, db_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_norm_act_sequential_keeps_names_and_cpu_semantics():
+    from hrfuser_b200.modules import CrossFFN, conv_bn
+    ffn = CrossFFN(18, 72, 18, dict(type='BN', requires_grad=True))
+    assert isinstance(ffn.layers, bn_train.NormActSequential)
+    keys = [k for k in ffn.state_dict() if k.endswith('weight')]
+    assert keys == [f'layers.{i}.weight' for i in (0, 1, 3, 4, 6, 7)]
+    seq = conv_bn(6, 8, 3, 1, dict(type='BN'), 'inplace').train()
+    x = torch.randn(2, 6, 9, 11)
+    ref = x
+    for m in seq:
+        ref = m(ref)
+    torch.manual_seed(0)
+    assert torch.equal(seq(x), ref)                           # CPU tensors: child-by-child walk
+    assert bn_train.act_code(nn.ReLU(True)) == 1 and bn_train.act_code(nn.GELU()) == 2
+    assert bn_train.act_code(nn.GELU(approximate='tanh')) is None and bn_train.act_code(nn.SiLU()) is None
 
 
 def test_function_host_logic_single_process(emulated_kernels):
@@ -194,6 +260,90 @@ GPU_SHAPES = [(2, 64, 192, 320),      # stem
               (2, 78, 96, 160),       # HRFuser-B
               (3, 18, 5, 7),          # HW % 4 != 0: scalar path
               (1, 7, 1, 1)]
+
+
+def _close_except_relu_ties(a, b, act, rtol, atol):
+    """assert_close, except that with ReLU a pre-activation within an ulp of zero may fall on
+    either side of the kink in two implementations.  One such element differs outright, and it
+    moves its channel's sum(dy) / sum(dy * xhat) by one dy: every dx of that channel shifts by
+    ~ w * invstd * dy / n (2e-5 at n = 1e5).  So: a 1e-5 fraction may differ outright, a few
+    channels' worth (3 %) may sit within atol + 1e-3."""
+    if act != 1:
+        return torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+    err, lim = (a - b).abs(), atol + rtol * b.abs()
+    outright = (err > lim + 1e-3).sum().item()
+    shifted = (err > lim).sum().item()
+    assert outright <= max(1, int(1e-5 * a.numel())), f'{outright} of {a.numel()} elements differ'
+    assert shifted <= max(1, int(3e-2 * a.numel())), f'{shifted} of {a.numel()} elements shifted'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('act', [1, 2])
+@pytest.mark.parametrize('shape', [(8, 72, 96, 160), (2, 312, 96, 160), (3, 18, 5, 7), (2, 64, 17, 24)])
+def test_gpu_fused_activation_kernels(shape, act):
+    """act(BN(x)) forward and backward in the BN kernels' own passes against nn.BatchNorm2d ->
+    nn.ReLU / nn.GELU under torch autograd (fp32), and against the fp64 emulation"""
+    x, w, b, dy = _case(*shape, seed=2, device='cuda')
+    y_ref, dx_ref, dw_ref, db_ref = _torch_bn_act_reference(x, w, b, dy, act)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    n0 = ops.launch_count()
+    y = bn_train._BatchNormTrainFn.apply(xr, wr, br, None, None, 1e-5, 0.1, None, act)
+    y.backward(dy)
+    assert ops.launch_count() - n0 == 6                          # 3 forward + 3 backward, nothing else
+    n = x.numel() / shape[1]
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    _close_except_relu_ties(xr.grad, dx_ref, act, rtol=1e-4, atol=2e-5)
+    tie = 8.0 if act == 1 else 0.0          # one element on the other side of the kink: +- dy * xhat
+    torch.testing.assert_close(wr.grad, dw_ref, rtol=1e-4, atol=2e-6 * n + 1e-3 + tie)
+    torch.testing.assert_close(br.grad, db_ref, rtol=1e-4, atol=2e-6 * n + 1e-3 + tie)
+    # bf16 planes
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    s = ops.bn_stats(xb)
+    yb, mean, invstd = ops.bn_normalize(xb, s, w, b, 1e-5, act=act)
+    y_e, mean_e, invstd_e = _emul_normalize(xb.float(), _emul_stats(xb), w, b, 1e-5, act=act)
+    torch.testing.assert_close(yb.float(), y_e, rtol=1e-2, atol=2e-2)
+    sb = ops.bn_bwd_stats(xb, dyb, mean_e, invstd_e, weight=w, bias=b, act=act)
+    sb_e = _emul_bwd_stats(xb, dyb, mean_e, invstd_e, weight=w, bias=b, act=act)
+    torch.testing.assert_close(sb, sb_e, rtol=1e-4, atol=2e-6 * n + 1e-3 + tie)
+    dxb = ops.bn_bwd_dx(xb, dyb, sb_e, s[2 * shape[1]:], w, mean_e, invstd_e, bias=b, act=act)
+    dx_e = _emul_bwd_dx(xb.float(), dyb.float(), sb_e, s[2 * shape[1]:], w, mean_e, invstd_e, bias=b, act=act)
+    _close_except_relu_ties(dxb.float(), dx_e, act, rtol=2e-2, atol=2e-2 * float(dx_e.abs().max()) + 1e-4)
+    with pytest.raises(RuntimeError, match='act'):
+        ops.bn_normalize(x, ops.bn_stats(x), w, b, 1e-5, act=3)
+
+
+@pytest.mark.gpu
+def test_gpu_norm_act_sequential_fuses_and_matches():
+    """CrossFFN / conv_bn / Bottleneck with the activation inside the BN kernels against the same
+    modules walking child by child (nn.GELU / nn.ReLU as separate torch ops)"""
+    from hrfuser_b200.modules import Bottleneck, CrossFFN, conv_bn
+    torch.manual_seed(0)
+    cfg = dict(type='BN', requires_grad=True)
+    cases = [(CrossFFN(18, 72, 18, cfg), (2, 40 * 56, 18), dict(H=40, W=56)),
+             (conv_bn(18, 36, 3, 2, cfg, 'inplace'), (2, 18, 40, 56), {}),
+             (Bottleneck(64, 16, cfg), (2, 64, 24, 40), {})]
+    for mod, shape, kw in cases:
+        mod = mod.cuda().train()
+        x = torch.randn(*shape, device='cuda')
+        res = []
+        for fuse in (True, False):
+            bn_train.NormActSequential.fuse_act = fuse
+            try:
+                mod.zero_grad(set_to_none=True)
+                xr = x.clone().requires_grad_(True)
+                n0 = ops.launch_count()
+                y = mod(xr, **kw)
+                y.square().mean().backward()
+                res.append((y.detach(), xr.grad, [p.grad.clone() for p in mod.parameters()],
+                            ops.launch_count() - n0))
+            finally:
+                bn_train.NormActSequential.fuse_act = True
+        (y1, g1, p1, l1), (y0, g0, p0, l0) = res
+        assert l1 == l0                                          # same kernels, the activations ride along
+        torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-5)
+        _close_except_relu_ties(g1, g0, 1, rtol=1e-3, atol=1e-6 + 1e-3 * float(g0.abs().max()))
+        for a, b in zip(p1, p0):
+            torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-6 + 1e-3 * float(b.abs().max()))
 
 
 @pytest.mark.gpu
