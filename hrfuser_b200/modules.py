@@ -233,12 +233,26 @@ class HRFormerBlock(nn.Module):
         self.ffn = CrossFFN(cin, int(cin * mlp_ratio), cout, norm_cfg)
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
 
+    def forward_tokens(self, t, H, W):
+        """the block on (B, H*W, C) tokens: consecutive blocks of a branch stay in this layout"""
+        t = t + self.drop_path(self.attn(self.norm1(t), None, H, W))
+        return t + self.drop_path(self.ffn(self.norm2(t), H, W))
+
     def forward(self, x):
         B, C, H, W = x.shape
-        t = _tokens(x)
-        t = t + self.drop_path(self.attn(self.norm1(t), None, H, W))
-        t = t + self.drop_path(self.ffn(self.norm2(t), H, W))
-        return _image(t, H, W).contiguous()
+        return _image(self.forward_tokens(_tokens(x), H, W), H, W).contiguous()
+
+
+def run_blocks(blocks, x):
+    """nn.Sequential of HRFormerBlocks on an NCHW map with ONE layout round trip for the whole
+    chain (the reference converts NCHW <-> tokens in every block, hrformer.py:365-373)"""
+    if not all(isinstance(b, HRFormerBlock) for b in blocks):
+        return blocks(x)
+    B, C, H, W = x.shape
+    t = _tokens(x)
+    for b in blocks:
+        t = b.forward_tokens(t, H, W)
+    return _image(t, H, W).contiguous()
 
 
 class HRFuserFusionBlock(nn.Module):
@@ -362,8 +376,8 @@ class HRFormerModule(nn.Module):
 
     def forward(self, xs):
         if self.num_branches == 1:
-            return [self.branches[0](xs[0])]
-        xs = [br(x) for br, x in zip(self.branches, xs)]
+            return [run_blocks(self.branches[0], xs[0])]
+        xs = [run_blocks(br, x) for br, x in zip(self.branches, xs)]
         outs = []
         for i, row in enumerate(self.fuse_layers):
             acc = xs[i]

@@ -13,7 +13,8 @@ CUDA graph over static input buffers:
     round trip per norm layer;
   * the gradients of all parameters that receive one are exchanged with ONE all-reduce over a
     flat bucket (sized for launch latency, not link count: NVSwitch gives every GPU full
-    bandwidth to every peer), averaged over the ranks as DDP does;
+    bandwidth to every peer), averaged over the ranks as DDP does; packed and unpacked with
+    multi-tensor kernels (cat / _foreach_copy_), not one launch per parameter;
   * parameters that receive no gradient (unused transitions of a config) are found during the
     eager warm-up steps, not per step.
 One process per GPU; `world == 1` captures the same graph without collectives.
@@ -33,12 +34,10 @@ def exchange_gradients(params, group, world):
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-    return off
+    # one multi-tensor copy back (a handful of launches), not one elementwise kernel per parameter:
+    # HRFuser-B has ~1 500 parameter tensors, the step is bound by its kernel count
+    torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
+    return flat.numel()
 
 
 class GraphedTrainStep:

@@ -56,3 +56,20 @@ s = sum(tot.values())
 print(f'{sum(cnt.values())} kernels, sum of durations {s / 1e3:.1f} ms')
 for n, t in tot.most_common(a.top):
     print(f'{t / 1e3:9.2f} ms {100 * t / s:5.1f}%  x{cnt[n]:<5d} {n}')
+
+# ---- the same step by the op that launched the kernels (autograd nodes / aten ops, self device time)
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof2:
+    step()
+    torch.cuda.synchronize()
+rows = []
+for k in prof2.key_averages():
+    t = getattr(k, 'self_device_time_total', None)
+    if t is None:
+        t = getattr(k, 'self_cuda_time_total', 0)
+    if t > 0:
+        rows.append((t, k.count, k.key))
+rows.sort(reverse=True)
+s2 = sum(r[0] for r in rows)
+print(f'\nby op (self device time), total {s2 / 1e3:.1f} ms')
+for t, n, key in rows[:a.top]:
+    print(f'{t / 1e3:9.2f} ms {100 * t / s2:5.1f}%  x{n:<5d} {key[:90]}')
