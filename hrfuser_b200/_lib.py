@@ -105,6 +105,8 @@ SIGNATURES = {
     'hrf_convgemm_fwd': (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     'hrf_convgemm_grouped_fwd': (C.c_int, [C.POINTER(ConvGemmDesc), C.c_int32, _VPP, _VPP, _VPP, _VPP, C.c_void_p]),
+    'hrf_convgemm_grouped_cat_fwd': (C.c_int, [C.POINTER(ConvGemmDesc), C.c_int32, _VPP, _VPP, C.c_int32, _VPP, _VPP,
+                                              C.c_void_p]),
     'hrf_dwpw_blob_floats': (C.c_size_t, [C.POINTER(DwPwDesc)]),
     'hrf_dwpw_pack': (C.c_int, [C.POINTER(DwPwDesc), _F, _FP4, _F, _FP4, C.c_float, _F]),
     'hrf_dwpw_fwd': (C.c_int, [C.POINTER(DwPwDesc), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -709,10 +709,20 @@ int hrf_convgemm_pack(const HrfConvGemmDesc* d, const float* w, const float* bia
   }
   return HRF_OK;
 }
-int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs, const void* const* resids,
-                             const float* const* blobs, void* const* outs, void* stream) {
+static int convgemm_launch(const HrfConvGemmDesc* d, int32_t n, const void* const* xs, const void* const* xs2,
+                           int32_t cin1, const void* const* resids, const float* const* blobs, void* const* outs,
+                           void* stream) {
   int rc = hrf_convgemm_supported(d);
   if (rc) return rc;
+  if (xs2) {
+    HRF_REQUIRE(d->ksize == 1 && d->stride == 1 && !resids, HRF_EUNSUPPORTED,
+                "convgemm_cat_fwd: 1x1, stride 1, no residual");
+    HRF_REQUIRE(cin1 > 0 && cin1 < d->Cin && cin1 % 64 == 0, HRF_EUNSUPPORTED,
+                "convgemm_cat_fwd: cin1=%d of Cin=%d (both parts multiples of 64)", cin1, d->Cin);
+    for (int q = 0; q < n; ++q)
+      HRF_REQUIRE(xs2[q] && xs2[q] != outs[q] && (reinterpret_cast<uintptr_t>(xs2[q]) & 15) == 0, HRF_EINVAL,
+                  "convgemm_cat_fwd: x2 null, aliasing out or not 16-byte aligned (problem %d)", q);
+  }
   HRF_REQUIRE(n >= 1 && n <= kMaxProb, HRF_EINVAL, "convgemm_fwd: 1..%d problems per launch, %d given", kMaxProb, n);
   HRF_REQUIRE(xs && blobs && outs, HRF_EINVAL, "convgemm_fwd: null pointer");
   ConvGemmParams p{};
@@ -739,11 +749,20 @@ int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* co
   p.d_tiles_w = FastDiv(p.tiles_w);
   cudaStream_t st = (cudaStream_t)stream;
   switch (ConvGemmLayout(d->Cin, d->Cout, p.taps).NPAD) {
-    case 32: return launch_conv_gemm_n<32>(p, xs, d->H, d->W, d->stride, st);
-    case 64: return launch_conv_gemm_n<64>(p, xs, d->H, d->W, d->stride, st);
-    case 128: return launch_conv_gemm_n<128>(p, xs, d->H, d->W, d->stride, st);
-    default: return launch_conv_gemm_n<256>(p, xs, d->H, d->W, d->stride, st);
+    case 32: return launch_conv_gemm_n<32>(p, xs, xs2, cin1, d->H, d->W, d->stride, st);
+    case 64: return launch_conv_gemm_n<64>(p, xs, xs2, cin1, d->H, d->W, d->stride, st);
+    case 128: return launch_conv_gemm_n<128>(p, xs, xs2, cin1, d->H, d->W, d->stride, st);
+    default: return launch_conv_gemm_n<256>(p, xs, xs2, cin1, d->H, d->W, d->stride, st);
   }
+}
+int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs, const void* const* resids,
+                             const float* const* blobs, void* const* outs, void* stream) {
+  return convgemm_launch(d, n, xs, nullptr, 0, resids, blobs, outs, stream);
+}
+int hrf_convgemm_grouped_cat_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs, const void* const* xs2,
+                                 int32_t cin1, const float* const* blobs, void* const* outs, void* stream) {
+  HRF_REQUIRE(xs2, HRF_EINVAL, "convgemm_cat_fwd: null pointer");
+  return convgemm_launch(d, n, xs, xs2, cin1, nullptr, blobs, outs, stream);
 }
 int hrf_convgemm_fwd(const HrfConvGemmDesc* d, const void* x, const void* resid, const float* blob, void* out,
                      void* stream) {

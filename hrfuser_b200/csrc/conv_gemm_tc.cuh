@@ -75,6 +75,8 @@ struct ConvGemmParams {
   int B, Ho, Wo, Cin, Cout, taps, relu, stride;   // relu: bit q = ReLU on problem q
   int tiles_w, tiles_h, n_tiles;    // n_tiles: per problem
   int n_stages, tiles_per_cta;      // RR mode: ring depth (runtime), contiguous tile range per CTA
+  int kc_split;                     // > 0: K chunks >= kc_split come from a SECOND activation tensor
+                                    // (maps.r), i.e. the conv of the concatenation [x | x2] (1x1 only)
   FastDiv d_tiles_prob, d_tiles_img, d_tiles_w;
 };
 struct ConvGemmMaps {               // 4 x 4 tensor maps = 2 KB of kernel parameters
@@ -219,7 +221,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
           unsigned char* a = sm + s * STAGE_B;
           mbar_expect_tx(&full[s], cg::A_BYTES + K::B_BYTES);
-          cg::tma_load_4d(a, &tm.x[pr], c0, w0 * p.stride + dx, h0 * p.stride + dy, b, &full[s]);
+          const bool second = p.kc_split > 0 && k >= p.kc_split;      // taps == 1: k is the chunk
+          cg::tma_load_4d(a, second ? &tm.r[pr] : &tm.x[pr], second ? c0 - p.kc_split * 64 : c0,
+                          w0 * p.stride + dx, h0 * p.stride + dy, b, &full[s]);
           tma_load_3d(a + cg::A_BYTES, &tm.w[pr], c0, 0, tap, &full[s]);
         }
         }
@@ -430,7 +434,8 @@ static bool conv_rr_enabled() {
 }
 
 template <int NPAD>
-static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, int Wi, int stride, cudaStream_t stream) {
+static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const void* const* xs2, int cin1, int Hi,
+                              int Wi, int stride, cudaStream_t stream) {
   using K = ConvGemmCfg<NPAD>;
   // row-reuse mode: 3x3, stride 1, the layer's weights + at least two ring stages fit
   const int wres = 9 * (p.Cin / 64) * K::B_BYTES;
@@ -441,17 +446,21 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, i
   HRF_REQUIRE(enc != nullptr, HRF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   ConvGemmMaps tm;
   const bool staged = K::NSUB > 0 && p.Cout == NPAD;
+  p.kc_split = xs2 ? cin1 / 64 : 0;
+  // activations [B][Hi][Wi][C] bf16 as (C, Wi, Hi, B); a stride-2 convolution steps over every
+  // second token / row (element strides), so its coordinates stay in INPUT units
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int Cx) -> CUresult {
+    const cuuint64_t gdim[4] = {(cuuint64_t)Cx, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)p.B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)Cx * 2, (cuuint64_t)Wi * Cx * 2, (cuuint64_t)Hi * Wi * Cx * 2};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)((rr ? cg::TM_H + 2 : cg::TM_H) * stride), 1u};
+    const cuuint32_t est[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, est,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
   for (int q = 0; q < p.n_prob; ++q) {
     {
-      // activations [B][Hi][Wi][Cin] bf16 as (Cin, Wi, Hi, B); a stride-2 convolution steps over
-      // every second token / row (element strides), so its coordinates stay in INPUT units
-      const cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)p.B};
-      const cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)Wi * p.Cin * 2, (cuuint64_t)Hi * Wi * p.Cin * 2};
-      const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)((rr ? cg::TM_H + 2 : cg::TM_H) * stride), 1u};
-      const cuuint32_t est[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
-      const CUresult r = enc(&tm.x[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[q]), gdim, gstr, box,
-                             est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      const CUresult r = act_map(&tm.x[q], xs[q], xs2 ? cin1 : p.Cin);
       HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: activation tensor map failed (%d)", (int)r);
     }
     {
@@ -482,6 +491,10 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, int Hi, i
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: residual tensor map failed (%d)", (int)r);
       }
+    }
+    if (xs2) {                                          // second K source rides in the residual's map slot
+      const CUresult r = act_map(&tm.r[q], xs2[q], p.Cin - cin1);
+      HRF_REQUIRE(r == CUDA_SUCCESS, HRF_ECUDA, "conv_gemm: second activation tensor map failed (%d)", (int)r);
     }
   }
   for (int q = p.n_prob; q < kMaxProb; ++q) { tm.x[q] = tm.x[0]; tm.w[q] = tm.w[0]; tm.c[q] = tm.c[0]; tm.r[q] = tm.r[0]; }

@@ -138,10 +138,37 @@ class _Bottleneck:
         self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra, engine=engine)
         if not self.c3.tc and extra is not None:
             self.c3 = _Conv(m.conv3, m.bn3, True, dtype, extra_bias=extra.to(dtype))
+        # conv3 and the downsample conv are both 1x1 convs into the same sum: ONE GEMM over the
+        # concatenated K = planes + inplanes (hrf_convgemm_grouped_cat_fwd); the downsample map
+        # (63 MB per stream at 96 x 160 x 8) is never written or re-read.  HRF_CONV_CAT=0: two launches
+        self.cat = None
+        d = m.downsample[0] if m.downsample is not None else None
+        if (d is not None and self.c3.tc and self.down.tc and d.kernel_size == (1, 1) and d.stride == (1, 1) and
+                m.conv3.in_channels % 64 == 0 and d.in_channels % 64 == 0 and
+                os.environ.get('HRF_CONV_CAT', '1') != '0'):
+            w3, b3 = _fold_conv_bn(m.conv3, m.bn3, torch.float32)
+            wd, bd = _fold_conv_bn(d, m.downsample[1], torch.float32)
+            both = nn.Conv2d(m.conv3.in_channels + d.in_channels, m.conv3.out_channels, 1, bias=True)
+            with torch.no_grad():
+                both.weight.copy_(torch.cat([w3, wd], 1))
+                both.bias.copy_(b3 + bd)
+            both = both.to(m.conv3.weight.device)
+            self.cat = _Conv(both, None, True, dtype, engine=engine)
+            self.cat.cin1 = m.conv3.in_channels
 
     def __call__(self, x):
+        if self.cat is not None:
+            return run_cat([self.cat], [self.c2(self.c1(x))], [x])[0]
         idt = x if self.down is None else self.down(x)
         return self.c3(self.c2(self.c1(x)), residual=idt)
+
+
+def run_cat(convs, ys, xs):
+    """relu(conv3(y) + downsample(x)) of one layer of n streams as one concatenated-K GEMM launch"""
+    tok = BackboneEngine._tokens
+    outs = ops.conv_gemm_cat_grouped([tok(y) for y in ys], [tok(x) for x in xs], [c.blob.t for c in convs],
+                                     convs[0].cout, [c.relu for c in convs])
+    return [BackboneEngine._image(o) for o in outs]
 
 
 class BackboneEngine:
@@ -463,6 +490,11 @@ class BackboneEngine:
         ys = self._conv_group([c[1] for c in chains], ys)
         for j in range(2, len(chains[0])):
             bs = [c[j] for c in chains]
+            if all(b.cat is not None for b in bs) and all(tuple(y.shape) == tuple(ys[0].shape) for y in ys):
+                t = self._conv_group([b.c1 for b in bs], ys)
+                t = self._conv_group([b.c2 for b in bs], t)
+                ys = run_cat([b.cat for b in bs], t, ys)
+                continue
             idt = ys if bs[0].down is None else self._conv_group([b.down for b in bs], ys)
             t = self._conv_group([b.c1 for b in bs], ys)
             t = self._conv_group([b.c2 for b in bs], t)

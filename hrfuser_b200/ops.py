@@ -241,6 +241,33 @@ def conv_gemm_grouped(xs, blobs, cout, ksize, stride=1, relu=False, residuals=No
     return outs
 
 
+def conv_gemm_cat_grouped(xs, xs2, blobs, cout, relu=False):
+    """1x1 conv of the channel concatenation [x | x2] (never materialised) on several tensors in
+    one launch (hrf_convgemm_grouped_cat_fwd): Bottleneck conv3 + downsample as ONE GEMM."""
+    lib = _lib.load()
+    n = len(xs)
+    for x, x2 in zip(xs, xs2):
+        _check_act(x)
+        _check_act(x2)
+        if (x.dtype != torch.bfloat16 or x2.dtype != torch.bfloat16 or tuple(x.shape) != tuple(xs[0].shape) or
+                tuple(x2.shape) != tuple(xs2[0].shape) or x.shape[:3] != x2.shape[:3]):
+            raise ValueError('conv_gemm_cat_grouped: bf16 tensors, one shape per source, same B / H / W')
+    B, H, W, c1 = xs[0].shape
+    cin = c1 + xs2[0].shape[3]
+    outs = [x.new_empty(B, H, W, cout) for x in xs]
+    mask = sum(1 << q for q, r in enumerate(relu) if r) if isinstance(relu, (list, tuple)) else \
+        ((1 << n) - 1 if relu else 0)
+    d = ConvGemmDesc(B, H, W, cin, cout, 1, 1, mask)
+    VP = C.c_void_p * n
+    no = B * H * W
+    with _timed('convgemm', C=cin, launches=1, bytes=float(n * no * (cin + cout) * 2),
+                flops=float(n * 2 * no * cin * cout)):
+        check(lib.hrf_convgemm_grouped_cat_fwd(
+            C.byref(d), n, VP(*[x.data_ptr() for x in xs]), VP(*[x.data_ptr() for x in xs2]), c1,
+            VP(*[b.data_ptr() for b in blobs]), VP(*[o.data_ptr() for o in outs]), _stream()))
+    return outs
+
+
 def pack_dwpw(conv_dw, bn_dw, conv_pw, bn_pw, bn_eps=1e-5):
     lib = _lib.load()
     cout, cin = conv_pw.weight.shape[:2]

@@ -217,6 +217,15 @@ int hrf_convgemm_fwd(const HrfConvGemmDesc* d, const void* x, const void* resid,
 int hrf_convgemm_grouped_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs,
                              const void* const* resids, const float* const* blobs,
                              void* const* outs, void* stream);
+/* The 1x1 convolution of the channel concatenation [x | x2] (x: cin1 channels, x2: d->Cin - cin1;
+ * both multiples of 64) without materialising it: the K loop takes its first cin1 / 64 chunks
+ * from x, the rest from x2.  A Bottleneck's conv3 and its downsample branch
+ * (resnet.py:263-302: out = relu(bn3(conv3(y)) + downsample(x))) are ONE GEMM this way, weights
+ * [W3 * s3 | Wd * sd] and bias b3 + bd folded by the caller: the downsample map is never written
+ * or re-read and the sum stays in the fp32 accumulator.  ksize 1, stride 1, no residual. */
+int hrf_convgemm_grouped_cat_fwd(const HrfConvGemmDesc* d, int32_t n, const void* const* xs,
+                                 const void* const* xs2, int32_t cin1, const float* const* blobs,
+                                 void* const* outs, void* stream);
 
 #define HRF_MAX_FUSE_TERMS 4
 typedef struct HrfFuseDesc {    /* out = ReLU(x + sum_j bilinear_up(up_j) + sum_j same_j) */

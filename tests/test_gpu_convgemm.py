@@ -97,3 +97,43 @@ def test_convgemm_grouped(built_lib, cin, cout, k, stride, resid):
     assert ops.launch_count() - n0 == 1
     for q in range(n):
         assert_parity(got[q], refs[q], 'bf16', f'grouped convgemm problem {q} {cin}->{cout}')
+
+
+@pytest.mark.parametrize('c1,c2,cout,B,H,W,n', [(64, 64, 256, 2, 96, 160, 3), (64, 64, 256, 1, 13, 21, 1),
+                                                (64, 128, 128, 2, 24, 40, 2), (128, 64, 64, 1, 8, 16, 4)])
+def test_convgemm_cat(built_lib, c1, c2, cout, B, H, W, n):
+    """relu(bn3(conv3(y)) + bn_d(downsample(x))) (reference resnet.py:263-302) as ONE GEMM over
+    the concatenated K = [y | x] (hrf_convgemm_grouped_cat_fwd), n streams in one launch, against
+    the two convolutions in fp32 on the same bf16-rounded operands."""
+    from hrfuser_b200 import ops
+    ys, xs, blobs, refs = [], [], [], []
+    relus = [q != 1 for q in range(n)]
+    for q in range(n):
+        torch.manual_seed(7 * q + c1 + cout + H)
+        conv3, bn3 = nn.Conv2d(c1, cout, 1, bias=False), nn.BatchNorm2d(cout)
+        down, bnd = nn.Conv2d(c2, cout, 1, bias=False), nn.BatchNorm2d(cout)
+        randomize_parameters(nn.Sequential(conv3, bn3, down, bnd), 5 * q + 2)
+        bn3.eval(), bnd.eval()
+        with torch.no_grad():
+            s3 = bn3.weight / torch.sqrt(bn3.running_var + bn3.eps)
+            sd = bnd.weight / torch.sqrt(bnd.running_var + bnd.eps)
+            both = nn.Conv2d(c1 + c2, cout, 1, bias=True)
+            both.weight.copy_(torch.cat([conv3.weight * s3.view(-1, 1, 1, 1), down.weight * sd.view(-1, 1, 1, 1)], 1))
+            both.bias.copy_(bn3.bias - bn3.running_mean * s3 + bnd.bias - bnd.running_mean * sd)
+        blobs.append(ops.pack_convgemm(both, None).cuda())
+        y = (torch.randn(B, H, W, c1) * 1.5).to(torch.bfloat16)
+        x = (torch.randn(B, H, W, c2) * 1.5).to(torch.bfloat16)
+        with torch.no_grad():
+            ref = (bn3(conv3(y.float().permute(0, 3, 1, 2))) + bnd(down(x.float().permute(0, 3, 1, 2)))).permute(0, 2, 3, 1)
+        refs.append(ref.relu() if relus[q] else ref)
+        ys.append(y.cuda())
+        xs.append(x.cuda())
+    n0 = ops.launch_count()
+    got = ops.conv_gemm_cat_grouped(ys, xs, blobs, cout, relus)
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 1
+    for q in range(n):
+        assert tuple(got[q].shape) == (B, H, W, cout)
+        assert_parity(got[q], refs[q], 'bf16', f'cat convgemm problem {q} {c1}+{c2}->{cout}')
+    with pytest.raises(RuntimeError):                    # 32 + c2 channels: not chunks of 64
+        ops.conv_gemm_cat_grouped([ys[0][..., :32].contiguous()], [xs[0]], blobs[:1], cout, True)
