@@ -89,6 +89,12 @@ constexpr int A_BYTES = 128 * 128;                    // 128 tokens x 64 channel
 constexpr int A_RR_BYTES = (TM_H + 2) * TM_W * 128;   // row-reuse box: 10 rows x 16 tokens x 64 channels
 constexpr int MAXST = 8;
 constexpr int NT = 192;
+// halo mode: the M tile is 16 rows x 8 tokens; ONE box of 18 rows x 10 tokens x 64 channels per K
+// chunk feeds all nine taps (tap (dy, dx) starts (dy * 10 + dx) tokens into the box)
+constexpr int HALO_TH = 16, HALO_TW = 8;
+constexpr int HALO_PITCH = (HALO_TW + 2) * 128;                // bytes between image rows of the box
+constexpr int HALO_BOX = (HALO_TH + 2) * HALO_PITCH;           // 23 040 bytes landed per box
+constexpr int HALO_STAGE = (HALO_BOX + 1023) / 1024 * 1024;    // ring stride: stages stay 1024-byte aligned
 
 // shared-memory descriptor of a 128-byte-swizzled K-major operand tile (rows of 128 bytes, 8-row
 // groups 1024 bytes apart), K step `ks` (16 elements = 32 bytes) -- sm_100 descriptor version 1,
@@ -99,6 +105,19 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, int ks) {
   d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                             // descriptor version
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// the same with a start address that is any multiple of 128 bytes and any 8-row-group stride:
+// the hardware applies the 128-byte-swizzle XOR to ABSOLUTE shared-memory address bits (7..9 into
+// 4..6), exactly as TMA wrote the box, so a row-granular shift and a 1 280-byte group stride read
+// the right rows with base_offset = 0 (tools/probes/swz_probe.cu, measured on B200)
+__device__ __forceinline__ uint64_t desc_sw128_sbo(uint32_t saddr, int ks, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)(((saddr + (uint32_t)ks * 32u) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 
@@ -129,13 +148,17 @@ struct ConvGemmCfg {
   static_assert(SMEM + kMaxProb * NPAD * 4 + 1024 <= 227 * 1024, "dynamic + static shared memory");
 };
 
-template <int NPAD, bool RR>
+// MODE 0: plain (activation tile + weight tile per K step); 1: row reuse (RR); 2: halo box (HALO).
+// RR and HALO keep the layer's weights resident and walk contiguous tile ranges.
+template <int NPAD, int MODE>
 __global__ void __launch_bounds__(cg::NT, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ ConvGemmMaps tm) {
   using namespace umma;
   using K = ConvGemmCfg<NPAD>;
-  const int STAGES = RR ? p.n_stages : K::STAGES;
-  constexpr int STAGE_B = RR ? cg::A_RR_BYTES : K::STAGE;
+  constexpr bool RR = MODE == 1, HALO = MODE == 2, RES = MODE != 0;
+  constexpr int TH = HALO ? cg::HALO_TH : cg::TM_H, TW = HALO ? cg::HALO_TW : cg::TM_W;   // the 128-token M tile
+  const int STAGES = RES ? p.n_stages : K::STAGES;
+  constexpr int STAGE_B = RR ? cg::A_RR_BYTES : HALO ? cg::HALO_STAGE : K::STAGE;
   extern __shared__ unsigned char sm_raw[];
   constexpr int NSLOT = K::NSLOT > 0 ? K::NSLOT : 1, NSUB = K::NSUB;
   __shared__ __align__(8) uint64_t full[cg::MAXST], empty[cg::MAXST], acc_full[2], acc_empty[2], w_full;
@@ -147,7 +170,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   // operand tiles need 1024-byte alignment (128-byte swizzle atom = 8 rows x 128 bytes)
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
-  const int kc = p.Cin / 64, n_k = RR ? 3 * kc : p.taps * kc;
+  const int kc = p.Cin / 64, n_k = RR ? 3 * kc : HALO ? kc : p.taps * kc;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -175,9 +198,9 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   unsigned char* c_slots = sm + STAGES * STAGE_B;
   unsigned char* w_res = c_slots + K::C_BYTES;       // RR: the layer's weights, resident
   // tiles of this CTA: strided over the grid, or (RR) one contiguous range
-  const int t_begin = RR ? blockIdx.x * p.tiles_per_cta : blockIdx.x;
-  const int t_step = RR ? 1 : gridDim.x;
-  const int t_end = RR ? (t_begin + p.tiles_per_cta < total_tiles ? t_begin + p.tiles_per_cta : total_tiles) : total_tiles;
+  const int t_begin = RES ? blockIdx.x * p.tiles_per_cta : blockIdx.x;
+  const int t_step = RES ? 1 : gridDim.x;
+  const int t_end = RES ? (t_begin + p.tiles_per_cta < total_tiles ? t_begin + p.tiles_per_cta : total_tiles) : total_tiles;
   for (int e = tid; e < p.n_prob * NPAD; e += cg::NT) s_bias[e] = __ldg(p.blob[e / NPAD] + (e % NPAD));
   if (warp == 1) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   tc_fence_before();
@@ -195,8 +218,8 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         p.d_tiles_prob.divmod(tile, pr, tl);
         p.d_tiles_img.divmod(tl, b, rem);
         p.d_tiles_w.divmod(rem, ty, tx);
-        const int h0 = ty * cg::TM_H, w0 = tx * cg::TM_W;
-        if constexpr (RR) {
+        const int h0 = ty * TH, w0 = tx * TW;
+        if constexpr (RES) {
           if (pr != cur_pr) {
             // (re)load the resident weights; the MMAs of the previous problem's tiles must have
             // read the old ones: the commit behind the last stage issued covers all of them
@@ -209,9 +232,14 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           for (int k = 0; k < n_k; ++k, ++it) {
             const int s = it % STAGES;
             if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1, 200 + s);
-            const int dxi = k / kc, c0 = (k - dxi * kc) * 64;
-            mbar_expect_tx(&full[s], cg::A_RR_BYTES);
-            cg::tma_load_4d(sm + s * STAGE_B, &tm.x[pr], c0, w0 + dxi - 1, h0 - 1, b, &full[s]);
+            if constexpr (HALO) {                   // k = channel chunk: the whole 18 x 10 halo box
+              mbar_expect_tx(&full[s], cg::HALO_BOX);
+              cg::tma_load_4d(sm + s * STAGE_B, &tm.x[pr], k * 64, w0 - 1, h0 - 1, b, &full[s]);
+            } else {
+              const int dxi = k / kc, c0 = (k - dxi * kc) * 64;
+              mbar_expect_tx(&full[s], cg::A_RR_BYTES);
+              cg::tma_load_4d(sm + s * STAGE_B, &tm.x[pr], c0, w0 + dxi - 1, h0 - 1, b, &full[s]);
+            }
           }
         } else {
         for (int k = 0; k < n_k; ++k, ++it) {
@@ -245,7 +273,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     int it = 0, tcount = 0, cur_pr = -1, wcount = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       const int acc = tcount & 1;
-      if constexpr (RR) {
+      if constexpr (RES) {
         const int pr = p.d_tiles_prob.div(tile);
         if (pr != cur_pr) {                           // this problem's weights have landed
           mbar_wait(&w_full, wcount & 1, 280);
@@ -261,7 +289,17 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a = smem_u32(sm + s * STAGE_B);
-          if constexpr (RR) {
+          if constexpr (HALO) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t at = a + (uint32_t)((tap / 3) * cg::HALO_PITCH + (tap % 3) * 128);
+              const uint32_t bq = smem_u32(w_res) + (uint32_t)((tap * kc + k) * K::B_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16(tmem + acc * NPAD, cg::desc_sw128_sbo(at, ks, cg::HALO_PITCH), cg::desc_sw128(bq, ks), idesc,
+                         (k | tap | ks) != 0);
+            }
+          } else if constexpr (RR) {
             const int dxi = k / kc, c = k - dxi * kc;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
@@ -287,7 +325,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     // ===== epilogue warps ==========================================================================
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;                    // token of the tile
-    const int hh = row >> 4, ww = row & 15;
+    const int hh = row / TW, ww = row % TW;
     int tcount = 0, cit = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       const int acc = tcount & 1;
@@ -299,7 +337,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out[pr]);
       const float* bias = s_bias + pr * NPAD;
       const bool relu = (p.relu >> pr) & 1;
-      const int h = ty * cg::TM_H + hh, w = tx * cg::TM_W + ww;
+      const int h = ty * TH + hh, w = tx * TW + ww;
       const bool live = h < p.Ho && w < p.Wo;
       const size_t tok = ((size_t)(b * p.Ho + (live ? h : 0)) * p.Wo + (live ? w : 0)) * p.Cout;
       mbar_wait(&acc_full[acc], (tcount >> 1) & 1, 230 + acc);
@@ -348,7 +386,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
           if (warp == 2 && elect_one()) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(&tm.c[pr]), "r"(smem_u32(slot)), "r"(j * 64), "r"(tx * cg::TM_W), "r"(ty * cg::TM_H), "r"(b)
+                         ::"l"(&tm.c[pr]), "r"(smem_u32(slot)), "r"(j * 64), "r"(tx * TW), "r"(ty * TH), "r"(b)
                          : "memory");
             tma_store_commit();
             if (cit >= 1) {                                     // the PREVIOUS slot's store has read its data
@@ -433,6 +471,12 @@ static bool conv_rr_enabled() {
   return !(e && e[0] == '0');
 }
 
+// HRF_CONV_HALO=0 keeps the row-reuse mode for them (A/B runs)
+static bool conv_halo_enabled() {
+  const char* e = std::getenv("HRF_CONV_HALO");
+  return !(e && e[0] == '0');
+}
+
 template <int NPAD>
 static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const void* const* xs2, int cin1, int Hi,
                               int Wi, int stride, cudaStream_t stream) {
@@ -440,8 +484,19 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
   // row-reuse mode: 3x3, stride 1, the layer's weights + at least two ring stages fit
   const int wres = 9 * (p.Cin / 64) * K::B_BYTES;
   const int room = 218 * 1024 - K::C_BYTES - wres;
-  const bool rr = p.taps == 9 && stride == 1 && room >= 2 * cg::A_RR_BYTES && conv_rr_enabled();
-  p.n_stages = rr ? (room / cg::A_RR_BYTES > cg::MAXST ? cg::MAXST : room / cg::A_RR_BYTES) : K::STAGES;
+  // halo mode: the same layers, one 18 x 10 box per channel chunk for all nine taps (2.6x less
+  // L2 -> shared-memory traffic than the three 10 x 16 boxes of the row-reuse mode)
+  const bool halo = p.taps == 9 && stride == 1 && room >= 2 * cg::HALO_STAGE && conv_rr_enabled() && conv_halo_enabled();
+  const bool rr = !halo && p.taps == 9 && stride == 1 && room >= 2 * cg::A_RR_BYTES && conv_rr_enabled();
+  const int res_stage = halo ? cg::HALO_STAGE : cg::A_RR_BYTES;
+  p.n_stages = (halo || rr) ? (room / res_stage > cg::MAXST ? cg::MAXST : room / res_stage) : K::STAGES;
+  const int TH = halo ? cg::HALO_TH : cg::TM_H, TW = halo ? cg::HALO_TW : cg::TM_W;
+  p.tiles_w = ceil_div(p.Wo, TW);
+  p.tiles_h = ceil_div(p.Ho, TH);
+  p.n_tiles = p.B * p.tiles_w * p.tiles_h;
+  p.d_tiles_prob = FastDiv(p.n_tiles);
+  p.d_tiles_img = FastDiv(p.tiles_w * p.tiles_h);
+  p.d_tiles_w = FastDiv(p.tiles_w);
   PFN_tmapEncodeTiled enc = tmap_encoder();
   HRF_REQUIRE(enc != nullptr, HRF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   ConvGemmMaps tm;
@@ -452,7 +507,8 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
   auto act_map = [&](CUtensorMap* m, const void* ptr, int Cx) -> CUresult {
     const cuuint64_t gdim[4] = {(cuuint64_t)Cx, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)p.B};
     const cuuint64_t gstr[3] = {(cuuint64_t)Cx * 2, (cuuint64_t)Wi * Cx * 2, (cuuint64_t)Hi * Wi * Cx * 2};
-    const cuuint32_t box[4] = {64u, (cuuint32_t)(cg::TM_W * stride), (cuuint32_t)((rr ? cg::TM_H + 2 : cg::TM_H) * stride), 1u};
+    const cuuint32_t box[4] = {64u, (cuuint32_t)(halo ? TW + 2 : TW * stride),
+                               (cuuint32_t)(halo || rr ? TH + 2 : TH * stride), 1u};
     const cuuint32_t est[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, est,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -479,7 +535,7 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
     if (staged) {
       const cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
       const cuuint64_t gstr[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.Wo * p.Cout * 2, (cuuint64_t)p.Ho * p.Wo * p.Cout * 2};
-      const cuuint32_t box[4] = {64u, (cuuint32_t)cg::TM_W, (cuuint32_t)cg::TM_H, 1u};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)TW, (cuuint32_t)TH, 1u};
       const cuuint32_t est[4] = {1u, 1u, 1u, 1u};
       CUresult r = enc(&tm.c[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out[q], gdim, gstr, box, est,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -500,19 +556,24 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
   for (int q = p.n_prob; q < kMaxProb; ++q) { tm.x[q] = tm.x[0]; tm.w[q] = tm.w[0]; tm.c[q] = tm.c[0]; tm.r[q] = tm.r[0]; }
   const int total = p.n_tiles * p.n_prob;
   int grid = total < 148 ? total : 148;
-  if (rr) {
+  if (halo || rr) {
     p.tiles_per_cta = ceil_div(total, grid);
     grid = ceil_div(total, p.tiles_per_cta);
-    const size_t smem = (size_t)p.n_stages * cg::A_RR_BYTES + K::C_BYTES + wres + 1024;
-    HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, true>, smem));
-    HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, true>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+    const size_t smem = (size_t)p.n_stages * res_stage + K::C_BYTES + wres + 1024;
+    if (halo) {
+      HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 2>, smem));
+      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 2>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+    } else {
+      HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 1>, smem));
+      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 1>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+    }
     count_launch();
     HRF_CUDA(cudaGetLastError());
     return HRF_OK;
   }
   p.tiles_per_cta = 0;
-  HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, false>, K::SMEM));
-  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, false>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
+  HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 0>, K::SMEM));
+  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 0>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
