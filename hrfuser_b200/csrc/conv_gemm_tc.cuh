@@ -42,6 +42,17 @@
 //     swizzle atoms) into the box -- so a tile costs 3 x 10 / 8 = 3.75 activation tile loads
 //     per channel chunk instead of 9;
 //   * CTAs walk contiguous tile ranges (neighbouring tiles share halo rows in L2).
+//
+// Halo mode (HALO, the default for those layers; HRF_CONV_HALO=0 falls back to RR).  The M tile is
+// 16 rows x 8 tokens and a K step is one 64-channel chunk: ONE box of 18 rows x 10 tokens feeds all
+// nine taps.  Tap (dy, dx) is that box read through a descriptor that starts (dy * 10 + dx) * 128
+// bytes into it with an 8-row-group stride of 10 * 128 = 1 280 bytes (the box's row pitch).  The
+// tensor core, like TMA, applies the 128-byte-swizzle XOR to absolute shared-memory address bits,
+// so starts and strides that are not multiples of the 1 024-byte atom read the right rows
+// (tools/probes/swz_probe.cu).  1.44 activation tile loads per channel chunk instead of 3.75.
+//
+// Concatenated K (kc_split, 1x1 only): K chunks past kc_split come from a second activation tensor
+// -- Bottleneck conv3 and its downsample conv as one GEMM (hrf_convgemm_grouped_cat_fwd).
 #pragma once
 #include <cuda.h>
 
