@@ -99,7 +99,13 @@ constexpr int TM_H = 8, TM_W = 16;                    // the 128-token M tile
 constexpr int A_BYTES = 128 * 128;                    // 128 tokens x 64 channels bf16
 constexpr int A_RR_BYTES = (TM_H + 2) * TM_W * 128;   // row-reuse box: 10 rows x 16 tokens x 64 channels
 constexpr int MAXST = 8;
-constexpr int NT = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, then `groups` sets of four epilogue warps (one warp
+// per TMEM lane quadrant).  Outputs of 128 / 256 accumulator columns get two sets that take
+// alternate 64-channel sub-tiles: one warp per scheduler has nothing to hide the TMEM-load, shared-
+// memory and barrier latencies of the epilogue behind, and at 256 columns the epilogue -- not HBM
+// -- bounded the kernel (8 100 cycles per tile against 4 300 at the HBM rate).
+__host__ __device__ constexpr int epi_groups(int npad) { return npad >= 128 ? 2 : 1; }
+__host__ __device__ constexpr int nt(int npad) { return 64 + 128 * epi_groups(npad); }
 // halo mode: the M tile is 16 rows x 8 tokens; ONE box of 18 rows x 10 tokens x 64 channels per K
 // chunk feeds all nine taps (tap (dy, dx) starts (dy * 10 + dx) tokens into the box)
 constexpr int HALO_TH = 16, HALO_TW = 8;
@@ -150,7 +156,9 @@ struct ConvGemmCfg {
   static constexpr int B_BYTES = NPAD * 128;
   static constexpr int STAGE = cg::A_BYTES + B_BYTES;
   static constexpr int NSUB = NPAD / 64;                      // 64-channel sub-tiles of the output (0: direct stores)
-  static constexpr int NSLOT = NSUB == 0 ? 0 : (NSUB < 2 ? 2 : NSUB);   // C slots (residual in, result out)
+  // C slots (residual in, result out): at least two per epilogue group -- a group frees a slot
+  // when it issues its NEXT store, so with one slot it would wait for itself
+  static constexpr int NSLOT = NSUB == 0 ? 0 : (NSUB <= 2 ? 2 * NSUB : NSUB);
   static constexpr int C_BYTES = NSLOT * cg::A_BYTES;
   static constexpr int ROOM = 218 * 1024 - C_BYTES;     // 227 KB - static (bias table, barriers) - slack
   static constexpr int STAGES = ROOM / STAGE > 8 ? 8 : ROOM / STAGE;
@@ -162,11 +170,12 @@ struct ConvGemmCfg {
 // MODE 0: plain (activation tile + weight tile per K step); 1: row reuse (RR); 2: halo box (HALO).
 // RR and HALO keep the layer's weights resident and walk contiguous tile ranges.
 template <int NPAD, int MODE>
-__global__ void __launch_bounds__(cg::NT, 1)
+__global__ void __launch_bounds__(cg::nt(NPAD), 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ ConvGemmMaps tm) {
   using namespace umma;
   using K = ConvGemmCfg<NPAD>;
   constexpr bool RR = MODE == 1, HALO = MODE == 2, RES = MODE != 0;
+  constexpr int EG = cg::epi_groups(NPAD);
   constexpr int TH = HALO ? cg::HALO_TH : cg::TM_H, TW = HALO ? cg::HALO_TW : cg::TM_W;   // the 128-token M tile
   const int STAGES = RES ? p.n_stages : K::STAGES;
   constexpr int STAGE_B = RR ? cg::A_RR_BYTES : HALO ? cg::HALO_STAGE : K::STAGE;
@@ -175,7 +184,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   __shared__ __align__(8) uint64_t full[cg::MAXST], empty[cg::MAXST], acc_full[2], acc_empty[2], w_full;
   __shared__ __align__(8) uint64_t c_full[NSLOT], c_empty[NSLOT];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[kMaxProb * NPAD];
+  __shared__ __align__(16) float s_bias[kMaxProb * NPAD];
 
   pdl_launch_dependents();
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
@@ -190,7 +199,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);                    // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], 4 * EG);               // one arrival per epilogue warp
     }
     for (int c = 0; c < NSLOT; ++c) {
       mbar_init(&c_full[c], 1);
@@ -212,7 +221,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   const int t_begin = RES ? blockIdx.x * p.tiles_per_cta : blockIdx.x;
   const int t_step = RES ? 1 : gridDim.x;
   const int t_end = RES ? (t_begin + p.tiles_per_cta < total_tiles ? t_begin + p.tiles_per_cta : total_tiles) : total_tiles;
-  for (int e = tid; e < p.n_prob * NPAD; e += cg::NT) s_bias[e] = __ldg(p.blob[e / NPAD] + (e % NPAD));
+  for (int e = tid; e < p.n_prob * NPAD; e += cg::nt(NPAD)) s_bias[e] = __ldg(p.blob[e / NPAD] + (e % NPAD));
   if (warp == 1) tmem_alloc(&tmem_base_s, K::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -335,9 +344,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
   } else {
     // ===== epilogue warps ==========================================================================
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int eg = (warp - 2) >> 2;                   // epilogue group: sub-tiles j with j % EG == eg
     const int row = q * 32 + lane;                    // token of the tile
     const int hh = row / TW, ww = row % TW;
-    int tcount = 0, cit = 0;
+    int tcount = 0, cit = 0, prev_cit = -1;           // prev_cit: the last slot THIS group stored
+    const bool solo = EG > 1 && NSUB > 0 && staged && p.resid[0] != nullptr;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       const int acc = tcount & 1;
       int pr, tl, b, rem, ty, tx;
@@ -359,6 +370,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
         const bool has_r = resid != nullptr;
 #pragma unroll 1
         for (int j = 0; j < NSUB; ++j, ++cit) {
+          // the other group's sub-tile.  With a residual, group 0 takes them all: the producer
+          // reloads a slot when its store has been issued AND the same group has issued the next
+          // one, and with alternating groups that hand-over put two exposed HBM latencies into
+          // every tile (conv3 + identity 28 -> 37 us); without one, two groups: 23.5 -> 15 us
+          if (EG > 1 && (solo ? eg != 0 : (j & (EG - 1)) != eg)) continue;
           const int cs = cit % NSLOT;
           unsigned char* slot = c_slots + cs * cg::A_BYTES;
           float v[64];
@@ -372,8 +388,11 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
           for (int ch = 0; ch < 8; ++ch) {
             uint4* cp = reinterpret_cast<uint4*>(rowp + ((ch ^ (row & 7)) << 4));
             float a[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 64 + ch * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 64 + ch * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = v[ch * 8 + e] + bias[j * 64 + ch * 8 + e];
+            for (int e = 0; e < 8; ++e) a[e] = v[ch * 8 + e] + bb[e];
             if (has_r) {
               const uint4 r = *cp;
               const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
@@ -394,21 +413,23 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
             *cp = make_uint4(o[0], o[1], o[2], o[3]);
           }
           fence_proxy_async();                                  // generic writes -> the TMA store's reads
-          asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
-          if (warp == 2 && elect_one()) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");   // the four warps of this group
+          if (q == 2 && elect_one()) {                          // warp 2 / warp 6: first warp of the group
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(&tm.c[pr]), "r"(smem_u32(slot)), "r"(j * 64), "r"(tx * TW), "r"(ty * TH), "r"(b)
                          : "memory");
             tma_store_commit();
-            if (cit >= 1) {                                     // the PREVIOUS slot's store has read its data
+            if (prev_cit >= 0) {                                // this group's PREVIOUS store has read its slot
               asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              cg::mbar_arrive(&c_empty[(cit - 1) % NSLOT]);
+              cg::mbar_arrive(&c_empty[prev_cit % NSLOT]);
             }
           }
+          prev_cit = cit;
         }
       } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < NPAD; c0 += 32) {
+        if (EG > 1 && ((c0 >> 5) & (EG - 1)) != eg) continue;
         float v[32];
         tmem_ld32(trow + c0, v);
         tmem_ld_wait();
@@ -462,7 +483,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p, const __grid_const
       __syncwarp();
       if (lane == 0) cg::mbar_arrive(&acc_empty[acc]);
     }
-    if (NSUB > 0 && staged && warp == 2 && elect_one()) tma_store_wait_all();   // same thread that issued them
+    if (NSUB > 0 && staged && q == 2 && elect_one()) tma_store_wait_all();      // same thread that issued them
   }
 
   tc_fence_before();
@@ -573,10 +594,10 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
     const size_t smem = (size_t)p.n_stages * res_stage + K::C_BYTES + wres + 1024;
     if (halo) {
       HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 2>, smem));
-      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 2>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 2>, dim3(grid), dim3(cg::nt(NPAD)), smem, stream, p, tm));
     } else {
       HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 1>, smem));
-      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 1>, dim3(grid), dim3(cg::NT), smem, stream, p, tm));
+      HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 1>, dim3(grid), dim3(cg::nt(NPAD)), smem, stream, p, tm));
     }
     count_launch();
     HRF_CUDA(cudaGetLastError());
@@ -584,7 +605,7 @@ static int launch_conv_gemm_n(ConvGemmParams p, const void* const* xs, const voi
   }
   p.tiles_per_cta = 0;
   HRF_CUDA(ensure_smem((const void*)conv_gemm_tc_kernel<NPAD, 0>, K::SMEM));
-  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 0>, dim3(grid), dim3(cg::NT), K::SMEM, stream, p, tm));
+  HRF_CUDA(launch_pdl(conv_gemm_tc_kernel<NPAD, 0>, dim3(grid), dim3(cg::nt(NPAD)), K::SMEM, stream, p, tm));
   count_launch();
   HRF_CUDA(cudaGetLastError());
   return HRF_OK;
