@@ -24,6 +24,6 @@ with open(sys.argv[2], 'w', newline='') as f:
     for i, r in enumerate(rows[2:]):
         d = dict(zip(hdr, r))
         for k, u in zip(hdr, units):
-            if k in PICK or ('issue_stalled' in k and k.endswith('per_warp_active.pct')):
+            if k in PICK or (k.startswith('smsp__average_warps_issue_stalled') and k.endswith('per_issue_active.ratio')):
                 w.writerow([i, d.get('Kernel Name', '')[:80], k, u, d[k]])
 print(len(rows) - 2, 'launches ->', sys.argv[2])
