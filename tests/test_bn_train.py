@@ -236,6 +236,23 @@ def _sync_worker(rank, world, port, q):
               and torch.allclose(gb, db_ref, rtol=1e-5, atol=1e-4)
               and torch.allclose(run_mean, rm, rtol=1e-5, atol=1e-6)
               and torch.allclose(run_var, rv, rtol=1e-5, atol=1e-6))
+    # the same with the GELU that follows the norm layer fused in: the all-reduced backward sums
+    # are sums of dy * act'(z) over BOTH ranks
+    xg = x[lo:hi].clone().requires_grad_(True)
+    wg, bg = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yg = bn_train._BatchNormTrainFn.apply(xg, wg, bg, None, None, 1e-5, 0.1, group, 2)
+    yg.backward(dy[lo:hi])
+    gw2, gb2 = wg.grad.clone(), bg.grad.clone()
+    dist.all_reduce(gw2)
+    dist.all_reduce(gb2)
+    parts = [None, None]
+    dist.all_gather_object(parts, (yg.detach(), xg.grad))
+    if rank == 0:
+        y_ref, dx_ref, dw_ref, db_ref = _torch_bn_act_reference(x, w, b, dy, 2)
+        ok = (ok and torch.allclose(torch.cat([p[0] for p in parts]), y_ref, rtol=1e-5, atol=1e-5)
+              and torch.allclose(torch.cat([p[1] for p in parts]), dx_ref, rtol=1e-4, atol=1e-5)
+              and torch.allclose(gw2, dw_ref, rtol=1e-5, atol=1e-4)
+              and torch.allclose(gb2, db_ref, rtol=1e-5, atol=1e-4))
         q.put(ok)
     dist.destroy_process_group()
 
