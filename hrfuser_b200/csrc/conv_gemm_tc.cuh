@@ -10,7 +10,8 @@
 //   K loop   taps x (Cin / 64): per step one A tile [128 tokens x 64 channels] and one B tile
 //            [N x 64] in 128-byte-swizzled K-major shared memory, four K = 16 UMMAs
 //
-// Roles (192 threads, one CTA per SM, persistent over the tiles):
+// Roles (192 threads -- 320 for 128 / 256 accumulator columns: a second set of epilogue warps, see cg::epi_groups --
+// one CTA per SM, persistent over the tiles):
 //   warp 0      TMA producer: for every K step one 4-D tensor-tile copy of the activations --
 //               box (64 channels, 16, 8, 1) at (c0, w0 + dx - 1, h0 + dy - 1, b); the unit
 //               zero-fills what lies outside the image, which IS the convolution's zero padding;
