@@ -146,14 +146,7 @@ class _Bottleneck:
         if (d is not None and self.c3.tc and self.down.tc and d.kernel_size == (1, 1) and d.stride == (1, 1) and
                 m.conv3.in_channels % 64 == 0 and d.in_channels % 64 == 0 and
                 os.environ.get('HRF_CONV_CAT', '1') != '0'):
-            w3, b3 = _fold_conv_bn(m.conv3, m.bn3, torch.float32)
-            wd, bd = _fold_conv_bn(d, m.downsample[1], torch.float32)
-            both = nn.Conv2d(m.conv3.in_channels + d.in_channels, m.conv3.out_channels, 1, bias=True)
-            with torch.no_grad():
-                both.weight.copy_(torch.cat([w3, wd], 1))
-                both.bias.copy_(b3 + bd)
-            both = both.to(m.conv3.weight.device)
-            self.cat = _Conv(both, None, True, dtype, engine=engine)
+            self.cat = _Conv(fold_conv3_downsample(m), None, True, dtype, engine=engine)
             self.cat.cin1 = m.conv3.in_channels
 
     def __call__(self, x):
@@ -161,6 +154,20 @@ class _Bottleneck:
             return run_cat([self.cat], [self.c2(self.c1(x))], [x])[0]
         idt = x if self.down is None else self.down(x)
         return self.c3(self.c2(self.c1(x)), residual=idt)
+
+
+def fold_conv3_downsample(m):
+    """Bottleneck `bn3(conv3(y)) + bn_d(downsample(x))` (reference resnet.py:287-300, eval-mode BN) as
+    ONE 1x1 convolution of the channel concatenation [y | x]: weights [W3 * s3 | Wd * sd], bias
+    b3 + bd."""
+    d, bnd = m.downsample[0], m.downsample[1]
+    w3, b3 = _fold_conv_bn(m.conv3, m.bn3, torch.float32)
+    wd, bd = _fold_conv_bn(d, bnd, torch.float32)
+    both = nn.Conv2d(m.conv3.in_channels + d.in_channels, m.conv3.out_channels, 1, bias=True)
+    with torch.no_grad():
+        both.weight.copy_(torch.cat([w3, wd], 1))
+        both.bias.copy_(b3 + bd)
+    return both.to(m.conv3.weight.device)
 
 
 def run_cat(convs, ys, xs):

@@ -182,3 +182,25 @@ def test_backbone_engine_is_dropped_by_parent_load():
     parent.backbone = net
     parent.load_state_dict(parent.state_dict())
     assert net._engine is None and net._graphs == {}
+
+
+def test_bottleneck_conv3_downsample_fold_into_one_conv():
+    """the algebra behind hrf_convgemm_grouped_cat_fwd: relu(bn3(conv3(y)) + bn_d(downsample(x)))
+    (reference resnet.py:287-300) == relu(conv_both(cat[y, x])) with the engine's folded weights"""
+    from hrfuser_b200.engine import fold_conv3_downsample
+    from hrfuser_b200.modules import make_bottleneck_layer
+    torch.manual_seed(3)
+    layer = make_bottleneck_layer(64, 64, 2, dict(type='BN'))
+    randomize_parameters(layer, 9)
+    layer.eval()
+    m = layer[0]
+    assert m.downsample is not None and layer[1].downsample is None
+    both = fold_conv3_downsample(m)
+    assert both.in_channels == m.conv3.in_channels + m.downsample[0].in_channels
+    x = torch.randn(2, 64, 9, 11)
+    with torch.no_grad():
+        y = m.relu(m.bn2(m.conv2(m.relu(m.bn1(m.conv1(x))))))
+        ref = m.relu(m.bn3(m.conv3(y)) + m.downsample(x))
+        got = torch.relu(both(torch.cat([y, x], 1)))
+        assert rel_err(got, ref) < 1e-6
+        assert rel_err(ref, m(x)) < 1e-6
